@@ -1,0 +1,260 @@
+// Flash-style masked attention for the CFM estimator (CausalConditionalDecoder transformer blocks:
+// 8 heads x 64, softmax(q k^T / 8 + mask) v).  The mask is never materialised: it is generated from
+// integers (valid length per sequence; optional block-causal chunk) inside the kernel.
+//
+// One CTA = 128 query rows of one (sequence, head).  warp 0: TMA producer (Q once, K/V tiles through a
+// 3-stage ring), warp 1: tcgen05.mma issuer (S = Q K^T into a double-buffered TMEM tile, O += P V),
+// warps 2-5: online softmax, thread-per-row, P written 16-bit into 128B-swizzled smem as the A operand
+// of the PV MMA; O accumulates in TMEM and is rescaled in place when the running max moves.
+#include "attention.cuh"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace cv2 {
+
+static constexpr int kQBytes = 128 * 64 * 2;   // 16 KB
+static constexpr int kKBytes = 128 * 64 * 2;   // 128 keys x 64 d
+static constexpr int kVBytes = 2 * 64 * 64 * 2;  // two [64 d x 64 keys] boxes
+static constexpr int kKVStages = 3;
+static constexpr int kPBytes = 2 * 128 * 64 * 2;  // 128 rows x 128 keys, two K-atoms
+static constexpr int kOffK = kQBytes;
+static constexpr int kOffV = kOffK + kKVStages * kKBytes;
+static constexpr int kOffP = kOffV + kKVStages * kVBytes;
+static constexpr int kOffBar = kOffP + kPBytes;
+static constexpr int kAttnSmem = kOffBar + 256 + 1024;
+
+static constexpr uint32_t kTmemS0 = 0, kTmemS1 = 128, kTmemO = 256;  // column offsets (512 allocated)
+
+__global__ void __launch_bounds__(192, 1)
+flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  const int t0 = blockIdx.x * 128;
+  const int h = blockIdx.y;
+  const int s = blockIdx.z;
+  const int len = p.lens ? p.lens[s] : p.len_all;
+  if (t0 >= len + p.halo) return;
+  const int sh = s * p.heads + h;
+  // number of key tiles this query tile can see
+  int kv_end = len;
+  if (p.chunk > 0) kv_end = min(len, ((t0 + 127) / p.chunk + 1) * p.chunk);
+  const int nkt = (kv_end + 127) / 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* q_full = bars;              // 1
+  uint64_t* kv_full = bars + 1;         // 3  (K and V of a stage land on the same barrier)
+  uint64_t* kv_empty = bars + 4;        // 3
+  uint64_t* s_full = bars + 7;          // 2
+  uint64_t* p_full = bars + 9;          // 1 (128 arrivals)
+  uint64_t* pv_done = bars + 10;        // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kKVStages; i++) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kQBytes);
+      tma_load_3d(smem, &tmQ, q_full, 0, t0, sh);
+      for (int j = 0; j < nkt; j++) {
+        const int st = j % kKVStages;
+        const uint32_t ph = (j / kKVStages) & 1;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_expect_tx(&kv_full[st], kKBytes + kVBytes);
+        tma_load_3d(smem + kOffK + st * kKBytes, &tmK, &kv_full[st], 0, j * 128, sh);
+        tma_load_3d(smem + kOffV + st * kVBytes, &tmV, &kv_full[st], j * 128, 0, sh);
+        tma_load_3d(smem + kOffV + st * kVBytes + 8192, &tmV, &kv_full[st], j * 128 + 64, 0, sh);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0);
+      constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0);
+      const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(smem));
+      const uint32_t p_addr = smem_u32(smem + kOffP);
+      auto issue_s = [&](int j) {
+        const int st = j % kKVStages;
+        mbar_wait(&kv_full[st], (j / kKVStages) & 1);
+        tc_fence_after();
+        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(smem + kOffK + st * kKBytes));
+        const uint32_t d = tmem_base + ((j & 1) ? kTmemS1 : kTmemS0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) umma_f16(d, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nkt; j++) {
+        // S buffer (j+1)&1 was last read by softmax j-1, whose p_full arrival we consumed in iteration j-1
+        if (j + 1 < nkt) issue_s(j + 1);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const int st = j % kKVStages;
+        const uint32_t v_addr = smem_u32(smem + kOffV + st * kVBytes);
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+          const uint64_t pa = umma_smem_desc_sw128(p_addr + a * 16384);
+          const uint64_t vb = umma_smem_desc_sw128(v_addr + a * 8192);
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            umma_f16(tmem_base + kTmemO, pa + (uint64_t)(k * 2), vb + (uint64_t)(k * 2), idesc_o, (j | a | k) != 0);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int t = t0 + r;
+    int kv_lim = len;
+    if (p.chunk > 0) kv_lim = min(len, (t / p.chunk + 1) * p.chunk);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float LOG2E = 1.4426950408889634f;
+    float m = -INFINITY, l = 0.f;
+    uint32_t raw[32];
+    uint8_t* prow = smem + kOffP + r * 128;
+    for (int j = 0; j < nkt; j++) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_addr = lane_addr + ((j & 1) ? kTmemS1 : kTmemS0);
+      const int kbase = j * 128;
+      // pass A: row max over the visible keys of this tile
+      float mx = -INFINITY;
+      for (int c = 0; c < 4; c++) {
+        tmem_ld32(s_addr + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++)
+          if (kbase + c * 32 + i < kv_lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = (m == -INFINITY) ? 0.f : exp2f((m - m_new) * LOG2E);
+      // PV of the previous tile must be complete before O is rescaled or P overwritten
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+          for (int c = 0; c < 2; c++) {
+            tmem_ld32(lane_addr + kTmemO + c * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i++) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
+            tmem_st32(lane_addr + kTmemO + c * 32, raw);
+          }
+          tmem_st_wait();
+        }
+      }
+      l *= alpha;
+      // pass B: probabilities -> 16-bit P tile in the swizzled K-major layout
+      const float mscaled = (m_new == -INFINITY) ? 0.f : m_new * LOG2E;
+      for (int c = 0; c < 4; c++) {
+        tmem_ld32(s_addr + c * 32, raw);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const float e = (kbase + c * 32 + i < kv_lim) ? exp2f(__uint_as_float(raw[i]) * LOG2E - mscaled) : 0.f;
+          pv[i] = e;
+          l += e;
+        }
+        uint8_t* atom = prow + (c >> 1) * 16384;
+        const int g0 = (c & 1) * 4;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          __half2 h0 = __floats2half2_rn(pv[g * 8 + 0], pv[g * 8 + 1]);
+          __half2 h1 = __floats2half2_rn(pv[g * 8 + 2], pv[g * 8 + 3]);
+          __half2 h2 = __floats2half2_rn(pv[g * 8 + 4], pv[g * 8 + 5]);
+          __half2 h3 = __floats2half2_rn(pv[g * 8 + 6], pv[g * 8 + 7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0);
+          u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2);
+          u.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(atom + (((g0 + g) ^ (r & 7)) << 4)) = u;
+        }
+      }
+      m = m_new;
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // final: O / l -> 16-bit [S, T_alloc, heads*64]
+    mbar_wait(pv_done, (nkt - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    __half* dst = p.out + ((long long)s * p.T_alloc + t) * (p.heads * 64) + h * 64;
+    const bool valid = t < len;
+    for (int c = 0; c < 2; c++) {
+      tmem_ld32(lane_addr + kTmemO + c * 32, raw);
+      tmem_ld_wait();
+      uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) f[e] = valid ? __uint_as_float(raw[i * 8 + e]) * inv : 0.f;
+        __half2 h0 = __floats2half2_rn(f[0], f[1]);
+        __half2 h1 = __floats2half2_rn(f[2], f[3]);
+        __half2 h2 = __floats2half2_rn(f[4], f[5]);
+        __half2 h3 = __floats2half2_rn(f[6], f[7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2);
+        u.w = *reinterpret_cast<uint32_t*>(&h3);
+        d4[i] = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+void launch_flash_attn(const AttnParams& p, cudaStream_t stream) {
+  CV2_CHECK(p.T_alloc % 128 == 0, "attention: T_alloc %d not a multiple of 128", p.T_alloc);
+  static bool configured = false;
+  if (!configured) {
+    CV2_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    configured = true;
+  }
+  const uint64_t SH = (uint64_t)p.S * p.heads;
+  uint64_t dq[3] = {64, (uint64_t)p.T_alloc, SH};
+  uint64_t sq[2] = {128, (uint64_t)p.T_alloc * 128};
+  uint32_t bq[3] = {64, 128, 1};
+  CUtensorMap tmQ = make_tmap_16b(p.q, 3, dq, sq, bq);
+  CUtensorMap tmK = make_tmap_16b(p.k, 3, dq, sq, bq);
+  uint64_t dv[3] = {(uint64_t)p.T_alloc, 64, SH};
+  uint64_t sv[2] = {(uint64_t)p.T_alloc * 2, (uint64_t)p.T_alloc * 128};
+  uint32_t bv[3] = {64, 64, 1};
+  CUtensorMap tmV = make_tmap_16b(p.vt, 3, dv, sv, bv);
+  dim3 grid(p.T_alloc / 128, p.heads, p.S);
+  flash_attn_kernel<<<grid, 192, kAttnSmem, stream>>>(tmQ, tmK, tmV, p);
+  CV2_LAUNCH_CHECK();
+}
+
+}  // namespace cv2

@@ -1,0 +1,286 @@
+// extern "C" surface of libcv2eu_b200.so (declared in include/cv2eu_b200.h).
+#include "../../include/cv2eu_b200.h"
+
+#include "attention.cuh"
+#include "engine.h"
+#include "flow_kernels.cuh"
+#include "hift_kernels.cuh"
+
+using namespace cv2;
+
+struct cv2_engine {
+  Engine e;
+};
+
+#define CV2_API_BEGIN try {
+#define CV2_API_END                                \
+  }                                                \
+  catch (const std::exception& ex) {               \
+    last_error_ref() = ex.what();                  \
+    return 1;                                      \
+  }                                                \
+  catch (...) {                                    \
+    last_error_ref() = "unknown error";            \
+    return 1;                                      \
+  }                                                \
+  return 0;
+
+static void require_sm100(int device) {
+  cudaDeviceProp prop;
+  CV2_CUDA(cudaGetDeviceProperties(&prop, device));
+  CV2_CHECK(prop.major == 10, "cv2eu_b200 needs an sm_100-class GPU (B200); device %d is sm_%d%d -- there is no fallback path",
+            device, prop.major, prop.minor);
+}
+
+extern "C" {
+
+const char* cv2_last_error(void) { return last_error_ref().c_str(); }
+int cv2_version(void) { return 1; }
+
+int cv2_engine_create(cv2_engine** out, int device) {
+  CV2_API_BEGIN
+  CV2_CHECK(out != nullptr, "null out");
+  int n = 0;
+  cudaError_t err = cudaGetDeviceCount(&n);
+  CV2_CHECK(err == cudaSuccess && n > 0, "no CUDA device available (%s) -- cv2eu_b200 has no CPU fallback",
+            cudaGetErrorString(err));
+  CV2_CUDA(cudaSetDevice(device));
+  require_sm100(device);
+  hift_init_tables();
+  cv2_engine* h = new cv2_engine();
+  h->e.device = device;
+  *out = h;
+  CV2_API_END
+}
+
+void cv2_engine_destroy(cv2_engine* e) { delete e; }
+
+int cv2_engine_set_tensor(cv2_engine* h, const char* name, const void* dptr, int dtype, int ndim, const int64_t* shape) {
+  CV2_API_BEGIN
+  CV2_CHECK(h && name && dptr, "null argument");
+  TensorRef t;
+  t.ptr = dptr;
+  t.dtype = dtype;
+  t.shape.assign(shape, shape + ndim);
+  h->e.tensors[name] = t;
+  h->e.weights.erase(std::string(name).substr(0, std::string(name).rfind('.')));
+  CV2_API_END
+}
+
+int cv2_engine_finalize(cv2_engine* h, int need_flow, int need_hift) {
+  CV2_API_BEGIN
+  CV2_CHECK(h, "null engine");
+  Engine& e = h->e;
+  // A dry run of each forward touches every tensor it needs and reports the first missing name.
+  if (need_flow) {
+    Arena ws;
+    FlowArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = 1; a.max_tok_total = 64; a.n_steps = 1; a.finalize = 1;
+    flow_forward(e, nullptr, a, ws);
+    e.has_flow = true;
+  }
+  if (need_hift) {
+    Arena ws;
+    HiftArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = 1; a.mel_T = 16;
+    hift_forward(e, nullptr, a, ws);
+    e.has_hift = true;
+  }
+  e.finalized = true;
+  CV2_API_END
+}
+
+long long cv2_engine_last_launches(cv2_engine* h) { return h ? h->e.launches : -1; }
+
+size_t cv2_estimator_workspace_bytes(cv2_engine* h, int B2, int T) {
+  try {
+    Arena ws;
+    EstArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B2 = B2; a.T = T;
+    return estimator_forward(h->e, nullptr, a, ws) + 4096;
+  } catch (const std::exception& ex) {
+    last_error_ref() = ex.what();
+    return 0;
+  }
+}
+
+int cv2_estimator_forward(cv2_engine* h, void* stream, const float* x, const float* mask, const float* mu, const float* t,
+                          const float* spks, const float* cond, float* out, int B2, int T, int streaming, void* workspace,
+                          size_t workspace_bytes) {
+  CV2_API_BEGIN
+  CV2_CHECK(h && h->e.has_flow, "engine not finalized for flow");
+  CV2_CHECK(x && mask && mu && t && spks && cond && out && workspace, "null argument");
+  Arena ws;
+  ws.base = static_cast<uint8_t*>(workspace);
+  ws.cap = workspace_bytes;
+  EstArgs a{x, mask, mu, t, spks, cond, out, B2, T, streaming};
+  h->e.launches = 0;
+  estimator_forward(h->e, (cudaStream_t)stream, a, ws);
+  CV2_API_END
+}
+
+size_t cv2_flow_workspace_bytes(cv2_engine* h, int B, int max_tok_total, int n_steps) {
+  try {
+    Arena ws;
+    FlowArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.max_tok_total = max_tok_total; a.n_steps = n_steps; a.finalize = 1;
+    return flow_forward(h->e, nullptr, a, ws) + 4096;
+  } catch (const std::exception& ex) {
+    last_error_ref() = ex.what();
+    return 0;
+  }
+}
+
+int cv2_flow_forward(cv2_engine* h, void* stream, const int32_t* token, int token_stride, const int32_t* token_len,
+                     const int32_t* prompt_token, int prompt_stride, const int32_t* prompt_len, const float* prompt_feat,
+                     long long prompt_feat_bstride, const int32_t* prompt_feat_len, const float* embedding,
+                     const float* rand_noise, int noise_stride, int B, int max_tok_total, int streaming, int finalize,
+                     const float* t_steps_dev, const float* dt_steps_host, int n_steps, float cfg_rate, float* mel_out,
+                     int mel_out_T, float* mu_out, float* enc_out, void* workspace, size_t workspace_bytes) {
+  CV2_API_BEGIN
+  CV2_CHECK(h && h->e.has_flow, "engine not finalized for flow");
+  CV2_CHECK(token && token_len && prompt_token && prompt_len && prompt_feat && prompt_feat_len && embedding && rand_noise &&
+                t_steps_dev && dt_steps_host && mel_out && workspace,
+            "null argument");
+  CV2_CHECK(B >= 1 && max_tok_total >= 4 && n_steps >= 1, "bad sizes B=%d max_tok_total=%d n_steps=%d", B, max_tok_total, n_steps);
+  CV2_CHECK(2 * max_tok_total <= noise_stride, "sequence of %d mel frames exceeds the CFM noise buffer (%d)", 2 * max_tok_total,
+            noise_stride);
+  Arena ws;
+  ws.base = static_cast<uint8_t*>(workspace);
+  ws.cap = workspace_bytes;
+  FlowArgs a;
+  memset(&a, 0, sizeof(a));
+  a.token = token; a.token_stride = token_stride; a.token_len = token_len;
+  a.prompt_token = prompt_token; a.prompt_stride = prompt_stride; a.prompt_len = prompt_len;
+  a.prompt_feat = prompt_feat; a.prompt_feat_bstride = prompt_feat_bstride; a.prompt_feat_len = prompt_feat_len;
+  a.embedding = embedding; a.rand_noise = rand_noise; a.noise_stride = noise_stride;
+  a.B = B; a.max_tok_total = max_tok_total; a.streaming = streaming; a.finalize = finalize;
+  a.t_steps = t_steps_dev; a.dt_steps = dt_steps_host; a.n_steps = n_steps; a.cfg = cfg_rate;
+  a.mel_out = mel_out; a.mel_out_T = mel_out_T; a.mu_out = mu_out; a.enc_out = enc_out;
+  h->e.launches = 0;
+  flow_forward(h->e, (cudaStream_t)stream, a, ws);
+  CV2_API_END
+}
+
+size_t cv2_hift_workspace_bytes(cv2_engine* h, int B, int mel_T) {
+  try {
+    Arena ws;
+    HiftArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.mel_T = mel_T;
+    return hift_forward(h->e, nullptr, a, ws) + 4096;
+  } catch (const std::exception& ex) {
+    last_error_ref() = ex.what();
+    return 0;
+  }
+}
+
+int cv2_hift_forward(cv2_engine* h, void* stream, const float* mel, int mel_T, const int32_t* lens, const float* cache_source,
+                     int cache_len, const float* noise, unsigned long long seed, float* speech, float* source, float* f0_out,
+                     int B, void* workspace, size_t workspace_bytes) {
+  CV2_API_BEGIN
+  CV2_CHECK(h && h->e.has_hift, "engine not finalized for hift");
+  CV2_CHECK(mel && speech && source && workspace, "null argument");
+  CV2_CHECK(B >= 1 && mel_T >= 1, "bad sizes");
+  Arena ws;
+  ws.base = static_cast<uint8_t*>(workspace);
+  ws.cap = workspace_bytes;
+  HiftArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mel = mel; a.mel_T = mel_T; a.lens = lens; a.cache_source = cache_source; a.cache_len = cache_source ? cache_len : 0;
+  a.noise = noise; a.seed = seed; a.speech = speech; a.source = source; a.f0_out = f0_out; a.B = B;
+  h->e.launches = 0;
+  hift_forward(h->e, (cudaStream_t)stream, a, ws);
+  CV2_API_END
+}
+
+int cv2_crossfade(void* stream, float* speech, const float* old_tail, const double* window, int n) {
+  CV2_API_BEGIN
+  launch_crossfade(speech, old_tail, window, n, (cudaStream_t)stream);
+  CV2_API_END
+}
+
+int cv2_op_gemm_tap(void* stream, const void* A, int S, int T_alloc, int Kc, long long ldA, const void* W, int N, int Ktot,
+                    const float* bias, int bn, int ntaps, const int* tap_off_host, const int32_t* lens, int len_all,
+                    const float* ln_g, const float* ln_b, float ln_eps, int act, float act_f, const float* act_a,
+                    const float* rowvec, int rowvec_ld, int mask_pre_res, const float* res, float out_scale, float* out32,
+                    int out32_accum, void* out16, const float* ln2_g, const float* ln2_b, void* out16_ln) {
+  CV2_API_BEGIN
+  Engine e;
+  Weight w;
+  w.w = static_cast<const __half*>(W);
+  w.b = bias;
+  w.N = N;
+  w.Ktot = Ktot;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.lens = lens; p.len_all = len_all; p.halo = 32;
+  p.ln = ln_g != nullptr; p.ln_g = ln_g; p.ln_b = ln_b; p.ln_eps = ln_eps;
+  p.act = act; p.act_f = act_f; p.act_a = act_a;
+  p.rowvec = rowvec; p.rowvec_ld = rowvec_ld;
+  p.mask_pre_res = mask_pre_res;
+  p.res = res; p.res_ld = N;
+  p.out_scale = out_scale;
+  p.out32 = out32; p.out32_ld = N; p.out32_accum = out32_accum;
+  int ne = 0;
+  if (out16) {
+    p.emit[ne].kind = EMIT_PLAIN; p.emit[ne].ptr = static_cast<__half*>(out16); p.emit[ne].ld = N; p.emit[ne].scale = 1.f;
+    ne++;
+  }
+  if (out16_ln) {
+    p.emit[ne].kind = EMIT_LN; p.emit[ne].ptr = static_cast<__half*>(out16_ln); p.emit[ne].ld = N; p.emit[ne].a = ln2_g;
+    p.emit[ne].b = ln2_b; p.emit[ne].f = 1e-5f; p.emit[ne].scale = 1.f;
+    ne++;
+  }
+  e.gemm((cudaStream_t)stream, static_cast<const __half*>(A), S, T_alloc, Kc, ldA, w, bn, ntaps, tap_off_host, p, false);
+  CV2_API_END
+}
+
+int cv2_op_flash_attn(void* stream, const void* q, const void* k, const void* vt, void* out, const int32_t* lens, int len_all,
+                      int S, int heads, int T_alloc, int chunk) {
+  CV2_API_BEGIN
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = static_cast<const __half*>(q); p.k = static_cast<const __half*>(k); p.vt = static_cast<const __half*>(vt);
+  p.out = static_cast<__half*>(out); p.lens = lens; p.len_all = len_all; p.S = S; p.heads = heads; p.T_alloc = T_alloc;
+  p.chunk = chunk; p.halo = 32;
+  launch_flash_attn(p, (cudaStream_t)stream);
+  CV2_API_END
+}
+
+int cv2_op_rel_attn(void* stream, const float* qkv, const float* pos, const float* bias_u, const float* bias_v, void* out,
+                    const int32_t* lens, int len_all, int S, int T_alloc, int Tmax, int chunk) {
+  CV2_API_BEGIN
+  RelAttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.qkv = qkv; p.pos = pos; p.bias_u = bias_u; p.bias_v = bias_v; p.out = static_cast<__half*>(out); p.lens = lens;
+  p.len_all = len_all; p.S = S; p.T_alloc = T_alloc; p.Tmax = Tmax; p.chunk = chunk;
+  launch_rel_attn(p, (cudaStream_t)stream);
+  CV2_API_END
+}
+
+int cv2_op_source_stft(void* stream, const float* src, int mel_T, const int32_t* lens, float* out, int F_alloc, int B) {
+  CV2_API_BEGIN
+  launch_source_stft(src, (long long)480 * mel_T, lens, mel_T, out, F_alloc, B, (cudaStream_t)stream);
+  CV2_API_END
+}
+
+int cv2_op_istft(void* stream, const float* cp, int F_alloc, const int32_t* lens, int mel_T, float* wav, int B) {
+  CV2_API_BEGIN
+  launch_istft(cp, F_alloc, 18, lens, mel_T, wav, (long long)480 * mel_T, B, mel_T, (cudaStream_t)stream);
+  CV2_API_END
+}
+
+int cv2_op_nsf_source(void* stream, const float* f0, int mel_T, const int32_t* lens, const float* noise, unsigned long long seed,
+                      const float* lw, const float* lb, float* phase_ws, float* src, int B) {
+  CV2_API_BEGIN
+  launch_nsf_source(f0, mel_T, phase_ws, mel_T, lens, mel_T, noise, (long long)480 * mel_T * 9, seed, lw, lb, nullptr, 0, 0, src,
+                    (long long)480 * mel_T, B, mel_T, (cudaStream_t)stream);
+  CV2_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+// Host-side engine: owns nothing on the device.  Weights are registered by name as raw device pointers
+// (torch-owned), activations live in a caller-provided workspace carved by a bump allocator, and every
+// forward is a pure sequence of kernel launches on the caller's stream (CUDA-graph capturable, no host sync).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "gemm_tap.cuh"
+#include "host_util.h"
+
+namespace cv2 {
+
+enum DType { DT_F32 = 0, DT_F16 = 1, DT_I32 = 2 };
+
+struct TensorRef {
+  const void* ptr = nullptr;
+  int dtype = 0;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto d : shape) n *= d;
+    return n;
+  }
+};
+
+// Bump allocator over the caller's workspace.  With base == nullptr it only measures.
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  void* alloc(size_t bytes) {
+    off = (off + 255) & ~size_t(255);
+    size_t o = off;
+    off += bytes;
+    if (off > peak) peak = off;
+    if (base && off > cap) fail("workspace too small: need > %zu bytes, have %zu", off, cap);
+    return base ? base + o : reinterpret_cast<void*>(uintptr_t(256) + o);  // fake non-null pointers when measuring
+  }
+  template <class T>
+  T* get(size_t n) { return reinterpret_cast<T*>(alloc(n * sizeof(T))); }
+  bool measuring() const { return base == nullptr; }
+};
+
+// A 16-bit weight matrix [N, Ktot] prepared for the tap GEMM (+ fp32 bias).
+struct Weight {
+  const __half* w = nullptr;
+  const float* b = nullptr;
+  int N = 0, Ktot = 0;
+  CUtensorMap map[3];       // per BN in {64,128,256}
+  bool map_ok[3] = {false, false, false};
+};
+
+struct LN {
+  const float* g = nullptr;
+  const float* b = nullptr;
+};
+
+struct Engine {
+  int device = 0;
+  std::unordered_map<std::string, TensorRef> tensors;
+  bool finalized = false;
+  bool has_flow = false, has_hift = false;
+  std::unordered_map<std::string, Weight> weights;      // lazily built from tensors
+  std::unordered_map<uint64_t, CUtensorMap> amap_cache;  // activation tensor maps
+  long long launches = 0;                                // kernels launched by the last forward (claims for bench)
+
+  const TensorRef& T(const std::string& name) const {
+    auto it = tensors.find(name);
+    if (it == tensors.end()) fail("engine: tensor '%s' was not registered", name.c_str());
+    return it->second;
+  }
+  const float* f32(const std::string& name) const {
+    const TensorRef& t = T(name);
+    if (t.dtype != DT_F32) fail("engine: tensor '%s' must be fp32", name.c_str());
+    return static_cast<const float*>(t.ptr);
+  }
+  Weight& W(const std::string& name);   // expects '<name>.w' (fp16 2-D) and optional '<name>.b'
+  LN ln(const std::string& name) const { return LN{f32(name + "_g"), f32(name + "_b")}; }
+
+  // ---- tap GEMM front-end ------------------------------------------------------------------------
+  // A: 16-bit [S, T_alloc, ld] (first Kc columns used).  Remaining epilogue fields come in through `p`.
+  void gemm(cudaStream_t st, const __half* A, int S, int T_alloc, int Kc, long long ldA, Weight& w, int bn, int ntaps,
+            const int* tap_off, GemmParams p, bool dry);
+};
+
+// forward passes (engine_flow.cu / engine_hift.cu)
+struct FlowArgs {
+  const int* token; int token_stride; const int* token_len;
+  const int* prompt_token; int prompt_stride; const int* prompt_len;
+  const float* prompt_feat; long long prompt_feat_bstride; const int* prompt_feat_len;
+  const float* embedding;       // [B,192]
+  const float* rand_noise;      // [80, noise_stride]
+  int noise_stride;
+  int B;
+  int max_tok_total;            // host-known max over b of prompt_len + token_len
+  int streaming, finalize;
+  const float* t_steps;         // host [n_steps]
+  const float* dt_steps;        // host [n_steps]
+  int n_steps;
+  float cfg;
+  float* mel_out;               // [B, 80, mel_out_T] NCT; frames after the prompt; zero padded
+  int mel_out_T;
+  float* mu_out;                // optional [B, 80, 2*T] (debug / tests) or null
+  float* enc_out;               // optional [B, 2*T_enc_alloc... see capi] or null
+};
+size_t flow_forward(Engine& e, cudaStream_t st, const FlowArgs& a, Arena& ws);
+
+struct EstArgs {
+  const float* x; const float* mask; const float* mu; const float* t; const float* spks; const float* cond;
+  float* out;
+  int B2, T, streaming;
+};
+size_t estimator_forward(Engine& e, cudaStream_t st, const EstArgs& a, Arena& ws);
+
+struct HiftArgs {
+  const float* mel;            // [B, 80, mel_T] NCT fp32
+  int mel_T;                   // stride / max frames
+  const int* lens;             // device [B] valid frames, or null (all mel_T)
+  const float* cache_source;   // [B, 1, cache_len] or null
+  int cache_len;
+  const float* noise;          // [B, 480*mel_T, 9] or null (-> in-kernel generator with `seed`)
+  unsigned long long seed;
+  float* speech;               // [B, 480*mel_T]
+  float* source;               // [B, 1, 480*mel_T]
+  float* f0_out;               // optional [B, mel_T]
+  int B;
+};
+size_t hift_forward(Engine& e, cudaStream_t st, const HiftArgs& a, Arena& ws);
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace cv2

@@ -1,0 +1,66 @@
+// Engine plumbing shared by the flow and HiFT forwards: weight lookup, tensor-map caches, GEMM front-end.
+#include "engine.h"
+
+namespace cv2 {
+
+Weight& Engine::W(const std::string& name) {
+  auto it = weights.find(name);
+  if (it != weights.end()) return it->second;
+  const TensorRef& t = T(name + ".w");
+  if (t.dtype != DT_F16 || t.shape.size() != 2) fail("engine: weight '%s.w' must be 16-bit 2-D", name.c_str());
+  Weight w;
+  w.w = static_cast<const __half*>(t.ptr);
+  w.N = (int)t.shape[0];
+  w.Ktot = (int)t.shape[1];
+  if (w.Ktot % 64 != 0) fail("engine: weight '%s.w' K=%d is not a multiple of 64", name.c_str(), w.Ktot);
+  auto bi = tensors.find(name + ".b");
+  if (bi != tensors.end()) {
+    if (bi->second.dtype != DT_F32 || bi->second.numel() != w.N) fail("engine: bias '%s.b' must be fp32 [%d]", name.c_str(), w.N);
+    w.b = static_cast<const float*>(bi->second.ptr);
+  }
+  return weights.emplace(name, w).first->second;
+}
+
+static inline uint64_t mix(uint64_t h, uint64_t v) {
+  h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+  return h;
+}
+
+void Engine::gemm(cudaStream_t st, const __half* A, int S, int T_alloc, int Kc, long long ldA, Weight& w, int bn, int ntaps,
+                  const int* tap_off, GemmParams p, bool dry) {
+  const int kb = (Kc + 63) / 64;
+  CV2_CHECK(w.Ktot == ntaps * kb * 64, "gemm: weight K=%d does not match taps=%d x Kc_pad=%d", w.Ktot, ntaps, kb * 64);
+  CV2_CHECK(bn == 64 || bn == 128 || bn == 256, "gemm: bad BN %d", bn);
+  p.S = S;
+  p.T_alloc = T_alloc;
+  p.N = w.N;
+  p.kb_per_tap = kb;
+  p.ntaps = ntaps;
+  for (int i = 0; i < ntaps; i++) p.tap_off[i] = tap_off[i];
+  if (!p.bias) p.bias = w.b;
+  if (p.out_scale == 0.f) p.out_scale = 1.f;
+  for (int e = 0; e < 3; e++)
+    if (p.emit[e].kind != EMIT_NONE && p.emit[e].scale == 0.f) p.emit[e].scale = 1.f;
+  launches++;
+  if (dry) return;
+  const int bi = bn == 64 ? 0 : (bn == 128 ? 1 : 2);
+  if (!w.map_ok[bi]) {
+    uint64_t dims[2] = {(uint64_t)w.Ktot, (uint64_t)w.N};
+    uint64_t strides[1] = {(uint64_t)w.Ktot * 2};
+    uint32_t box[2] = {64, (uint32_t)bn};
+    w.map[bi] = make_tmap_16b(w.w, 2, dims, strides, box);
+    w.map_ok[bi] = true;
+  }
+  uint64_t key = mix(mix(mix(mix(mix(0x1234, (uint64_t)(uintptr_t)A), (uint64_t)Kc), (uint64_t)ldA), (uint64_t)T_alloc), (uint64_t)S);
+  auto it = amap_cache.find(key);
+  if (it == amap_cache.end()) {
+    uint64_t dims[3] = {(uint64_t)Kc, (uint64_t)T_alloc, (uint64_t)S};
+    uint64_t strides[2] = {(uint64_t)ldA * 2, (uint64_t)T_alloc * (uint64_t)ldA * 2};
+    uint32_t box[3] = {64, 128, 1};
+    if (amap_cache.size() > 8192) amap_cache.clear();
+    it = amap_cache.emplace(key, make_tmap_16b(A, 3, dims, strides, box)).first;
+  }
+  launch_gemm_tap(bn, it->second, w.map[bi], p, st);
+}
+
+}  // namespace cv2

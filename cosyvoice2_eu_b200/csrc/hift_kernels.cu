@@ -1,0 +1,401 @@
+// HiFT vocoder kernels that are not tensor-core contractions (reference: cosyvoice/hifigan/generator.py,
+// f0_predictor.py).  The F0 predictor stays fp32 (its output drives a chaotic phase integrator);
+// NSF source, source STFT and the iSTFT head are bandwidth-bound fp32 kernels.
+#include "hift_kernels.cuh"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace cv2 {
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 conv1d k=3 pad=1 + ELU, channels-last (ConvRNNF0Predictor.condnet, f0_predictor.py:31-52).
+// Classic 64x64 register-tiled SGEMM over K = 3*Cin; rows beyond len read as 0 (tensor-edge semantics).
+// w: [3][Cin][Cout] (Cout contiguous), weight-norm folded on the host.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv3_elu_f32_kernel(const float* __restrict__ x, int Cin, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ y, int Cout,
+                                                            const int* __restrict__ lens, int len_all, int T_alloc) {
+  __shared__ float xs[16][64 + 4];   // [k][t]
+  __shared__ float ws[16][64 + 4];   // [k][co]
+  const int b = blockIdx.z, t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int len = lens ? lens[b] : len_all;
+  if (t0 >= len) return;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 4x4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+  const float* xb = x + (long long)b * T_alloc * Cin;
+  for (int tap = 0; tap < 3; tap++) {
+    for (int k0 = 0; k0 < Cin; k0 += 16) {
+      // x tile: 64 t x 16 k
+      for (int e = tid; e < 64 * 16; e += 256) {
+        const int tt = e >> 4, kk = e & 15;
+        const int ts = t0 + tt + tap - 1;
+        float v = 0.f;
+        if (ts >= 0 && ts < len && k0 + kk < Cin) v = xb[(long long)ts * Cin + k0 + kk];
+        xs[kk][tt] = v;
+      }
+      for (int e = tid; e < 16 * 64; e += 256) {
+        const int kk = e >> 6, cc = e & 63;
+        float v = 0.f;
+        if (k0 + kk < Cin) v = w[((long long)tap * Cin + k0 + kk) * Cout + c0 + cc];
+        ws[kk][cc] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 16; kk++) {
+        const float4 a = *reinterpret_cast<const float4*>(&xs[kk][ty * 4]);
+        const float4 bb = *reinterpret_cast<const float4*>(&ws[kk][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) acc[i][j] += av[i] * bv[j];
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int t = t0 + ty * 4 + i;
+    if (t >= T_alloc) continue;
+    float4 o;
+    float* ov = reinterpret_cast<float*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; j++) ov[j] = (t < len) ? elu_f(acc[i][j] + bias[c0 + tx * 4 + j]) : 0.f;
+    *reinterpret_cast<float4*>(y + ((long long)b * T_alloc + t) * Cout + c0 + tx * 4) = o;
+  }
+}
+void launch_conv3_elu_f32(const float* x, int Cin, const float* w, const float* bias, float* y, int Cout, const int* lens,
+                          int len_all, int B, int T_alloc, cudaStream_t st) {
+  dim3 grid((T_alloc + 63) / 64, Cout / 64, B);
+  conv3_elu_f32_kernel<<<grid, 256, 0, st>>>(x, Cin, w, bias, y, Cout, lens, len_all, T_alloc);
+  CV2_LAUNCH_CHECK();
+}
+
+// classifier Linear 512 -> 1 + abs (f0_predictor.py:58); warp per frame
+__global__ void f0_head_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                               float* __restrict__ f0, const int* __restrict__ lens, int len_all, int T_alloc, int f0_stride) {
+  const int bi = blockIdx.y;
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int len = lens ? lens[bi] : len_all;
+  if (t >= T_alloc) return;
+  float acc = 0.f;
+  if (t < len) {
+    const float* xr = x + ((long long)bi * T_alloc + t) * 512;
+    for (int i = lane; i < 512; i += 32) acc += xr[i] * w[i];
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  }
+  if (lane == 0 && t < f0_stride) f0[(long long)bi * f0_stride + t] = (t < len) ? fabsf(acc + b[0]) : 0.f;
+}
+void launch_f0_head(const float* x, const float* w, const float* b, float* f0, const int* lens, int len_all, int B, int T_alloc,
+                    int f0_stride, cudaStream_t st) {
+  f0_head_kernel<<<dim3((T_alloc + 7) / 8, B), 256, 0, st>>>(x, w, b, f0, lens, len_all, T_alloc, f0_stride);
+  CV2_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// NSF source (SineGen2 + SourceModuleHnNSF2, generator.py:261-283, 314-339, 375-389).
+// Step 1 (frame rate): per harmonic, rad = fp32(f0*h / 24000) mod 1; inclusive scan with fp64 accumulation and
+//   fp32 outputs (what ATen's CPU cumsum does); P = ((C*2)*pi)*480 with fp32 roundings in that order.
+// Step 2 (sample rate): linear interpolation of P (ATen upsample_linear1d, align_corners=False, scale 1/480),
+//   sin, voiced gate, additive Gaussian noise, Linear 9->1, tanh.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void nsf_phase_kernel(const float* __restrict__ f0, int f0_stride, const int* __restrict__ lens, int len_all,
+                                 float* __restrict__ P, int T_alloc) {
+  const int b = blockIdx.x, h = threadIdx.x;  // 9 threads
+  if (h >= 9) return;
+  const int len = lens ? lens[b] : len_all;
+  const float hm = (float)(h + 1);
+  double c = 0.0;
+  const float PI32 = 3.14159274101257324f;  // float(np.pi)
+  for (int t = 0; t < len; t++) {
+    const float fn = __fmul_rn(f0[(long long)b * f0_stride + t], hm);
+    const float rad = fmodf(__fdiv_rn(fn, 24000.f), 1.f);
+    c += (double)rad;
+    const float cf = (float)c;
+    const float ph = __fmul_rn(__fmul_rn(__fmul_rn(cf, 2.f), PI32), 480.f);
+    P[((long long)b * T_alloc + t) * 9 + h] = ph;
+  }
+}
+
+__device__ __forceinline__ float gauss_hash(unsigned long long seed, unsigned long long idx) {
+  // counter-based N(0,1): two 32-bit hashes -> Box-Muller (production mode only; parity mode injects noise)
+  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  const float u1 = ((unsigned)(z >> 40) + 1.f) * (1.f / 16777217.f);
+  const float u2 = (unsigned)((z >> 8) & 0xFFFFFF) * (1.f / 16777216.f);
+  return sqrtf(-2.f * __logf(u1)) * __cosf(6.283185307f * u2);
+}
+
+__global__ void nsf_source_kernel(const float* __restrict__ f0, int f0_stride, const float* __restrict__ P, int T_alloc,
+                                  const int* __restrict__ lens, int len_all, const float* __restrict__ noise,
+                                  long long noise_bstride, unsigned long long seed, const float* __restrict__ lw,
+                                  const float* __restrict__ lb, const float* __restrict__ cache, int cache_len,
+                                  long long cache_bstride, float* __restrict__ src, long long src_bstride) {
+  const int b = blockIdx.y;
+  const int len = lens ? lens[b] : len_all;
+  const long long L = (long long)len * 480;
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= L) return;
+  if (j < cache_len) {  // inference(): s[:, :, :cache_len] = cache_source  (generator.py:579-580)
+    src[(long long)b * src_bstride + j] = cache[(long long)b * cache_bstride + j];
+    return;
+  }
+  // ATen area_pixel_compute_source_index: scale*(dst+0.5)-0.5 clamped at 0, scale = float(1/480)
+  const float scale = (float)(1.0 / 480.0);
+  float sidx = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)j, 0.5f)), 0.5f);
+  sidx = fmaxf(sidx, 0.f);
+  const int i0 = min((int)sidx, len - 1);
+  const int i1 = min(i0 + 1, len - 1);
+  const float l1 = __fsub_rn(sidx, (float)i0);
+  const float l0 = __fsub_rn(1.f, l1);
+  const int frame = (int)(j / 480);
+  const float uv = f0[(long long)b * f0_stride + frame] > 10.f ? 1.f : 0.f;
+  const float namp = uv * 0.003f + (1.f - uv) * 0.1f / 3.f;
+  const float* p0 = P + ((long long)b * T_alloc + i0) * 9;
+  const float* p1 = P + ((long long)b * T_alloc + i1) * 9;
+  const float* nz = noise ? noise + (long long)b * noise_bstride + j * 9 : nullptr;
+  float acc = lb[0];
+#pragma unroll
+  for (int h = 0; h < 9; h++) {
+    const float ph = __fadd_rn(__fmul_rn(l0, p0[h]), __fmul_rn(l1, p1[h]));
+    const float sine = sinf(ph) * 0.1f;
+    const float n = nz ? nz[h] : gauss_hash(seed + (unsigned long long)b * 0x1000003ull, (unsigned long long)j * 9 + h);
+    acc += lw[h] * (sine * uv + namp * n);
+  }
+  src[(long long)b * src_bstride + j] = tanhf(acc);
+}
+void launch_nsf_source(const float* f0, int f0_stride, float* P, int T_alloc, const int* lens, int len_all, const float* noise,
+                       long long noise_bstride, unsigned long long seed, const float* lw, const float* lb, const float* cache,
+                       int cache_len, long long cache_bstride, float* src, long long src_bstride, int B, int max_len,
+                       cudaStream_t st) {
+  nsf_phase_kernel<<<B, 32, 0, st>>>(f0, f0_stride, lens, len_all, P, T_alloc);
+  CV2_LAUNCH_CHECK();
+  const long long Lmax = (long long)max_len * 480;
+  nsf_source_kernel<<<dim3((unsigned)((Lmax + 255) / 256), B), 256, 0, st>>>(f0, f0_stride, P, T_alloc, lens, len_all, noise,
+                                                                             noise_bstride, seed, lw, lb, cache, cache_len,
+                                                                             cache_bstride, src, src_bstride);
+  CV2_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Source STFT (generator.py:504-510): n_fft 16, hop 4, periodic Hann, center=True (reflect pad 8).
+// Output channels-last fp32 [B, F_alloc, 18] = [Re X0..8 | Im X0..8]; frames >= L/4+1 are zero.
+// ---------------------------------------------------------------------------------------------------------
+__constant__ float c_cos16[16];
+__constant__ float c_sin16[16];
+__constant__ float c_hann16[16];
+static bool g_tables_ready = false;
+static void ensure_tables() {
+  if (g_tables_ready) return;
+  float c[16], s[16], w[16];
+  for (int i = 0; i < 16; i++) {
+    c[i] = (float)cos(2.0 * M_PI * i / 16.0);
+    s[i] = (float)sin(2.0 * M_PI * i / 16.0);
+    w[i] = (float)(0.5 * (1.0 - cos(2.0 * M_PI * i / 16.0)));
+  }
+  CV2_CUDA(cudaMemcpyToSymbol(c_cos16, c, sizeof(c)));
+  CV2_CUDA(cudaMemcpyToSymbol(c_sin16, s, sizeof(s)));
+  CV2_CUDA(cudaMemcpyToSymbol(c_hann16, w, sizeof(w)));
+  g_tables_ready = true;
+}
+void hift_init_tables() { ensure_tables(); }
+
+__global__ void source_stft_kernel(const float* __restrict__ src, long long src_bstride, const int* __restrict__ lens, int len_all,
+                                   float* __restrict__ out, int F_alloc) {
+  const int b = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F_alloc) return;
+  const int len = lens ? lens[b] : len_all;  // mel frames
+  const int L = len * 480;
+  const int F = L / 4 + 1;
+  float* o = out + ((long long)b * F_alloc + f) * 18;
+  if (f >= F) {
+#pragma unroll
+    for (int k = 0; k < 18; k++) o[k] = 0.f;
+    return;
+  }
+  float x[16];
+  const float* sb = src + (long long)b * src_bstride;
+#pragma unroll
+  for (int n = 0; n < 16; n++) {
+    int m = 4 * f + n - 8;
+    if (m < 0) m = -m;
+    if (m >= L) m = 2 * (L - 1) - m;
+    x[n] = sb[m] * c_hann16[n];
+  }
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    float re = 0.f, im = 0.f;
+#pragma unroll
+    for (int n = 0; n < 16; n++) {
+      const int idx = (k * n) & 15;
+      re += x[n] * c_cos16[idx];
+      im -= x[n] * c_sin16[idx];
+    }
+    o[k] = re;
+    o[9 + k] = im;
+  }
+}
+void launch_source_stft(const float* src, long long src_bstride, const int* lens, int len_all, float* out, int F_alloc, int B,
+                        cudaStream_t st) {
+  ensure_tables();
+  source_stft_kernel<<<dim3((F_alloc + 127) / 128, B), 128, 0, st>>>(src, src_bstride, lens, len_all, out, F_alloc);
+  CV2_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// source_downs[i]: Conv1d(18 -> C, k, stride r, pad r/2) on the source spectrum (generator.py:455-466, 533).
+// fp32 SIMT (K = 18*k is tiny).  w: [k][18][C] (C contiguous).  Emits the fp32 result and snake(alpha)(result)
+// in 16-bit as the A operand of the source ResBlock's first conv.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void source_down_kernel(const float* __restrict__ stft, int F_alloc, const float* __restrict__ w,
+                                   const float* __restrict__ bias, int k, int stride, int pad, int C, const int* __restrict__ lens,
+                                   int len_all, int frames_per_len, int frames_add, float* __restrict__ out32,
+                                   __half* __restrict__ out16, const float* __restrict__ alpha, int T_alloc) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.y + threadIdx.y;
+  const int len = lens ? lens[b] : len_all;
+  const int T_out = len * frames_per_len + frames_add;       // output frames of this stage
+  const int F = len * 120 + 1;                               // stft frames
+  if (t >= T_alloc) return;
+  const long long orow = ((long long)b * T_alloc + t) * C;
+  if (t >= T_out) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      out32[orow + c] = 0.f;
+      out16[orow + c] = __float2half_rn(0.f);
+    }
+    return;
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = bias[c];
+    for (int j = 0; j < k; j++) {
+      const int f = t * stride + j - pad;
+      if (f < 0 || f >= F) continue;
+      const float* sp = stft + ((long long)b * F_alloc + f) * 18;
+      const float* wp = w + (long long)j * 18 * C + c;
+#pragma unroll
+      for (int ch = 0; ch < 18; ch++) acc += sp[ch] * wp[(long long)ch * C];
+    }
+    out32[orow + c] = acc;
+    out16[orow + c] = __float2half_rn(snake_f(acc, alpha[c]));
+  }
+}
+void launch_source_down(const float* stft, int F_alloc, const float* w, const float* bias, int k, int stride, int pad, int C,
+                        const int* lens, int len_all, int frames_per_len, int frames_add, float* out32, __half* out16,
+                        const float* alpha, int B, int T_alloc, cudaStream_t st) {
+  const int tx = C >= 128 ? 128 : 64;
+  const int ty = 256 / tx;
+  source_down_kernel<<<dim3((T_alloc + ty - 1) / ty, B), dim3(tx, ty), 0, st>>>(stft, F_alloc, w, bias, k, stride, pad, C, lens,
+                                                                                  len_all, frames_per_len, frames_add, out32,
+                                                                                  out16, alpha, T_alloc);
+  CV2_LAUNCH_CHECK();
+}
+
+// reflection pad (1,0) of the last upsampler output (generator.py:529-530): row 0 <- row 2 (= x[1])
+__global__ void reflect_row0_kernel(float* __restrict__ x, int T_alloc, int C) {
+  const int b = blockIdx.x;
+  float* base = x + (long long)b * T_alloc * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) base[c] = base[2 * C + c];
+}
+void launch_reflect_row0(float* x, int B, int T_alloc, int C, cudaStream_t st) {
+  reflect_row0_kernel<<<B, 64, 0, st>>>(x, T_alloc, C);
+  CV2_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// iSTFT head (generator.py:546-551, 512-518): conv_post output [B, F_alloc, 18] ->
+// mag = min(exp(c[0:9]), 100), phi = sin(c[9:18]), X = mag (cos phi + i sin phi), 16-point inverse real DFT,
+// Hann-windowed overlap-add of the 4 frames covering each output sample, divide by the window envelope,
+// trim 8 samples per side, clamp to +-0.99.  One pass: 18 B read + 4 B written per output sample... per hop.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp, int F_alloc, int ld, const int* __restrict__ lens,
+                                                    int len_all, float* __restrict__ wav, long long wav_bstride) {
+  __shared__ float Xre[260][9];
+  __shared__ float Xim[260][9];
+  const int b = blockIdx.y;
+  const int len = lens ? lens[b] : len_all;
+  const int F = len * 120 + 1;
+  const int q0 = blockIdx.x * 256;          // first hop of this block; hop q covers samples n = 4q..4q+3
+  if (q0 >= F - 1) return;
+  // frames q0-1 .. q0+257
+  for (int e = threadIdx.x; e < 259; e += 256) {
+    const int f = q0 - 1 + e;
+    if (f >= 0 && f < F) {
+      const float* c = cp + ((long long)b * F_alloc + f) * ld;
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        const float mag = fminf(expf(c[k]), 100.f);
+        const float ph = sinf(c[9 + k]);
+        float sn, cs;
+        sincosf(ph, &sn, &cs);
+        Xre[e][k] = mag * cs;
+        Xim[e][k] = mag * sn;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        Xre[e][k] = 0.f;
+        Xim[e][k] = 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  const int q = q0 + threadIdx.x;
+  if (q >= F - 1) return;
+  float y[4] = {0.f, 0.f, 0.f, 0.f};
+  float env[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int df = -1; df <= 2; df++) {
+    const int f = q + df;
+    if (f < 0 || f >= F) continue;
+    const int e = threadIdx.x + 1 + df;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int kp = 4 * q + 8 + i - 4 * f;   // position inside frame f: 8 + i - 4 df in [0, 16)
+      float g = Xre[e][0] + ((kp & 1) ? -Xre[e][8] : Xre[e][8]);
+#pragma unroll
+      for (int k = 1; k < 8; k++) {
+        const int idx = (k * kp) & 15;
+        g += 2.f * (Xre[e][k] * c_cos16[idx] - Xim[e][k] * c_sin16[idx]);
+      }
+      const float w = c_hann16[kp];
+      y[i] += w * g * (1.f / 16.f);
+      env[i] += w * w;
+    }
+  }
+  float4 o;
+  o.x = fminf(fmaxf(y[0] / env[0], -0.99f), 0.99f);
+  o.y = fminf(fmaxf(y[1] / env[1], -0.99f), 0.99f);
+  o.z = fminf(fmaxf(y[2] / env[2], -0.99f), 0.99f);
+  o.w = fminf(fmaxf(y[3] / env[3], -0.99f), 0.99f);
+  *reinterpret_cast<float4*>(wav + (long long)b * wav_bstride + 4 * (long long)q) = o;
+}
+void launch_istft(const float* cp, int F_alloc, int ld, const int* lens, int len_all, float* wav, long long wav_bstride, int B,
+                  int max_len, cudaStream_t st) {
+  ensure_tables();
+  const int hops = max_len * 120;
+  istft_kernel<<<dim3((hops + 255) / 256, B), 256, 0, st>>>(cp, F_alloc, ld, lens, len_all, wav, wav_bstride);
+  CV2_LAUNCH_CHECK();
+}
+
+// streaming crossfade (common.py:142-150): float64 Hamming window maths, stored as fp32
+__global__ void crossfade_kernel(float* __restrict__ speech, const float* __restrict__ old_tail, const double* __restrict__ window,
+                                 int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) speech[i] = (float)((double)speech[i] * window[i] + (double)old_tail[i] * window[n + i]);
+}
+void launch_crossfade(float* speech, const float* old_tail, const double* window, int n, cudaStream_t st) {
+  crossfade_kernel<<<(n + 255) / 256, 256, 0, st>>>(speech, old_tail, window, n);
+  CV2_LAUNCH_CHECK();
+}
+
+}  // namespace cv2

@@ -1,0 +1,325 @@
+"""Python host of the B200 token2wav engine: the reference's interface for this path, backed by the C ABI.
+
+Mirrors (names, argument meaning, return values):
+  * CausalMaskedDiffWithXvec.inference        cosyvoice/flow/flow.py:235-283        -> B200Flow.inference
+  * ConditionalCFM.forward_estimator slot     cosyvoice/flow/flow_matching.py:125-150 -> B200Flow.estimator_forward
+  * HiFTGenerator.inference                   cosyvoice/hifigan/generator.py:570-582 -> B200HiFT.inference
+  * CosyVoice2Model.token2wav                 cosyvoice/cli/model.py:300-334         -> B200Token2Wav.token2wav
+plus batched entry points (`inference_batch`, `token2wav_batch`) that the reference (hard-wired to batch 1,
+flow.py:246) does not have; they compute exactly the per-utterance B=1 result for every utterance.
+
+torch is used for device memory and streams only; all arithmetic runs in libcv2eu_b200.so.
+"""
+import ctypes as C
+import math
+import threading
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from . import pack as _pack
+
+_DT = {torch.float32: 0, torch.float16: 1, torch.int32: 2}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def euler_schedule(n_timesteps=10):
+    """t / dt exactly as ConditionalCFM.solve_euler computes them in fp32 (flow_matching.py:86-121):
+    cosine t_span, dt from the RUNNING t."""
+    t_span = torch.linspace(0, 1, n_timesteps + 1, dtype=torch.float32)
+    t_span = 1 - torch.cos(t_span * 0.5 * torch.pi)
+    t, dt = t_span[0], t_span[1] - t_span[0]
+    ts, dts = [], []
+    for step in range(1, n_timesteps + 1):
+        ts.append(float(t))
+        dts.append(float(dt))
+        t = t + dt
+        if step < n_timesteps:
+            dt = t_span[step + 1] - t
+    return np.asarray(ts, np.float32), np.asarray(dts, np.float32)
+
+
+class _Engine:
+    """Owns the C engine handle, the packed device weights and the workspaces."""
+
+    def __init__(self, device="cuda:0"):
+        if not torch.cuda.is_available():
+            raise _lib.Cv2Error("cosyvoice2_eu_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        h = C.c_void_p()
+        _lib.check(self.lib.cv2_engine_create(C.byref(h), idx))
+        self.h = h
+        self.tensors = {}
+        self.ws = {}
+        self.lock = threading.Lock()
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.cv2_engine_destroy(self.h)
+        except Exception:
+            pass
+
+    def register(self, packed):
+        for name, t in packed.items():
+            t = t.to(self.device).contiguous()
+            self.tensors[name] = t
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            _lib.check(self.lib.cv2_engine_set_tensor(self.h, name.encode(), _lib.ptr(t), _DT[t.dtype], t.dim(), shape))
+
+    def finalize(self, flow, hift):
+        _lib.check(self.lib.cv2_engine_finalize(self.h, int(flow), int(hift)))
+
+    def workspace(self, key, nbytes):
+        """Zero-initialised, cached per (kind, shape, stream)."""
+        key = key + (torch.cuda.current_stream().cuda_stream,)
+        w = self.ws.get(key)
+        if w is None or w.numel() < nbytes:
+            w = torch.zeros(int(nbytes), dtype=torch.uint8, device=self.device)
+            self.ws[key] = w
+        return w
+
+    def last_launches(self):
+        return int(self.lib.cv2_engine_last_launches(self.h))
+
+
+_shared = {}
+
+
+def get_engine(device="cuda:0"):
+    e = _shared.get(str(device))
+    if e is None:
+        e = _Engine(device)
+        _shared[str(device)] = e
+    return e
+
+
+class B200Flow:
+    """Drop-in for the reference flow object (CausalMaskedDiffWithXvec) on the inference path."""
+
+    token_mel_ratio = 2
+    pre_lookahead_len = 3
+    input_frame_rate = 25
+    n_timesteps = 10
+    inference_cfg_rate = 0.7
+
+    def __init__(self, device="cuda:0", engine=None):
+        self.eng = engine or get_engine(device)
+        self.device = self.eng.device
+        g = torch.Generator(device="cpu")
+        g.manual_seed(0)  # CausalConditionalCFM.__init__: set_all_random_seed(0); randn([1,80,15000])  (flow_matching.py:195-198)
+        self.rand_noise = torch.randn([1, 80, 50 * 300], generator=g).to(self.device)
+        ts, dts = euler_schedule(self.n_timesteps)
+        self._t_dev = torch.from_numpy(ts).to(self.device)
+        self._dt_host = (C.c_float * len(dts))(*dts.tolist())
+        self.loaded = False
+
+    # nn.Module-ish surface used by CosyVoice2Model.__init__/load (model.py:267-269, 85-86)
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def half(self):
+        return self
+
+    def load_state_dict(self, sd, strict=True):
+        self.eng.register(_pack.pack_flow({k: v.detach().cpu() for k, v in sd.items()}))
+        self.eng.finalize(True, False)
+        self.loaded = True
+
+    # ---- estimator slot (boundary #4) ----
+    def estimator_forward(self, x, mask, mu, t, spks, cond, streaming=False):
+        """CausalConditionalDecoder.forward on contiguous fp32 NCT device tensors; returns a new tensor."""
+        B2, _, T = x.shape
+        f = lambda a: a.to(self.device, torch.float32).contiguous()
+        x, mask, mu, t, spks, cond = map(f, (x, mask, mu, t, spks, cond))
+        out = torch.empty_like(x)
+        n = self.eng.lib.cv2_estimator_workspace_bytes(self.eng.h, B2, T)
+        if n == 0:
+            raise _lib.Cv2Error(self.eng.lib.cv2_last_error().decode())
+        ws = self.eng.workspace(("est", B2, T), n)
+        _lib.check(self.eng.lib.cv2_estimator_forward(self.eng.h, _stream(), _lib.ptr(x), _lib.ptr(mask), _lib.ptr(mu), _lib.ptr(t),
+                                                      _lib.ptr(spks), _lib.ptr(cond), _lib.ptr(out), B2, T, int(streaming),
+                                                      _lib.ptr(ws), ws.numel()))
+        return out
+
+    # ---- batched flow ----
+    def inference_batch(self, tokens, prompt_tokens, prompt_feats, embeddings, streaming=False, finalize=True,
+                        return_intermediates=False):
+        """tokens / prompt_tokens: lists of int tensors [N_b] ; prompt_feats: list of [2P_b, 80]; embeddings: list of [192].
+        Returns (mel [B,80,Tmax] zero padded, mel_lens int32 [B] on the device)."""
+        B = len(tokens)
+        dev = self.device
+        tl = [int(t.numel()) for t in tokens]
+        pl = [int(t.numel()) for t in prompt_tokens]
+        fl = [int(f.shape[0]) for f in prompt_feats]
+        max_total = max(a + b for a, b in zip(tl, pl))
+        drop = 0 if finalize else self.pre_lookahead_len
+        mel_lens = [2 * (a + b - drop) - c for a, b, c in zip(tl, pl, fl)]
+        mel_T = max(mel_lens)
+        assert min(mel_lens) > 0
+        tok = torch.zeros(B, max(tl), dtype=torch.int32)
+        ptk = torch.zeros(B, max(max(pl), 1), dtype=torch.int32)
+        pf = torch.zeros(B, max(max(fl), 1), 80, dtype=torch.float32)
+        for b in range(B):
+            tok[b, :tl[b]] = tokens[b].reshape(-1).to(torch.int32).cpu()
+            ptk[b, :pl[b]] = prompt_tokens[b].reshape(-1).to(torch.int32).cpu()
+            pf[b, :fl[b]] = prompt_feats[b].reshape(-1, 80).float().cpu()
+        emb = torch.stack([e.reshape(192).float().cpu() for e in embeddings])
+        lens = torch.tensor([tl, pl, fl], dtype=torch.int32)
+        tok, ptk, pf, emb, lens = (a.to(dev, non_blocking=True) for a in (tok, ptk, pf, emb, lens))
+        return self._forward_device(tok, lens[0], ptk, lens[1], pf, lens[2], emb, B, max_total, mel_T, streaming, finalize,
+                                    return_intermediates) + (torch.tensor(mel_lens, dtype=torch.int32),)
+
+    def _forward_device(self, tok, tok_len, ptk, ptk_len, pf, pf_len, emb, B, max_total, mel_T, streaming, finalize,
+                        return_intermediates=False):
+        dev = self.device
+        mel = torch.empty(B, 80, mel_T, dtype=torch.float32, device=dev)
+        mu = torch.empty(B, 80, 2 * max_total, dtype=torch.float32, device=dev) if return_intermediates else None
+        enc = torch.empty(B, 2 * max_total, 512, dtype=torch.float32, device=dev) if return_intermediates else None
+        n = self.eng.lib.cv2_flow_workspace_bytes(self.eng.h, B, max_total, self.n_timesteps)
+        if n == 0:
+            raise _lib.Cv2Error(self.eng.lib.cv2_last_error().decode())
+        ws = self.eng.workspace(("flow", B, max_total), n)
+        _lib.check(self.eng.lib.cv2_flow_forward(
+            self.eng.h, _stream(), _lib.ptr(tok), tok.shape[1], _lib.ptr(tok_len), _lib.ptr(ptk), ptk.shape[1], _lib.ptr(ptk_len),
+            _lib.ptr(pf), pf.shape[1] * 80, _lib.ptr(pf_len), _lib.ptr(emb), _lib.ptr(self.rand_noise), self.rand_noise.shape[2], B,
+            max_total, int(streaming), int(finalize), _lib.ptr(self._t_dev), self._dt_host, self.n_timesteps,
+            self.inference_cfg_rate, _lib.ptr(mel), mel_T, _lib.ptr(mu), _lib.ptr(enc), _lib.ptr(ws), ws.numel()))
+        if return_intermediates:
+            return mel, dict(mu=mu, encoder_out=enc)
+        return (mel,)
+
+    @torch.inference_mode()
+    def inference(self, token, token_len, prompt_token, prompt_token_len, prompt_feat, prompt_feat_len, embedding, streaming,
+                  finalize):
+        """Reference signature (flow.py:236-245); returns (mel f32 [1,80,T_gen], None)."""
+        assert token.shape[0] == 1
+        out = self.inference_batch([token[0]], [prompt_token[0]], [prompt_feat[0]], [embedding[0]], streaming=streaming,
+                                   finalize=finalize)
+        return out[0], None
+
+
+class B200HiFT:
+    """Drop-in for HiFTGenerator on the inference path."""
+
+    def __init__(self, device="cuda:0", engine=None):
+        self.eng = engine or get_engine(device)
+        self.device = self.eng.device
+        self.loaded = False
+        self._seed = 0
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def load_state_dict(self, sd, strict=True):
+        self.eng.register(_pack.pack_hift({k: v.detach().cpu() for k, v in sd.items()}))
+        self.eng.finalize(False, True)
+        self.loaded = True
+
+    @torch.inference_mode()
+    def inference(self, speech_feat, cache_source=torch.zeros(1, 1, 0), noise=None, lens=None, return_f0=False):
+        """speech_feat f32 [B,80,T]; cache_source [B,1,n]; noise (parity mode) [B,480T,9] replaces the reference's
+        torch.randn_like draw (generator.py:334).  Returns (speech [B,480T], source [B,1,480T])."""
+        dev = self.device
+        mel = speech_feat.to(dev, torch.float32).contiguous()
+        B, _, T = mel.shape
+        speech = torch.empty(B, 480 * T, dtype=torch.float32, device=dev)
+        source = torch.empty(B, 1, 480 * T, dtype=torch.float32, device=dev)
+        f0 = torch.empty(B, T, dtype=torch.float32, device=dev) if return_f0 else None
+        cache_len = int(cache_source.shape[2]) if cache_source is not None else 0
+        cs = cache_source.to(dev, torch.float32).contiguous() if cache_len > 0 else None
+        nz = noise.to(dev, torch.float32).contiguous() if noise is not None else None
+        ln = lens.to(dev, torch.int32).contiguous() if lens is not None else None
+        if lens is not None:
+            speech.zero_()
+            source.zero_()
+        n = self.eng.lib.cv2_hift_workspace_bytes(self.eng.h, B, T)
+        if n == 0:
+            raise _lib.Cv2Error(self.eng.lib.cv2_last_error().decode())
+        ws = self.eng.workspace(("hift", B, T), n)
+        self._seed += 1
+        _lib.check(self.eng.lib.cv2_hift_forward(self.eng.h, _stream(), _lib.ptr(mel), T, _lib.ptr(ln), _lib.ptr(cs), cache_len,
+                                                 _lib.ptr(nz), self._seed, _lib.ptr(speech), _lib.ptr(source), _lib.ptr(f0), B,
+                                                 _lib.ptr(ws), ws.numel()))
+        if return_f0:
+            return speech, source, f0
+        return speech, source
+
+
+class B200Token2Wav:
+    """CosyVoice2Model.token2wav (cosyvoice/cli/model.py:300-334) with the same per-uuid hift cache
+    (model.py:271-276: token_hop_len 25, mel_cache_len 8, source_cache_len 3840, hamming(7680) crossfade)."""
+
+    def __init__(self, flow: B200Flow, hift: B200HiFT):
+        self.flow, self.hift = flow, hift
+        self.device = flow.device
+        self.token_hop_len = 25
+        self.mel_cache_len = 8
+        self.source_cache_len = int(self.mel_cache_len * 480)
+        self.speech_window = np.hamming(2 * self.source_cache_len)
+        self._window_dev = torch.from_numpy(self.speech_window).to(self.device)   # float64, like the reference's maths
+        self.lock = threading.Lock()
+        self.hift_cache_dict = {}
+
+    def _fade_in_out(self, speech, old_tail):
+        n = self.source_cache_len
+        speech = speech.contiguous()
+        old = old_tail[..., -n:].contiguous()
+        _lib.check(self.flow.eng.lib.cv2_crossfade(_stream(), _lib.ptr(speech), _lib.ptr(old), _lib.ptr(self._window_dev), n))
+        return speech
+
+    @torch.inference_mode()
+    def token2wav(self, token, prompt_token, prompt_feat, embedding, token_offset, uuid, stream=False, finalize=False, speed=1.0,
+                  noise=None):
+        tts_mel, _ = self.flow.inference(token=token, token_len=None, prompt_token=prompt_token, prompt_token_len=None,
+                                         prompt_feat=prompt_feat, prompt_feat_len=None, embedding=embedding, streaming=stream,
+                                         finalize=finalize)
+        tts_mel = tts_mel[:, :, token_offset * self.flow.token_mel_ratio:]
+        cache = self.hift_cache_dict.get(uuid)
+        if cache is not None:
+            tts_mel = torch.concat([cache['mel'], tts_mel], dim=2)
+            hift_cache_source = cache['source']
+        else:
+            hift_cache_source = torch.zeros(1, 1, 0)
+        if finalize is False:
+            tts_speech, tts_source = self.hift.inference(speech_feat=tts_mel, cache_source=hift_cache_source, noise=noise)
+            if cache is not None:
+                tts_speech = self._fade_in_out(tts_speech, cache['speech'])
+            self.hift_cache_dict[uuid] = {'mel': tts_mel[:, :, -self.mel_cache_len:],
+                                          'source': tts_source[:, :, -self.source_cache_len:],
+                                          'speech': tts_speech[:, -self.source_cache_len:]}
+            tts_speech = tts_speech[:, :-self.source_cache_len]
+        else:
+            if speed != 1.0:
+                assert cache is None, 'speed change only support non-stream inference mode'
+                tts_mel = torch.nn.functional.interpolate(tts_mel, size=int(tts_mel.shape[2] / speed), mode='linear')
+            tts_speech, tts_source = self.hift.inference(speech_feat=tts_mel, cache_source=hift_cache_source, noise=noise)
+            if cache is not None:
+                tts_speech = self._fade_in_out(tts_speech, cache['speech'])
+        return tts_speech
+
+    @torch.inference_mode()
+    def token2wav_batch(self, tokens, prompt_tokens, prompt_feats, embeddings, noises=None):
+        """Offline (finalize=True) token2wav for a batch of independent utterances.
+        Returns (speech [B, Lmax] zero padded, lengths int32 [B] in samples)."""
+        mel, mel_lens = self.flow.inference_batch(tokens, prompt_tokens, prompt_feats, embeddings, streaming=False, finalize=True)
+        noise = None
+        if noises is not None:
+            T = mel.shape[2]
+            noise = torch.zeros(len(tokens), 480 * T, 9)
+            for b, nz in enumerate(noises):
+                noise[b, :nz.shape[-2]] = nz.reshape(-1, 9)
+        speech, _ = self.hift.inference(mel, noise=noise, lens=mel_lens)
+        return speech, mel_lens * 480

@@ -1,0 +1,106 @@
+/* cv2eu_b200 -- C ABI of the B200-native token2wav engine for CosyVoice2-EU.
+ *
+ * Plain C, raw device pointers + a CUDA stream, no torch types: this is the same convention as the reference's one
+ * existing FFI on this path, the TensorRT estimator slot (cosyvoice/flow/flow_matching.py:129-150: set_tensor_address
+ * on caller-owned contiguous NCT fp32 buffers, execute_async_v3(current_stream); I/O names and shapes from
+ * cosyvoice/bin/export_onnx.py:89-109; context pool cosyvoice/utils/common.py:171-186).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; cv2_last_error() gives the message (thread local);
+ *   - the library never allocates caller-visible device memory: weights are registered by name as device pointers that
+ *     the caller keeps alive, activations live in a caller-provided, ZERO-INITIALISED workspace whose size is queried
+ *     with the *_workspace_bytes functions (same arguments as the forward);
+ *   - all work is enqueued on `stream` (a cudaStream_t); no host synchronisation, CUDA-graph capturable;
+ *   - one in-flight call per (engine, workspace); concurrency = one workspace per stream.
+ *   - there is no CPU fallback: without an sm_100a device every forward fails.
+ */
+#ifndef CV2EU_B200_H_
+#define CV2EU_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cv2_engine cv2_engine;
+
+enum { CV2_F32 = 0, CV2_F16 = 1, CV2_I32 = 2 };
+
+const char* cv2_last_error(void);
+int cv2_version(void);
+
+/* ---- engine / weights (replaces flow.load_state_dict / hift.load_state_dict, cosyvoice/cli/model.py:85-90) ---- */
+int cv2_engine_create(cv2_engine** out, int device);
+void cv2_engine_destroy(cv2_engine* e);
+/* register one packed tensor (names: cosyvoice2_eu_b200/pack.py) */
+int cv2_engine_set_tensor(cv2_engine* e, const char* name, const void* dptr, int dtype, int ndim, const int64_t* shape);
+/* validates that every tensor the flow and/or hift forward needs is present */
+int cv2_engine_finalize(cv2_engine* e, int need_flow, int need_hift);
+/* kernels launched by the most recent forward on this engine */
+long long cv2_engine_last_launches(cv2_engine* e);
+
+/* ---- estimator: CausalConditionalDecoder.forward (cosyvoice/flow/decoder.py:405-494), the reference's TRT slot
+ *      (flow_matching.py:125-150).  x, mu, cond: [B2,80,T]; mask: [B2,1,T] (prefix of ones); t: [B2]; spks: [B2,80];
+ *      out: [B2,80,T] (may alias x).  All fp32, contiguous, on the device. ---- */
+size_t cv2_estimator_workspace_bytes(cv2_engine* e, int B2, int T);
+int cv2_estimator_forward(cv2_engine* e, void* stream, const float* x, const float* mask, const float* mu, const float* t,
+                          const float* spks, const float* cond, float* out, int B2, int T, int streaming, void* workspace,
+                          size_t workspace_bytes);
+
+/* ---- flow: CausalMaskedDiffWithXvec.inference (cosyvoice/flow/flow.py:235-283), batched over B utterances.
+ *      token [B,token_stride] i32, token_len [B] i32, prompt_token [B,prompt_stride] i32, prompt_len [B] i32,
+ *      prompt_feat [B, prompt_feat_bstride] f32 (each utterance [2P,80] row-major), prompt_feat_len [B] i32,
+ *      embedding [B,192] f32, rand_noise [80, noise_stride] f32 (CausalConditionalCFM.rand_noise),
+ *      t_steps [n_steps] f32 ON THE DEVICE (running t of solve_euler), dt_steps [n_steps] f32 ON THE HOST,
+ *      mel_out [B,80,mel_out_T] f32: frames after the prompt, zero padded.  max_tok_total = max_b(prompt_len+token_len)
+ *      is the only host-side length (grid sizing); everything else stays on the device.
+ *      mu_out (optional, [B,80,2*max_tok_total]) and enc_out (optional, [B,2*max_tok_total,512]) expose
+ *      intermediates for parity tests. ---- */
+size_t cv2_flow_workspace_bytes(cv2_engine* e, int B, int max_tok_total, int n_steps);
+int cv2_flow_forward(cv2_engine* e, void* stream, const int32_t* token, int token_stride, const int32_t* token_len,
+                     const int32_t* prompt_token, int prompt_stride, const int32_t* prompt_len, const float* prompt_feat,
+                     long long prompt_feat_bstride, const int32_t* prompt_feat_len, const float* embedding,
+                     const float* rand_noise, int noise_stride, int B, int max_tok_total, int streaming, int finalize,
+                     const float* t_steps_dev, const float* dt_steps_host, int n_steps, float cfg_rate, float* mel_out,
+                     int mel_out_T, float* mu_out, float* enc_out, void* workspace, size_t workspace_bytes);
+
+/* ---- hift: HiFTGenerator.inference (cosyvoice/hifigan/generator.py:570-582), batched.
+ *      mel [B,80,mel_T] f32; lens [B] i32 valid frames (NULL: all mel_T); cache_source [B,1,cache_len] or NULL;
+ *      noise [B,480*mel_T,9] f32 = the N(0,1) draw of SineGen2 (generator.py:334) for parity runs, NULL -> in-kernel
+ *      counter-based generator seeded with `seed`; speech [B,480*mel_T]; source [B,1,480*mel_T]; f0_out optional [B,mel_T]. */
+size_t cv2_hift_workspace_bytes(cv2_engine* e, int B, int mel_T);
+int cv2_hift_forward(cv2_engine* e, void* stream, const float* mel, int mel_T, const int32_t* lens, const float* cache_source,
+                     int cache_len, const float* noise, unsigned long long seed, float* speech, float* source, float* f0_out,
+                     int B, void* workspace, size_t workspace_bytes);
+
+/* ---- streaming glue: fade_in_out (cosyvoice/utils/common.py:142-150) on the device.  window: [2n] f64 device. ---- */
+int cv2_crossfade(void* stream, float* speech, const float* old_tail, const double* window, int n);
+
+/* ---- single-kernel entry points (parity tests of the individual kernels) ---- */
+/* out = epilogue(sum_taps A[s, t+off, :] W^T): A 16-bit [S,T_alloc,ldA], W 16-bit [N, ntaps*ceil64(Kc)], see gemm_tap.cuh.
+ * act: 0 none 1 mish 2 gelu 3 silu 4 elu 5 lrelu(act_f) 6 snake(act_a).  Optional outputs: out32 [S*T_alloc,N] fp32,
+ * out16 [S*T_alloc,N] 16-bit of the same value, out16_ln = LayerNorm(value; ln2_g, ln2_b, eps 1e-5) 16-bit. */
+int cv2_op_gemm_tap(void* stream, const void* A, int S, int T_alloc, int Kc, long long ldA, const void* W, int N, int Ktot,
+                    const float* bias, int bn, int ntaps, const int* tap_off_host, const int32_t* lens, int len_all,
+                    const float* ln_g, const float* ln_b, float ln_eps, int act, float act_f, const float* act_a,
+                    const float* rowvec, int rowvec_ld, int mask_pre_res, const float* res, float out_scale, float* out32,
+                    int out32_accum, void* out16, const float* ln2_g, const float* ln2_b, void* out16_ln);
+/* q,k [S,H,T_alloc,64], vt [S,H,64,T_alloc] 16-bit -> out [S,T_alloc,H*64] 16-bit */
+int cv2_op_flash_attn(void* stream, const void* q, const void* k, const void* vt, void* out, const int32_t* lens, int len_all,
+                      int S, int heads, int T_alloc, int chunk);
+/* encoder relative-position attention, fp32 qkv [S,T_alloc,1536], pos [2*Tmax-1,512] */
+int cv2_op_rel_attn(void* stream, const float* qkv, const float* pos, const float* bias_u, const float* bias_v, void* out,
+                    const int32_t* lens, int len_all, int S, int T_alloc, int Tmax, int chunk);
+/* source STFT: src [B, 480*mel_T] -> out [B, F_alloc, 18] */
+int cv2_op_source_stft(void* stream, const float* src, int mel_T, const int32_t* lens, float* out, int F_alloc, int B);
+/* iSTFT head: conv_post output [B, F_alloc, 18] -> wav [B, 480*mel_T] */
+int cv2_op_istft(void* stream, const float* cp, int F_alloc, const int32_t* lens, int mel_T, float* wav, int B);
+/* NSF source: f0 [B, mel_T] -> src [B, 480*mel_T]; phase_ws [B, mel_T, 9] scratch */
+int cv2_op_nsf_source(void* stream, const float* f0, int mel_T, const int32_t* lens, const float* noise, unsigned long long seed,
+                      const float* lw, const float* lb, float* phase_ws, float* src, int B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CV2EU_B200_H_ */
