@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- token2wav throughput on B200 (BASELINE.json metric: audio-seconds per second; RTF at batch 1).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path (flow.inference + hift.inference, i.e. token2wav offline) over one batch of
+synthetic utterances per GPU.  Workload at every N: BASELINE.json configs[2] per GPU -- 64 variable-length
+utterances, durations U[4, 20] s (N = round(25 d) tokens, 75-token / 150-frame prompt), weak scaling (every rank gets
+its own 64-utterance shard of the corpus, as configs[4] shards by utterance; the only collective is the final gather).
+configs[1] (single 10 s utterance, batch 1) is timed as well and reported under "rtf_batch1".
+
+`value`   : generated audio-seconds / second with all inputs resident in HBM (device timed, max over ranks).
+`e2e`     : the same through the public API (B200Token2Wav.token2wav_batch) with host inputs in pinned memory,
+            H2D of tokens / prompt mel / x-vectors and D2H of the waveforms inside the timed region (+ NCCL gather of
+            lengths and audio to rank 0 when N > 1).
+`roofline`: dominant kernel family by device time (CUDA events around every launch of the family, recorded on the
+            launching stream during the timed region): algorithmic FLOPs / family time vs the measured dense bf16 peak.
+`cpu_baseline` / --impl reference: the oracle port of the reference's CPU token2wav (torch fp32, all host threads) on a
+            bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PROMPT = 75
+BATCH = 64
+FAMILIES = ["gemm_tap<64>", "gemm_tap<128>", "gemm_tap<256>", "flash_attn", "rel_attn", "f0_conv_f32", "nsf_source", "source_stft",
+            "source_down", "istft", "layernorm"]
+
+
+def workload(rank, batch=BATCH):
+    """configs[2]: durations U[4,20] s -> tokens; seeded per rank."""
+    rng = np.random.Generator(np.random.Philox(key=1000 + rank))
+    dur = rng.uniform(4.0, 20.0, size=batch)
+    return [int(round(25 * d)) for d in dur]
+
+
+def algorithmic_flops(n_tokens, n_prompt=N_PROMPT):
+    """Unpadded algorithmic FLOPs (multiply-add = 2) per kernel family for a list of utterances; layer dims from
+    cosyvoice2.yaml:39-112, totals agree with SURVEY.md 8(d) (2.43 TFLOP for the 8 s utterance of configs[0])."""
+    f = dict.fromkeys(FAMILIES, 0.0)
+    for n in n_tokens:
+        tt = n + n_prompt          # token-rate frames
+        T = 2 * tt                 # mel frames seen by the estimator
+        tg = 2 * n                 # generated mel frames (hift)
+        est_lin = 132161536.0
+        f["gemm_tap<256>"] += 20 * T * (est_lin - 40960.0)
+        f["gemm_tap<128>"] += 20 * T * 40960.0
+        f["flash_attn"] += 20 * T * 114688.0 * T
+        f["gemm_tap<256>"] += tt * (4.194304e6 + 6 * 7.340032e6) + T * (3.227648e6 - 81920.0 + 4 * 7.340032e6)
+        f["gemm_tap<128>"] += T * 81920.0
+        f["rel_attn"] += tt * 6 * 4096.0 * tt + T * 4 * 8192.0 * tt
+        f["gemm_tap<256>"] += tg * (573440.0 + 4194304.0 + 8 * 336 * 65536.0)
+        f["gemm_tap<128>"] += tg * (8 * 720896.0 + 40 * 336 * 16384.0)
+        f["gemm_tap<64>"] += tg * (40 * 114688.0 + 120 * 384 * 4096.0 + 120 * 16128.0)
+        f["source_down"] += tg * (8 * 276480.0 + 40 * 27648.0 + 120 * 2304.0)
+        f["f0_conv_f32"] += tg * 6.54e6
+    return f
+
+
+def sample_clocks(stop, out):
+    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    idx = os.environ.get("LOCAL_RANK", "0")
+    try:
+        p = subprocess.Popen(["nvidia-smi", "-i", idx, f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                             stdout=subprocess.PIPE, text=True)
+    except Exception:
+        return
+    while not stop.is_set():
+        line = p.stdout.readline()
+        if not line:
+            break
+        out.append(line.strip())
+    p.terminate()
+
+
+def clocks_summary(lines):
+    sm, mx, reasons = [], 0, set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for ln in lines:
+        c = [x.strip() for x in ln.split(",")]
+        try:
+            sm.append(float(c[0]))
+            mx = max(mx, float(c[1]))
+            for n, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        except Exception:
+            continue
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+            "samples": len(sm)}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return p, "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_run(n_tok, threads=None):
+    """Oracle port of the reference CPU token2wav on one utterance; returns (seconds, audio_seconds)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import token2wav_oracle as O
+    from synth import weights
+    if threads:
+        torch.set_num_threads(threads)
+    fs, hs = weights.to_torch(weights.make_flow_state()), weights.to_torch(weights.make_hift_state())
+    u = {k: torch.from_numpy(v) for k, v in weights.make_utterance(n_tok, N_PROMPT, seed=7).items()}
+    eng = O.OracleToken2Wav(fs, hs, weights.cfm_rand_noise())
+    eng.hift_cache_dict["b"] = None
+    t0 = time.perf_counter()
+    wav = eng.token2wav(u["token"], u["prompt_token"], u["prompt_feat"], u["embedding"], 0, "b", finalize=True)
+    dt = time.perf_counter() - t0
+    return dt, wav.shape[1] / 24000.0
+
+
+def main_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the Python reference cannot
+    travel to the GPU box), all host threads, bounded sample = one median-length (12 s) utterance of the workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    n_tok = 300
+    times, audio = [], 0.0
+    for i in range(args.warmup + args.steps):
+        dt, a = cpu_reference_run(n_tok, cores)
+        if i >= args.warmup:
+            times.append(dt)
+            audio += a
+    total = sum(times)
+    val = audio / total
+    line = {"impl": "reference", "metric": "token2wav_audio_seconds_per_second", "value": val, "unit": "audio-s/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * total / max(len(times), 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[2] sample: one 12 s utterance (300 tokens + 75-token prompt) per step, offline, 10 Euler steps"},
+            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                             "sample": "one 12 s utterance per step, torch fp32 CPU, all host threads"},
+            "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from cosyvoice2_eu_b200 import B200Flow, B200HiFT, B200Token2Wav
+    from synth import weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    # ---- engine with random-init weights of the CosyVoice2-0.5B-EU architecture ----
+    flow, hift = B200Flow(dev), B200HiFT(dev)
+    flow.load_state_dict(weights.to_torch(weights.make_flow_state()))
+    hift.load_state_dict(weights.to_torch(weights.make_hift_state()))
+    t2w = B200Token2Wav(flow, hift)
+    eng = flow.eng
+
+    # ---- this rank's shard: BATCH utterances, length-sorted (bucketing keeps neighbours similar) ----
+    n_tokens = sorted(workload(rank, args.batch))
+    utts = [weights.make_utterance(n, N_PROMPT, seed=rank * 100000 + i) for i, n in enumerate(n_tokens)]
+    tokens = [torch.from_numpy(u["token"][0]) for u in utts]
+    ptoks = [torch.from_numpy(u["prompt_token"][0]) for u in utts]
+    pfeats = [torch.from_numpy(u["prompt_feat"][0]) for u in utts]
+    embs = [torch.from_numpy(u["embedding"][0]) for u in utts]
+    audio_s = sum(2 * n * 480 for n in n_tokens) / 24000.0
+    B = len(n_tokens)
+    max_total = max(n_tokens) + N_PROMPT
+    mel_T = 2 * max(n_tokens)
+
+    # device-resident inputs for the kernel-only measurement
+    tok_d = torch.zeros(B, max(n_tokens), dtype=torch.int32)
+    for b, t in enumerate(tokens):
+        tok_d[b, :t.numel()] = t
+    tok_d = tok_d.to(dev)
+    ptk_d = torch.stack(ptoks).to(torch.int32).to(dev)
+    pf_d = torch.stack(pfeats).to(dev)
+    emb_d = torch.stack(embs).to(dev)
+    tl_d = torch.tensor(n_tokens, dtype=torch.int32, device=dev)
+    pl_d = torch.full((B,), N_PROMPT, dtype=torch.int32, device=dev)
+    fl_d = torch.full((B,), 2 * N_PROMPT, dtype=torch.int32, device=dev)
+    mel_lens_d = (tl_d * 2).contiguous()
+
+    def step_resident():
+        (mel,) = flow._forward_device(tok_d, tl_d, ptk_d, pl_d, pf_d, fl_d, emb_d, B, max_total, mel_T, False, True)
+        n1 = eng.last_launches()
+        speech, _ = hift.inference(mel, lens=mel_lens_d)
+        return speech, n1 + eng.last_launches()
+
+    def step_e2e():
+        speech, lens = t2w.token2wav_batch(tokens, ptoks, pfeats, embs)
+        out = speech.cpu()                                   # D2H of the step's result
+        if world > 1:                                        # final gather of (lengths, padded audio) on rank 0
+            lens_g = [torch.empty_like(lens.to(dev)) for _ in range(world)] if rank == 0 else None
+            dist.gather(lens.to(dev), lens_g, dst=0)
+            aud_g = [torch.empty_like(speech) for _ in range(world)] if rank == 0 else None
+            dist.gather(speech, aud_g, dst=0)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        _, launches_per_step = step_resident()
+    barrier()
+
+    # ---- timed region 1: device-resident inputs, CUDA events, per-family profiling on ----
+    stop, clk = threading.Event(), []
+    th = threading.Thread(target=sample_clocks, args=(stop, clk), daemon=True)
+    th.start()
+    import ctypes as C
+    eng.lib.cv2_engine_set_profiling(eng.h, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    fam_ms = (C.c_double * len(FAMILIES))()
+    fam_n = (C.c_longlong * len(FAMILIES))()
+    eng.lib.cv2_engine_read_profile(eng.h, fam_ms, fam_n, len(FAMILIES))
+    eng.lib.cv2_engine_set_profiling(eng.h, 0)
+
+    # ---- timed region 2: end to end through the public API with host buffers ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    stop.set()
+    h2d = flow.last_h2d_bytes
+    d2h = out.numel() * 4 + 4 * B
+
+    # ---- configs[1]: batch-1 latency / RTF (single 10 s utterance) ----
+    u1 = weights.make_utterance(250, N_PROMPT, seed=99)
+    a1 = [torch.from_numpy(u1[k][0]) for k in ("token", "prompt_token", "prompt_feat", "embedding")]
+    for _ in range(3):
+        t2w.token2wav_batch([a1[0]], [a1[1]], [a1[2]], [a1[3]])
+    torch.cuda.synchronize()
+    lat = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        w, _ = t2w.token2wav_batch([a1[0]], [a1[1]], [a1[2]], [a1[3]])
+        w.cpu()
+        lat.append(time.perf_counter() - t0)
+    lat1 = float(np.median(lat))
+
+    # ---- reduce over ranks ----
+    t_max = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    aud = torch.tensor([audio_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(aud, op=dist.ReduceOp.SUM)
+    ms, ms_e2e = float(t_max[0]), float(t_max[1])
+    total_audio = float(aud[0])
+
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        flops = algorithmic_flops(n_tokens)
+        fam = {n: {"ms_per_step": fam_ms[i] / args.steps, "launches_per_step": fam_n[i] / args.steps,
+                   "algorithmic_tflop_per_step": flops[n] / 1e12,
+                   "tflops": (flops[n] / 1e12) / (fam_ms[i] / args.steps / 1e3) if fam_ms[i] > 0 else None}
+               for i, n in enumerate(FAMILIES) if fam_n[i] > 0}
+        dom = max(fam, key=lambda n: fam[n]["ms_per_step"])
+        d = fam[dom]
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        ach = d["tflops"] or 0.0
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src + " sustained dense bf16 (kernel timed inside a long step)",
+                    "avg_launch_ms": d["ms_per_step"] / d["launches_per_step"],
+                    "algorithmic_gflop_per_launch": 1e3 * d["algorithmic_tflop_per_step"] / d["launches_per_step"],
+                    "share_of_step": d["ms_per_step"] / (ms / args.steps)}
+        total_flop = sum(flops.values()) * world
+        line = {
+            "metric": "token2wav_audio_seconds_per_second", "value": total_audio * args.steps / (ms / 1e3), "unit": "audio-s/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp16 operands, fp32 accumulate (tcgen05 kind::f16)",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2] per GPU: 64 utterances, durations U[4,20] s (100-500 tokens) + 75-token "
+                                   "prompt, offline token2wav, 10 Euler steps with CFG, length-sorted ragged batch",
+                       "utterances_per_gpu": B, "audio_seconds_per_step_per_gpu": audio_s, "parallelism": f"utterance-sharded dp{world}",
+                       "l2": "per-step working set (GBs of activations) is far larger than the 126 MB L2; no explicit flush",
+                       "weights": "random-init CosyVoice2-0.5B-EU architecture (synth/weights.py)"},
+            "e2e": {"value": total_audio * args.steps / (ms_e2e / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": roofline,
+            "families": fam,
+            "whole_step_tflops": total_flop / 1e12 / (ms / args.steps / 1e3) / world,
+            "rtf_batch1": {"workload": "BASELINE configs[1]: single 10 s utterance (250 tokens + 75-token prompt), batch 1",
+                           "latency_s": lat1, "rtf": lat1 / 10.0, "audio_s_per_s": 10.0 / lat1},
+            "clocks": clocks_summary(clk),
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count()
+            dt, a = cpu_reference_run(200, cores)
+            line["cpu_baseline"] = {"value": a / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                    "sample": "one 8 s utterance (200 tokens + 75-token prompt, configs[0]) run once through the "
+                                              "oracle port of the reference CPU token2wav (torch fp32, all host threads)",
+                                    "seconds": dt}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

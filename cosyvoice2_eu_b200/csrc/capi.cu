@@ -94,6 +94,36 @@ int cv2_engine_finalize(cv2_engine* h, int need_flow, int need_hift) {
 
 long long cv2_engine_last_launches(cv2_engine* h) { return h ? h->e.launches : -1; }
 
+int cv2_engine_set_profiling(cv2_engine* h, int on) {
+  CV2_API_BEGIN
+  CV2_CHECK(h, "null engine");
+  h->e.profiling = on != 0;
+  h->e.prof.clear();
+  h->e.ev_used = 0;
+  CV2_API_END
+}
+
+int cv2_engine_read_profile(cv2_engine* h, double* ms_per_family, long long* launches_per_family, int n_families) {
+  CV2_API_BEGIN
+  CV2_CHECK(h && ms_per_family && launches_per_family, "null argument");
+  for (int i = 0; i < n_families; i++) {
+    ms_per_family[i] = 0.0;
+    launches_per_family[i] = 0;
+  }
+  for (auto& r : h->e.prof) {
+    CV2_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    CV2_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    if (r.family < n_families) {
+      ms_per_family[r.family] += ms;
+      launches_per_family[r.family]++;
+    }
+  }
+  h->e.prof.clear();
+  h->e.ev_used = 0;
+  CV2_API_END
+}
+
 size_t cv2_estimator_workspace_bytes(cv2_engine* h, int B2, int T) {
   try {
     Arena ws;

@@ -69,6 +69,33 @@ struct Engine {
   std::unordered_map<uint64_t, CUtensorMap> amap_cache;  // activation tensor maps
   long long launches = 0;                                // kernels launched by the last forward (claims for bench)
 
+  // ---- optional per-launch timing (CUDA events on the launching stream), grouped by kernel family ----
+  enum Family { F_GEMM64 = 0, F_GEMM128, F_GEMM256, F_FLASH_ATTN, F_REL_ATTN, F_F0_CONV, F_NSF, F_STFT, F_SRC_DOWN, F_ISTFT,
+                F_LAYERNORM, F_COUNT };
+  bool profiling = false;
+  struct ProfRec { int family; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  cudaEvent_t next_event() {
+    if (ev_used == ev_pool.size()) {
+      cudaEvent_t ev;
+      CV2_CUDA(cudaEventCreate(&ev));
+      ev_pool.push_back(ev);
+    }
+    return ev_pool[ev_used++];
+  }
+  void prof_begin(cudaStream_t st, int family) {
+    if (!profiling) return;
+    ProfRec r{family, next_event(), next_event()};
+    CV2_CUDA(cudaEventRecord(r.a, st));
+    prof.push_back(r);
+  }
+  void prof_end(cudaStream_t st) {
+    if (!profiling) return;
+    CV2_CUDA(cudaEventRecord(prof.back().b, st));
+  }
+
   const TensorRef& T(const std::string& name) const {
     auto it = tensors.find(name);
     if (it == tensors.end()) fail("engine: tensor '%s' was not registered", name.c_str());

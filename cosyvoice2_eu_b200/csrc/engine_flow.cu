@@ -111,7 +111,11 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
         ap.q = b.Q16; ap.k = b.K16; ap.vt = b.VT16; ap.out = b.ATT16;
         ap.lens = lens; ap.S = S; ap.heads = 8; ap.T_alloc = T; ap.chunk = streaming ? 50 : 0; ap.halo = kHalo;
         e.launches++;
-        if (!dry) launch_flash_attn(ap, st);
+        if (!dry) {
+          e.prof_begin(st, Engine::F_FLASH_ATTN);
+          launch_flash_attn(ap, st);
+          e.prof_end(st);
+        }
       }
       {  // out-proj + bias + residual ; emit LN(norm3)
         GemmParams p = base_params(lens);
@@ -242,7 +246,11 @@ static void enc_layer(Engine& e, cudaStream_t st, const EncBuffers& b, const std
     ap.qkv = b.QKV32; ap.pos = b.POS32; ap.bias_u = e.f32(lp + ".bias_u"); ap.bias_v = e.f32(lp + ".bias_v");
     ap.out = b.ATT16; ap.lens = lens; ap.S = S; ap.T_alloc = T; ap.Tmax = T; ap.chunk = chunk;
     e.launches++;
-    if (!dry) launch_rel_attn(ap, st);
+    if (!dry) {
+      e.prof_begin(st, Engine::F_REL_ATTN);
+      launch_rel_attn(ap, st);
+      e.prof_end(st);
+    }
   }
   {  // linear_out + residual
     GemmParams p = base_params(lens);

@@ -72,17 +72,23 @@ size_t hift_forward(Engine& e, cudaStream_t st, const HiftArgs& a, Arena& ws) {
     for (int l = 0; l < 5; l++) {
       const std::string n = "f0.c" + std::to_string(l);
       float* out = (l & 1) ? FB : FA;
+      e.prof_begin(st, Engine::F_F0_CONV);
       launch_conv3_elu_f32(cur, cin, e.f32(n + ".w"), e.f32(n + ".b"), out, 512, lens[0], 0, B, Ta[0], st);
+      e.prof_end(st);
       cur = out;
       cin = 512;
     }
     launch_f0_head(cur, e.f32("f0.cls.w"), e.f32("f0.cls.b"), F0, lens[0], 0, B, Ta[0], Ta[0], st);
     if (a.f0_out) CV2_CUDA(cudaMemcpy2DAsync(a.f0_out, (size_t)a.mel_T * 4, F0, (size_t)Ta[0] * 4, (size_t)a.mel_T * 4, B,
                                              cudaMemcpyDeviceToDevice, st));
+    e.prof_begin(st, Engine::F_NSF);
     launch_nsf_source(F0, Ta[0], PH, Ta[0], lens[0], 0, a.noise, (long long)480 * a.mel_T * 9, a.seed, e.f32("hift.src.lw"),
                       e.f32("hift.src.lb"), a.cache_source, a.cache_len, a.cache_len, a.source, (long long)480 * a.mel_T, B,
                       a.mel_T, st);
+    e.prof_end(st);
+    e.prof_begin(st, Engine::F_STFT);
     launch_source_stft(a.source, (long long)480 * a.mel_T, lens[0], 0, STFT, Ta[3], B, st);
+    e.prof_end(st);
   }
 
   // ---- conv_pre (k7) + leaky_relu(0.1) -> U16 ----
@@ -134,8 +140,10 @@ size_t hift_forward(Engine& e, cudaStream_t st, const HiftArgs& a, Arena& ws) {
     e.launches++;
     if (!dry) {
       const std::string dn = "hift.sd." + std::to_string(i);
+      e.prof_begin(st, Engine::F_SRC_DOWN);
       launch_source_down(STFT, Ta[3], e.f32(dn + ".w"), e.f32(dn + ".b"), sd_k[i], sd_s[i], sd_p[i], C, lens[0], 0, sd_fpl[i],
                          sd_add[i], SI32, S16, e.f32(sp + ".a1.0"), B, T, st);
+      e.prof_end(st);
     }
     const int bnc = C >= 256 ? 256 : C;
     // source ResBlock; its last conv also adds the upsampled main path and emits the three ResBlock inputs
@@ -211,7 +219,11 @@ size_t hift_forward(Engine& e, cudaStream_t st, const HiftArgs& a, Arena& ws) {
     e.gemm(st, up_in, B, Ta[3], 64, 64, e.W("hift.conv_post"), 64, 7, taps, p, dry);
   }
   e.launches++;
-  if (!dry) launch_istft(CP32, Ta[3], 18, lens[0], 0, a.speech, (long long)480 * a.mel_T, B, a.mel_T, st);
+  if (!dry) {
+    e.prof_begin(st, Engine::F_ISTFT);
+    launch_istft(CP32, Ta[3], 18, lens[0], 0, a.speech, (long long)480 * a.mel_T, B, a.mel_T, st);
+    e.prof_end(st);
+  }
   return ws.peak;
 }
 

@@ -151,6 +151,19 @@ class B200Flow:
                                                       _lib.ptr(ws), ws.numel()))
         return out
 
+    def _staging(self, name, shape, dtype):
+        """Zeroed pinned host buffer, cached per (name, shape)."""
+        key = (name, tuple(shape), torch.cuda.current_stream().cuda_stream)
+        cache = self.__dict__.setdefault("_pinned", {})
+        buf = cache.get(key)
+        if buf is None:
+            buf = torch.zeros(*shape, dtype=dtype).pin_memory()
+            cache[key] = buf
+        else:
+            torch.cuda.current_stream().synchronize()   # previous async copy out of this buffer must have finished
+            buf.zero_()
+        return buf
+
     # ---- batched flow ----
     def inference_batch(self, tokens, prompt_tokens, prompt_feats, embeddings, streaming=False, finalize=True,
                         return_intermediates=False):
@@ -166,15 +179,20 @@ class B200Flow:
         mel_lens = [2 * (a + b - drop) - c for a, b, c in zip(tl, pl, fl)]
         mel_T = max(mel_lens)
         assert min(mel_lens) > 0
-        tok = torch.zeros(B, max(tl), dtype=torch.int32)
-        ptk = torch.zeros(B, max(max(pl), 1), dtype=torch.int32)
-        pf = torch.zeros(B, max(max(fl), 1), 80, dtype=torch.float32)
+        # pinned staging buffers -> async H2D on the current stream
+        tok = self._staging("tok", (B, max(tl)), torch.int32)
+        ptk = self._staging("ptk", (B, max(max(pl), 1)), torch.int32)
+        pf = self._staging("pf", (B, max(max(fl), 1), 80), torch.float32)
         for b in range(B):
             tok[b, :tl[b]] = tokens[b].reshape(-1).to(torch.int32).cpu()
             ptk[b, :pl[b]] = prompt_tokens[b].reshape(-1).to(torch.int32).cpu()
             pf[b, :fl[b]] = prompt_feats[b].reshape(-1, 80).float().cpu()
-        emb = torch.stack([e.reshape(192).float().cpu() for e in embeddings])
-        lens = torch.tensor([tl, pl, fl], dtype=torch.int32)
+        emb = self._staging("emb", (B, 192), torch.float32)
+        for b in range(B):
+            emb[b] = embeddings[b].reshape(192).float().cpu()
+        lens = self._staging("lens", (3, B), torch.int32)
+        lens.copy_(torch.tensor([tl, pl, fl], dtype=torch.int32))
+        self.last_h2d_bytes = sum(a.numel() * a.element_size() for a in (tok, ptk, pf, emb, lens))
         tok, ptk, pf, emb, lens = (a.to(dev, non_blocking=True) for a in (tok, ptk, pf, emb, lens))
         return self._forward_device(tok, lens[0], ptk, lens[1], pf, lens[2], emb, B, max_total, mel_T, streaming, finalize,
                                     return_intermediates) + (torch.tensor(mel_lens, dtype=torch.int32),)

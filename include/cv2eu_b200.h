@@ -40,6 +40,11 @@ int cv2_engine_finalize(cv2_engine* e, int need_flow, int need_hift);
 /* kernels launched by the most recent forward on this engine */
 long long cv2_engine_last_launches(cv2_engine* e);
 
+/* per-launch CUDA-event timing on the launching stream, summed per kernel family (bench.py roofline):
+ * 0 gemm<64> 1 gemm<128> 2 gemm<256> 3 flash_attn 4 rel_attn 5 f0_conv 6 nsf_source 7 source_stft 8 source_down 9 istft 10 layernorm */
+int cv2_engine_set_profiling(cv2_engine* e, int on);
+int cv2_engine_read_profile(cv2_engine* e, double* ms_per_family, long long* launches_per_family, int n_families);
+
 /* ---- estimator: CausalConditionalDecoder.forward (cosyvoice/flow/decoder.py:405-494), the reference's TRT slot
  *      (flow_matching.py:125-150).  x, mu, cond: [B2,80,T]; mask: [B2,1,T] (prefix of ones); t: [B2]; spks: [B2,80];
  *      out: [B2,80,T] (may alias x).  All fp32, contiguous, on the device. ---- */

@@ -176,7 +176,8 @@ def test_flash_attention(chunk):
     qd, kd = q.cuda(), k.cuda()
     vtd = v.transpose(2, 3).contiguous().cuda()
     out = torch.zeros(S, T, H * D, dtype=torch.float16, device="cuda")
-    lib.check(L.cv2_op_flash_attn(_s(), lib.ptr(qd), lib.ptr(kd), lib.ptr(vtd), lib.ptr(out), lib.ptr(lens.cuda()), 0, S, H, T, chunk))
+    lens_d = lens.cuda()
+    lib.check(L.cv2_op_flash_attn(_s(), lib.ptr(qd), lib.ptr(kd), lib.ptr(vtd), lib.ptr(out), lib.ptr(lens_d), 0, S, H, T, chunk))
     torch.cuda.synchronize()
     err = float((out.float().cpu() - ref).abs().max())
     assert err < 5e-3, err
@@ -206,8 +207,9 @@ def test_rel_attention(chunk):
     pos = F.linear(O.rel_pos_table(Tal)[0], p["linear_pos.weight"])          # rows: rel = Tal-1 ... -(Tal-1)
     pos = torch.flip(pos, [0]).contiguous()                                  # -> row r <-> rel = r - (Tal-1)
     out = torch.zeros(S, Tal, 512, dtype=torch.float16, device="cuda")
-    lib.check(L.cv2_op_rel_attn(_s(), lib.ptr(qkv.cuda()), lib.ptr(pos.cuda()), lib.ptr(p["pos_bias_u"].reshape(-1).cuda()),
-                                lib.ptr(p["pos_bias_v"].reshape(-1).cuda()), lib.ptr(out), lib.ptr(lens.cuda()), 0, S, Tal, Tal, chunk))
+    keep = [qkv.cuda(), pos.cuda(), p["pos_bias_u"].reshape(-1).cuda(), p["pos_bias_v"].reshape(-1).cuda(), lens.cuda()]
+    lib.check(L.cv2_op_rel_attn(_s(), lib.ptr(keep[0]), lib.ptr(keep[1]), lib.ptr(keep[2]), lib.ptr(keep[3]), lib.ptr(out),
+                                lib.ptr(keep[4]), 0, S, Tal, Tal, chunk))
     torch.cuda.synchronize()
     for s in range(S):
         n = int(lens[s])
@@ -227,11 +229,13 @@ def test_source_stft_and_istft():
     src = torch.tanh(torch.randn(B, 480 * T, generator=g))
     F_alloc = 120 * T + 1 + 63
     out = torch.zeros(B, F_alloc, 18, device="cuda")
-    lib.check(L.cv2_op_source_stft(_s(), lib.ptr(src.cuda()), T, lib.ptr(lens.cuda()), lib.ptr(out), F_alloc, B))
+    src_d, lens_d = src.cuda(), lens.cuda()
+    lib.check(L.cv2_op_source_stft(_s(), lib.ptr(src_d), T, lib.ptr(lens_d), lib.ptr(out), F_alloc, B))
     cp = torch.randn(B, F_alloc, 18, generator=g) * 1.5
     cp[:, :, 0] += 4.0      # push one bin through the 1e2 clip
     wav = torch.zeros(B, 480 * T, device="cuda")
-    lib.check(L.cv2_op_istft(_s(), lib.ptr(cp.cuda()), F_alloc, lib.ptr(lens.cuda()), T, lib.ptr(wav), B))
+    cp_d = cp.cuda()
+    lib.check(L.cv2_op_istft(_s(), lib.ptr(cp_d), F_alloc, lib.ptr(lens_d), T, lib.ptr(wav), B))
     torch.cuda.synchronize()
     for b in range(B):
         n = int(lens[b])
@@ -260,8 +264,9 @@ def test_nsf_source():
     ref = O.nsf_source(sd, f0, noise)[:, 0]
     ph = torch.zeros(B, T, 9, device="cuda")
     src = torch.zeros(B, 480 * T, device="cuda")
-    lib.check(L.cv2_op_nsf_source(_s(), lib.ptr(f0.cuda()), T, None, lib.ptr(noise.cuda()), 0, lib.ptr(lw.reshape(-1).cuda()),
-                                  lib.ptr(lb.cuda()), lib.ptr(ph), lib.ptr(src), B))
+    keep = [f0.cuda(), noise.cuda(), lw.reshape(-1).cuda(), lb.cuda()]   # device pointers must outlive the launch
+    lib.check(L.cv2_op_nsf_source(_s(), lib.ptr(keep[0]), T, None, lib.ptr(keep[1]), 0, lib.ptr(keep[2]), lib.ptr(keep[3]),
+                                  lib.ptr(ph), lib.ptr(src), B))
     torch.cuda.synchronize()
     err = (src.cpu() - ref).abs()
     refd = ref.double().numpy()
