@@ -1,5 +1,11 @@
-// Tap GEMM kernel (see gemm_tap.cuh).  tcgen05.mma (kind::f16, fp32 accumulate in TMEM), operands staged by
-// TMA into 128B-swizzled shared memory through a 4-stage mbarrier ring.
+// Tap GEMM kernel (see gemm_tap.cuh).  Persistent, warp-specialised:
+//   warp 0      TMA producer: A/B k-blocks into a 4-stage 128B-swizzled smem ring (mbarrier full/empty)
+//   warp 1      tcgen05.mma issuer (kind::f16, fp32 accumulate) into a DOUBLE-BUFFERED TMEM accumulator
+//   warps 2-9   epilogue: 8 warps, two per TMEM lane quarter (each thread owns half a row), so the epilogue of tile i
+//               overlaps the MMAs of tile i+1; LayerNorm statistics are combined between the two half-row threads
+//               through shared memory.
+// Each CTA walks tiles blockIdx.x, +gridDim.x, ... in (n fastest, then t, then sequence) order and skips tiles that lie
+// entirely in a sequence's padding.
 #include "common.cuh"
 #include "gemm_tap.cuh"
 #include "host_util.h"
@@ -10,30 +16,68 @@ static constexpr int kStages = 4;
 static constexpr int kTileM = 128;
 static constexpr int kKBlock = 64;                       // 64 x 16-bit = one 128B swizzle row
 static constexpr int kABytes = kTileM * kKBlock * 2;     // 16 KB
+static constexpr int kEpiWarps = 8;
+static constexpr int kThreads = 64 + kEpiWarps * 32;     // 320
 
 template <int BN>
 struct GemmSmem {
   static constexpr int kBBytes = BN * kKBlock * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOff = kStages * kStageBytes;
-  static constexpr int kTotal = kBarOff + 128 + 1024;    // barriers + alignment slack
+  static constexpr int kRedOff = kStages * kStageBytes;           // 4 x [2][128] floats for LayerNorm exchanges
+  static constexpr int kBarOff = kRedOff + 4 * 2 * 128 * 4;
+  static constexpr int kTotal = kBarOff + 256 + 1024;             // barriers + alignment slack
 };
 
-__device__ __forceinline__ float apply_act(float v, int act, float f, float a) {
-  switch (act) {
-    case ACT_MISH: return mish_f(v);
-    case ACT_GELU: return gelu_erf_f(v);
-    case ACT_SILU: return silu_f(v);
-    case ACT_ELU: return elu_f(v);
-    case ACT_LRELU: return v > 0.f ? v : v * f;
-    case ACT_SNAKE: return snake_f(v, a);
-    default: return v;
-  }
+// ---- fast epilogue math (fp32) ----
+__device__ __forceinline__ float fast_mish(float x) {
+  // x * tanh(softplus(x)) = x * n / (n + 2), n = e^x (e^x + 2)
+  const float e = __expf(fminf(x, 20.f));
+  const float n = e * (e + 2.f);
+  const float y = __fdividef(x * n, n + 2.f);
+  return x > 20.f ? x : y;
+}
+__device__ __forceinline__ float fast_gelu_erf(float x) {
+  // exact-erf GELU; erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7)
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfz = 1.f - poly * t * __expf(-z * z);
+  return 0.5f * x * (1.f + copysignf(erfz, x));
+}
+__device__ __forceinline__ float fast_silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_snake(float x, float a) {
+  const float s = __sinf(x * a);
+  return fmaf(s * s, __fdividef(1.f, a + 1e-9f), x);
 }
 
-__device__ __forceinline__ void store_h32(__half* dst, const float* v, bool full, int nvalid) {
+// 32 consecutive floats starting at p (p 16B aligned when full)
+__device__ __forceinline__ void load32(const float* __restrict__ p, float* d, bool full, int nv) {
   if (full) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(p) + i);
+      d[i * 4 + 0] = f.x; d[i * 4 + 1] = f.y; d[i * 4 + 2] = f.z; d[i * 4 + 3] = f.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; i++) d[i] = (i < nv) ? __ldg(p + i) : 0.f;
+  }
+}
+__device__ __forceinline__ void store32_f32(float* __restrict__ p, const float* v, bool full, int nv) {
+  if (full) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) reinterpret_cast<float4*>(p)[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; i++)
+      if (i < nv) p[i] = v[i];
+  }
+}
+__device__ __forceinline__ void store32_f16(__half* __restrict__ p, const float* v, bool full, int nv) {
+  if (full) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       __half2 h0 = __floats2half2_rn(v[i * 8 + 0], v[i * 8 + 1]);
@@ -45,33 +89,52 @@ __device__ __forceinline__ void store_h32(__half* dst, const float* v, bool full
       u.y = *reinterpret_cast<uint32_t*>(&h1);
       u.z = *reinterpret_cast<uint32_t*>(&h2);
       u.w = *reinterpret_cast<uint32_t*>(&h3);
-      d4[i] = u;
+      reinterpret_cast<uint4*>(p)[i] = u;
     }
   } else {
-    for (int i = 0; i < nvalid; i++) dst[i] = __float2half_rn(v[i]);
+#pragma unroll
+    for (int i = 0; i < 32; i++)
+      if (i < nv) p[i] = __float2half_rn(v[i]);
   }
 }
 
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+
+struct TileCoord {
+  int n0, t0, s, len;
+};
+// tile -> coordinates; returns false when the tile lies entirely in the padding
+__device__ __forceinline__ bool tile_coord(const GemmParams& p, int tile, int n_tiles, int t_tiles, int BN, TileCoord& c) {
+  const int n = tile % n_tiles;
+  const int rest = tile / n_tiles;
+  const int tt = rest % t_tiles;
+  c.s = rest / t_tiles;
+  c.n0 = n * BN;
+  c.t0 = tt * kTileM;
+  c.len = p.lens ? __ldg(p.lens + c.s) : p.len_all;
+  return c.t0 < c.len + p.halo;
+}
+
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using SM = GemmSmem<BN>;
-  const int n0 = blockIdx.x * BN;
-  const int t0 = blockIdx.y * kTileM;
-  const int s = blockIdx.z;
-  const int len = p.lens ? p.lens[s] : p.len_all;
-  if (t0 >= len + p.halo) return;  // tile entirely in the padding: nothing reads it
-
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* red = reinterpret_cast<float*>(smem + SM::kRedOff);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::kBarOff);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty_bar + kStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_it = p.ntaps * p.kb_per_tap;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int t_tiles = p.T_alloc / kTileM;
+  const int total_tiles = n_tiles * t_tiles * p.S;
+  constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // 128 / 256 / 512
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -80,10 +143,13 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kEpiWarps);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -92,261 +158,334 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------- TMA producer -------------------------------
-      for (int it = 0; it < num_it; it++) {
-        const int st = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&empty_bar[st], ph ^ 1);
-        const int tap = it / p.kb_per_tap;
-        const int kb = it - tap * p.kb_per_tap;
-        uint8_t* a_dst = smem + st * SM::kStageBytes;
-        uint8_t* b_dst = a_dst + kABytes;
-        mbar_expect_tx(&full_bar[st], SM::kStageBytes);
-        tma_load_3d(a_dst, &tmA, &full_bar[st], kb * kKBlock, t0 + p.tap_off[tap], s);
-        tma_load_2d(b_dst, &tmB, &full_bar[st], it * kKBlock, n0);
+      int kit = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileCoord c;
+        if (!tile_coord(p, tile, n_tiles, t_tiles, BN, c)) continue;
+        for (int it = 0; it < num_it; it++, kit++) {
+          const int st = kit % kStages;
+          const uint32_t ph = (kit / kStages) & 1;
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          const int tap = it / p.kb_per_tap;
+          const int kb = it - tap * p.kb_per_tap;
+          uint8_t* a_dst = smem + st * SM::kStageBytes;
+          uint8_t* b_dst = a_dst + kABytes;
+          mbar_expect_tx(&full_bar[st], SM::kStageBytes);
+          tma_load_3d(a_dst, &tmA, &full_bar[st], kb * kKBlock, c.t0 + p.tap_off[tap], c.s);
+          tma_load_2d(b_dst, &tmB, &full_bar[st], it * kKBlock, c.n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------- MMA issuer ---------------------------------
       constexpr uint32_t idesc = umma_idesc_f16(kTileM, BN, 0);
-      for (int it = 0; it < num_it; it++) {
-        const int st = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&full_bar[st], ph);
+      int kit = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileCoord c;
+        if (!tile_coord(p, tile, n_tiles, t_tiles, BN, c)) continue;
+        const int acc = lt & 1;
+        mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + st * SM::kStageBytes);
-        const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
-        const uint64_t b_desc = umma_smem_desc_sw128(a_addr + kABytes);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int it = 0; it < num_it; it++, kit++) {
+          const int st = kit % kStages;
+          const uint32_t ph = (kit / kStages) & 1;
+          mbar_wait(&full_bar[st], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + st * SM::kStageBytes);
+          const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
+          const uint64_t b_desc = umma_smem_desc_sw128(a_addr + kABytes);
 #pragma unroll
-        for (int k = 0; k < kKBlock / 16; k++) {
-          // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
-          umma_f16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kKBlock / 16; k++)
+            umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[st]);
         }
-        umma_commit(&empty_bar[st]);  // frees this smem stage when the MMAs have read it
+        umma_commit(&tmem_full[acc]);
+        lt++;
       }
-      umma_commit(tmem_full);  // accumulator complete
     }
   } else {
     // --------------------------------- epilogue -----------------------------------
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;       // row inside the tile
-    const int t = t0 + r;
-    const bool valid = t < len;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int ncols = min(BN, p.N - n0);           // valid columns in this tile
-    const int nchunks = (ncols + 31) / 32;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-
-    float mean = 0.f, rstd = 1.f;
-    uint32_t raw[32];
-    if (p.ln) {  // LayerNorm over the N columns of this row (requires the whole row in one tile)
-      float sum = 0.f;
-      for (int c = 0; c < nchunks; c++) {
-        tmem_ld32(taddr + c * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i++) {
-          const int col = c * 32 + i;
-          if (col < ncols) sum += __uint_as_float(raw[i]) + (p.bias ? __ldg(p.bias + n0 + col) : 0.f);
-        }
-      }
-      mean = sum / (float)ncols;
-      float sq = 0.f;
-      for (int c = 0; c < nchunks; c++) {
-        tmem_ld32(taddr + c * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i++) {
-          const int col = c * 32 + i;
-          if (col < ncols) {
-            const float d = __uint_as_float(raw[i]) + (p.bias ? __ldg(p.bias + n0 + col) : 0.f) - mean;
-            sq += d * d;
-          }
-        }
-      }
-      rstd = rsqrtf(sq / (float)ncols + p.ln_eps);
-    }
-
+    const int ew = warp - 2;
+    const int q = warp & 3;              // TMEM lane quarter accessible to this warp
+    const int half = ew >> 2;            // which half of the tile's columns this thread owns
+    const int r = q * 32 + lane;
+    constexpr int kHalfCols = BN / 2;
+    constexpr int kChunks = kHalfCols / 32;   // 4 / 2 / 1
+    float* red_a = red;                  // [2][128] each
+    float* red_b = red + 256;
+    float* red_c = red + 512;
+    float* red_d = red + 768;
     bool stat2 = false;
 #pragma unroll
     for (int e = 0; e < 3; e++) stat2 |= (p.emit[e].kind == EMIT_LN);
-    float sum2 = 0.f;
-    const long long row = (long long)s * p.T_alloc + t;
-    const float* rv = p.rowvec ? p.rowvec + (long long)s * p.rowvec_ld : nullptr;
 
-    for (int c = 0; c < nchunks; c++) {
-      tmem_ld32(taddr + c * 32, raw);
-      tmem_ld_wait();
-      const int cbase = n0 + c * 32;
-      const int nv = min(32, ncols - c * 32);
-      const bool full = nv == 32;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      TileCoord c;
+      if (!tile_coord(p, tile, n_tiles, t_tiles, BN, c)) continue;
+      const int acc = lt & 1;
+      const int t = c.t0 + r;
+      const bool valid = t < c.len;
+      const int ncols = min(BN, p.N - c.n0);                         // valid columns of this tile
+      const int my_c0 = half * kHalfCols;                            // first column (within tile) of this thread
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + my_c0;
+      const long long row = (long long)c.s * p.T_alloc + t;
+      mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+      tc_fence_after();
+
+      float mean = 0.f, rstd = 1.f;
+      uint32_t raw[32];
       float v[32];
+      if (p.ln) {  // LayerNorm over the N columns of the row (whole row lives in this tile)
+        float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; i++) {
-        const int col = cbase + i;
-        float x = __uint_as_float(raw[i]);
-        if (i < nv) {
-          if (p.bias) x += __ldg(p.bias + col);
-          if (p.ln) x = (x - mean) * rstd * __ldg(p.ln_g + col) + __ldg(p.ln_b + col);
-          if (p.act) x = apply_act(x, p.act, p.act_f, p.act == ACT_SNAKE ? __ldg(p.act_a + col) : 0.f);
-          if (rv) x += __ldg(rv + col);
-          if (p.mask_pre_res && !valid) x = 0.f;
-        } else {
-          x = 0.f;
+        for (int ch = 0; ch < kChunks; ch++) {
+          const int cl = my_c0 + ch * 32;
+          const int nv = min(32, ncols - cl);
+          if (nv <= 0) break;
+          tmem_ld32(taddr + ch * 32, raw);
+          float bch[32];
+          load32(p.bias + c.n0 + cl, bch, nv == 32, nv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            if (i < nv) sum += __uint_as_float(raw[i]) + bch[i];
         }
-        v[i] = x;
-      }
-      if (p.res) {
-        const float* rp = p.res + row * p.res_ld + cbase;
-        if (full) {
+        red_a[half * 128 + r] = sum;
+        epi_bar();
+        mean = (red_a[r] + red_a[128 + r]) / (float)ncols;
+        float sq = 0.f;
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const float4 f = __ldg(reinterpret_cast<const float4*>(rp) + i);
-            v[i * 4 + 0] += f.x; v[i * 4 + 1] += f.y; v[i * 4 + 2] += f.z; v[i * 4 + 3] += f.w;
-          }
-        } else {
-          for (int i = 0; i < nv; i++) v[i] += __ldg(rp + i);
-        }
-      }
-      if (p.res2) {
-        const float* rp = p.res2 + row * p.res2_ld + cbase;
-        if (full) {
+        for (int ch = 0; ch < kChunks; ch++) {
+          const int cl = my_c0 + ch * 32;
+          const int nv = min(32, ncols - cl);
+          if (nv <= 0) break;
+          tmem_ld32(taddr + ch * 32, raw);
+          float bch[32];
+          load32(p.bias + c.n0 + cl, bch, nv == 32, nv);
+          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const float4 f = __ldg(reinterpret_cast<const float4*>(rp) + i);
-            v[i * 4 + 0] += f.x; v[i * 4 + 1] += f.y; v[i * 4 + 2] += f.z; v[i * 4 + 3] += f.w;
-          }
-        } else {
-          for (int i = 0; i < nv; i++) v[i] += __ldg(rp + i);
-        }
-      }
-      if (p.out_scale != 1.f) {
-#pragma unroll
-        for (int i = 0; i < 32; i++) v[i] *= p.out_scale;
-      }
-      if (p.out32) {
-        if (p.flat) {
-          // transposed conv: row t holds stride*Cout consecutive output elements of the sequence slab
-          const long long e0 = (long long)t * p.out32_ld + cbase + p.flat_off;
-          const long long hi = (long long)len * p.flat_hi_per_len + p.flat_hi_add;
-          if (e0 >= p.flat_lo && e0 + nv <= hi) {
-            float* op = p.out32 + (long long)s * p.flat_seq_elems + e0;
-            if (full) {
-#pragma unroll
-              for (int i = 0; i < 8; i++)
-                reinterpret_cast<float4*>(op)[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
-            } else {
-              for (int i = 0; i < nv; i++) op[i] = v[i];
+          for (int i = 0; i < 32; i++)
+            if (i < nv) {
+              const float d = __uint_as_float(raw[i]) + bch[i] - mean;
+              sq = fmaf(d, d, sq);
             }
-          }
-        } else {
-          float* op = p.out32 + row * p.out32_ld + cbase;
-          if (p.out32_accum) {
-            if (full) {
+        }
+        red_b[half * 128 + r] = sq;
+        epi_bar();
+        rstd = rsqrtf((red_b[r] + red_b[128 + r]) / (float)ncols + p.ln_eps);
+      }
+
+      float sum2 = 0.f;
+      const float* rv = p.rowvec ? p.rowvec + (long long)c.s * p.rowvec_ld : nullptr;
 #pragma unroll
-              for (int i = 0; i < 8; i++) {
-                const float4 f = reinterpret_cast<const float4*>(op)[i];
-                v[i * 4 + 0] += f.x; v[i * 4 + 1] += f.y; v[i * 4 + 2] += f.z; v[i * 4 + 3] += f.w;
-              }
-            } else {
-              for (int i = 0; i < nv; i++) v[i] += op[i];
-            }
-          }
-          if (full) {
+      for (int ch = 0; ch < kChunks; ch++) {
+        const int cl = my_c0 + ch * 32;          // column within the tile
+        const int nv = min(32, ncols - cl);
+        if (nv <= 0) break;
+        const bool full = nv == 32;
+        const int cbase = c.n0 + cl;              // global column
+        tmem_ld32(taddr + ch * 32, raw);
+        float tmp[32];
+        if (p.bias) load32(p.bias + cbase, tmp, full, nv);
+        tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; i++)
-              reinterpret_cast<float4*>(op)[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+        for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]);
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] += tmp[i];
+        }
+        if (p.ln) {
+          load32(p.ln_g + cbase, tmp, full, nv);
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = (v[i] - mean) * rstd * tmp[i];
+          load32(p.ln_b + cbase, tmp, full, nv);
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] += tmp[i];
+        }
+        switch (p.act) {
+          case ACT_MISH:
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = fast_mish(v[i]);
+            break;
+          case ACT_GELU:
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = fast_gelu_erf(v[i]);
+            break;
+          case ACT_SILU:
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = fast_silu(v[i]);
+            break;
+          case ACT_ELU:
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = elu_f(v[i]);
+            break;
+          case ACT_LRELU:
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = v[i] > 0.f ? v[i] : v[i] * p.act_f;
+            break;
+          case ACT_SNAKE:
+            load32(p.act_a + cbase, tmp, full, nv);
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = fast_snake(v[i], tmp[i]);
+            break;
+          default: break;
+        }
+        if (rv) {
+          load32(rv + cbase, tmp, full, nv);
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] += tmp[i];
+        }
+        if (p.mask_pre_res && !valid) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = 0.f;
+        }
+        if (p.res) {
+          load32(p.res + row * p.res_ld + cbase, tmp, full, nv);
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] += tmp[i];
+        }
+        if (p.res2) {
+          load32(p.res2 + row * p.res2_ld + cbase, tmp, full, nv);
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] += tmp[i];
+        }
+        if (p.out_scale != 1.f) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] *= p.out_scale;
+        }
+        if (!full) {
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            if (i >= nv) v[i] = 0.f;
+        }
+        if (p.out32) {
+          if (p.flat) {
+            // transposed conv: row t holds stride*Cout consecutive output elements of the sequence slab
+            const long long e0 = (long long)t * p.out32_ld + cbase + p.flat_off;
+            const long long hi = (long long)c.len * p.flat_hi_per_len + p.flat_hi_add;
+            if (e0 >= p.flat_lo && e0 + nv <= hi) store32_f32(p.out32 + (long long)c.s * p.flat_seq_elems + e0, v, full, nv);
           } else {
-            for (int i = 0; i < nv; i++) op[i] = v[i];
+            float* op = p.out32 + row * p.out32_ld + cbase;
+            if (p.out32_accum) {
+              load32(op, tmp, full, nv);
+#pragma unroll
+              for (int i = 0; i < 32; i++) v[i] += tmp[i];
+            }
+            store32_f32(op, v, full, nv);
           }
         }
-      }
-      // 16-bit emits (the next contraction's A operand); padded rows are written as zeros
-#pragma unroll
-      for (int e = 0; e < 3; e++) {
-        const Emit& em = p.emit[e];
-        if (em.kind == EMIT_NONE || em.kind == EMIT_LN) continue;
-        float w[32];
-#pragma unroll
-        for (int i = 0; i < 32; i++) {
-          float x = v[i];
-          if (em.kind == EMIT_SNAKE) x = (i < nv) ? snake_f(x, __ldg(em.a + cbase + i)) : 0.f;
-          else if (em.kind == EMIT_LRELU) x = x > 0.f ? x : x * em.f;
-          w[i] = valid ? x * em.scale : 0.f;
-        }
-        store_h32(em.ptr + row * em.ld + em.col_off + cbase, w, full, nv);
-      }
-      if (p.q) {  // attention operand split
-        const int hd = p.heads * 64;
-        const int which = cbase / hd;            // 0 q, 1 k, 2 v (a 32-col chunk never straddles)
-        const int cc = cbase - which * hd;
-        const int h = cc >> 6, d0 = cc & 63;
-        if (which < 2) {
-          float w[32];
-          const float sc = which == 0 ? p.q_scale : 1.f;
-#pragma unroll
-          for (int i = 0; i < 32; i++) w[i] = valid ? v[i] * sc : 0.f;
-          __half* dst = (which == 0 ? p.q : p.k) + (((long long)s * p.heads + h) * p.T_alloc + t) * 64 + d0;
-          store_h32(dst, w, true, 32);
-        } else {
-          __half* dst = p.vt + (((long long)s * p.heads + h) * 64 + d0) * p.T_alloc + t;
-#pragma unroll
-          for (int i = 0; i < 32; i++) dst[(long long)i * p.T_alloc] = __float2half_rn(valid ? v[i] : 0.f);
-        }
-      }
-      if (stat2) {
-#pragma unroll
-        for (int i = 0; i < 32; i++) {
-          sum2 += v[i];
-          raw[i] = __float_as_uint(v[i]);
-        }
-        tmem_st32(taddr + c * 32, raw);
-      }
-    }
-    if (stat2) {  // LayerNorm of the final row value (pre-norm of the next sub-block), emitted as 16-bit
-      tmem_st_wait();
-      const float mean2 = sum2 / (float)ncols;
-      float sq2 = 0.f;
-      for (int c = 0; c < nchunks; c++) {
-        tmem_ld32(taddr + c * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i++) {
-          if (c * 32 + i < ncols) {
-            const float d = __uint_as_float(raw[i]) - mean2;
-            sq2 += d * d;
-          }
-        }
-      }
-      for (int c = 0; c < nchunks; c++) {
-        tmem_ld32(taddr + c * 32, raw);
-        tmem_ld_wait();
-        const int cbase = n0 + c * 32;
-        const int nv = min(32, ncols - c * 32);
+        // 16-bit emits (the next contraction's A operand); padded rows are written as zeros
 #pragma unroll
         for (int e = 0; e < 3; e++) {
           const Emit& em = p.emit[e];
-          if (em.kind != EMIT_LN) continue;
-          const float rstd2 = rsqrtf(sq2 / (float)ncols + em.f);
+          if (em.kind == EMIT_NONE || em.kind == EMIT_LN) continue;
           float w[32];
+          if (em.kind == EMIT_SNAKE) {
+            load32(em.a + cbase, tmp, full, nv);
+#pragma unroll
+            for (int i = 0; i < 32; i++) w[i] = fast_snake(v[i], tmp[i]);
+          } else if (em.kind == EMIT_LRELU) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) w[i] = v[i] > 0.f ? v[i] : v[i] * em.f;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) w[i] = v[i];
+          }
+          const float sc = valid ? em.scale : 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; i++) w[i] *= sc;
+          store32_f16(em.ptr + row * em.ld + em.col_off + cbase, w, full, nv);
+        }
+        if (p.q) {  // attention operand split: q (pre-scaled) and k row-major per head, v transposed per head
+          const int hd = p.heads * 64;
+          const int which = cbase / hd;            // 0 q, 1 k, 2 v (a 32-col chunk never straddles)
+          const int cc = cbase - which * hd;
+          const int h = cc >> 6, d0 = cc & 63;
+          if (which < 2) {
+            const float sc = valid ? (which == 0 ? p.q_scale : 1.f) : 0.f;
+            float w[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) w[i] = v[i] * sc;
+            store32_f16((which == 0 ? p.q : p.k) + (((long long)c.s * p.heads + h) * p.T_alloc + t) * 64 + d0, w, true, 32);
+          } else {
+            __half* dst = p.vt + (((long long)c.s * p.heads + h) * 64 + d0) * p.T_alloc + t;
+#pragma unroll
+            for (int i = 0; i < 32; i++) dst[(long long)i * p.T_alloc] = __float2half_rn(valid ? v[i] : 0.f);
+          }
+        }
+        if (stat2) {
 #pragma unroll
           for (int i = 0; i < 32; i++) {
-            float x = 0.f;
-            if (i < nv && valid)
-              x = ((__uint_as_float(raw[i]) - mean2) * rstd2 * __ldg(em.a + cbase + i) + __ldg(em.b + cbase + i)) * em.scale;
-            w[i] = x;
+            sum2 += v[i];
+            raw[i] = __float_as_uint(v[i]);
           }
-          store_h32(em.ptr + row * em.ld + em.col_off + cbase, w, nv == 32, nv);
+          tmem_st32(taddr + ch * 32, raw);
         }
       }
+      if (stat2) {  // LayerNorm of the final row value (pre-norm of the next sub-block), emitted as 16-bit
+        tmem_st_wait();
+        red_c[half * 128 + r] = sum2;
+        epi_bar();
+        const float mean2 = (red_c[r] + red_c[128 + r]) / (float)ncols;
+        float sq2 = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ch++) {
+          const int nv = min(32, ncols - (my_c0 + ch * 32));
+          if (nv <= 0) break;
+          tmem_ld32(taddr + ch * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            if (i < nv) {
+              const float d = __uint_as_float(raw[i]) - mean2;
+              sq2 = fmaf(d, d, sq2);
+            }
+        }
+        red_d[half * 128 + r] = sq2;
+        epi_bar();
+        const float var2 = (red_d[r] + red_d[128 + r]) / (float)ncols;
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ch++) {
+          const int cl = my_c0 + ch * 32;
+          const int nv = min(32, ncols - cl);
+          if (nv <= 0) break;
+          const int cbase = c.n0 + cl;
+          tmem_ld32(taddr + ch * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 3; e++) {
+            const Emit& em = p.emit[e];
+            if (em.kind != EMIT_LN) continue;
+            const float rstd2 = rsqrtf(var2 + em.f);
+            float g[32], w[32];
+            load32(em.a + cbase, g, nv == 32, nv);
+#pragma unroll
+            for (int i = 0; i < 32; i++) w[i] = (__uint_as_float(raw[i]) - mean2) * rstd2 * g[i];
+            load32(em.b + cbase, g, nv == 32, nv);
+            const float sc = valid ? em.scale : 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i++) w[i] = (w[i] + g[i]) * sc;
+            store32_f16(em.ptr + row * em.ld + em.col_off + cbase, w, nv == 32, nv);
+          }
+        }
+      }
+      // release this accumulator buffer to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      lt++;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
+
+static int g_num_sms = 0;
 
 template <int BN>
 static void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
@@ -355,8 +494,16 @@ static void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
     CV2_CUDA(cudaFuncSetAttribute(gemm_tap_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
     configured = true;
   }
-  dim3 grid((p.N + BN - 1) / BN, p.T_alloc / kTileM, p.S);
-  gemm_tap_kernel<BN><<<grid, 192, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, p);
+  if (g_num_sms == 0) {
+    int dev = 0;
+    CV2_CUDA(cudaGetDevice(&dev));
+    CV2_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int total = ((p.N + BN - 1) / BN) * (p.T_alloc / kTileM) * p.S;
+  // persistent: one CTA per SM
+  const int per_sm = 1;
+  const int grid = total < g_num_sms * per_sm ? total : g_num_sms * per_sm;
+  gemm_tap_kernel<BN><<<grid, kThreads, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, p);
   CV2_LAUNCH_CHECK();
 }
 
@@ -366,6 +513,7 @@ void launch_gemm_tap(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, con
   bool wants_row = p.ln;
   for (int e = 0; e < 3; e++) wants_row |= (p.emit[e].kind == EMIT_LN);
   CV2_CHECK(!wants_row || p.N <= bn, "gemm_tap: LayerNorm epilogue needs the full row in one tile (N=%d, BN=%d)", p.N, bn);
+  CV2_CHECK(!p.ln || p.bias, "gemm_tap: LayerNorm epilogue expects a bias");
   CV2_CHECK(!p.q || (p.N == 3 * p.heads * 64), "gemm_tap: qkv split needs N == 3*heads*64");
   switch (bn) {
     case 64: launch_bn<64>(tmA, tmB, p, stream); break;
