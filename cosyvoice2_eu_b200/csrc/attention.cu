@@ -15,17 +15,17 @@ namespace cv2 {
 static constexpr int kQBytes = 128 * 64 * 2;   // 16 KB
 static constexpr int kKBytes = 128 * 64 * 2;   // 128 keys x 64 d
 static constexpr int kVBytes = 2 * 64 * 64 * 2;  // two [64 d x 64 keys] boxes
-static constexpr int kKVStages = 3;
+static constexpr int kKVStages = 2;
 static constexpr int kPBytes = 2 * 128 * 64 * 2;  // 128 rows x 128 keys, two K-atoms
 static constexpr int kOffK = kQBytes;
 static constexpr int kOffV = kOffK + kKVStages * kKBytes;
 static constexpr int kOffP = kOffV + kKVStages * kVBytes;
 static constexpr int kOffBar = kOffP + kPBytes;
-static constexpr int kAttnSmem = kOffBar + 256 + 1024;
+static constexpr int kAttnSmem = kOffBar + 256;   // 112.25 KB: two CTAs per SM
 
-static constexpr uint32_t kTmemS0 = 0, kTmemS1 = 128, kTmemO = 256;  // column offsets (512 allocated)
+static constexpr uint32_t kTmemS = 0, kTmemO = 128;   // column offsets (256 allocated: two CTAs share the SM's 512)
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   const int t0 = blockIdx.x * 128;
@@ -39,16 +39,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   if (p.chunk > 0) kv_end = min(len, ((t0 + 127) / p.chunk + 1) * p.chunk);
   const int nkt = (kv_end + 127) / 128;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // swizzle-128B tiles need 1024 B alignment
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars;              // 1
-  uint64_t* kv_full = bars + 1;         // 3  (K and V of a stage land on the same barrier)
-  uint64_t* kv_empty = bars + 4;        // 3
-  uint64_t* s_full = bars + 7;          // 2
-  uint64_t* p_full = bars + 9;          // 1 (128 arrivals)
-  uint64_t* pv_done = bars + 10;        // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* kv_full = bars + 1;         // 2  (K and V of a stage land on the same barrier)
+  uint64_t* kv_empty = bars + 3;        // 2
+  uint64_t* s_full = bars + 5;          // 1
+  uint64_t* p_full = bars + 6;          // 1 (128 arrivals)
+  uint64_t* pv_done = bars + 7;         // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -62,13 +61,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    mbar_init(&s_full[0], 1);
-    mbar_init(&s_full[1], 1);
+    mbar_init(s_full, 1);
     mbar_init(p_full, 128);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -99,17 +97,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mbar_wait(&kv_full[st], (j / kKVStages) & 1);
         tc_fence_after();
         const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(smem + kOffK + st * kKBytes));
-        const uint32_t d = tmem_base + ((j & 1) ? kTmemS1 : kTmemS0);
+        const uint32_t d = tmem_base + kTmemS;
 #pragma unroll
         for (int k = 0; k < 4; k++) umma_f16(d, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0);
-        umma_commit(&s_full[j & 1]);
+        umma_commit(s_full);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
       for (int j = 0; j < nkt; j++) {
-        // S buffer (j+1)&1 was last read by softmax j-1, whose p_full arrival we consumed in iteration j-1
-        if (j + 1 < nkt) issue_s(j + 1);
-        mbar_wait(p_full, j & 1);
+        mbar_wait(p_full, j & 1);   // softmax j has consumed S_j and written P_j
         tc_fence_after();
         const int st = j % kKVStages;
         const uint32_t v_addr = smem_u32(smem + kOffV + st * kVBytes);
@@ -123,6 +119,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         umma_commit(&kv_empty[st]);
         umma_commit(pv_done);
+        if (j + 1 < nkt) issue_s(j + 1);   // the co-resident CTA keeps the tensor pipe busy meanwhile
       }
     }
   } else {
@@ -137,21 +134,28 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     uint32_t raw[32];
     uint8_t* prow = smem + kOffP + r * 128;
     for (int j = 0; j < nkt; j++) {
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const uint32_t s_addr = lane_addr + ((j & 1) ? kTmemS1 : kTmemS0);
+      const uint32_t s_addr = lane_addr + kTmemS;
       const int kbase = j * 128;
       // pass A: row max over the visible keys of this tile
       float mx = -INFINITY;
+      const bool all_visible = kbase + 128 <= kv_lim;   // no masking needed inside this tile for this row
+#pragma unroll
       for (int c = 0; c < 4; c++) {
         tmem_ld32(s_addr + c * 32, raw);
         tmem_ld_wait();
+        if (all_visible) {
 #pragma unroll
-        for (int i = 0; i < 32; i++)
-          if (kbase + c * 32 + i < kv_lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            if (kbase + c * 32 + i < kv_lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        }
       }
       const float m_new = fmaxf(m, mx);
-      const float alpha = (m == -INFINITY) ? 0.f : exp2f((m - m_new) * LOG2E);
+      const float alpha = (m == -INFINITY) ? 0.f : fast_exp2((m - m_new) * LOG2E);
       // PV of the previous tile must be complete before O is rescaled or P overwritten
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);
@@ -170,16 +174,23 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       l *= alpha;
       // pass B: probabilities -> 16-bit P tile in the swizzled K-major layout
       const float mscaled = (m_new == -INFINITY) ? 0.f : m_new * LOG2E;
+#pragma unroll
       for (int c = 0; c < 4; c++) {
         tmem_ld32(s_addr + c * 32, raw);
         tmem_ld_wait();
         float pv[32];
+        if (all_visible) {
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-          const float e = (kbase + c * 32 + i < kv_lim) ? exp2f(__uint_as_float(raw[i]) * LOG2E - mscaled) : 0.f;
-          pv[i] = e;
-          l += e;
+          for (int i = 0; i < 32; i++) pv[i] = fast_exp2(fmaf(__uint_as_float(raw[i]), LOG2E, -mscaled));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            pv[i] = (kbase + c * 32 + i < kv_lim) ? fast_exp2(fmaf(__uint_as_float(raw[i]), LOG2E, -mscaled)) : 0.f;
         }
+        float ls = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i++) ls += pv[i];
+        l += ls;
         uint8_t* atom = prow + (c >> 1) * 16384;
         const int g0 = (c & 1) * 4;
 #pragma unroll
@@ -232,7 +243,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
 void launch_flash_attn(const AttnParams& p, cudaStream_t stream) {

@@ -178,6 +178,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int ab_fmt /
 // ------------------------------------------------------------------------------------------
 // math
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float mish_f(float x) {
   // x * tanh(softplus(x)); softplus with PyTorch's threshold 20
   float sp = x > 20.f ? x : log1pf(__expf(x));
