@@ -115,7 +115,20 @@ __device__ __forceinline__ bool tile_coord(const GemmParams& p, int tile, int n_
   return c.t0 < c.len + p.halo;
 }
 
-template <int BN>
+// Compile-time epilogue configuration.  Every field is -1 (decided at run time from GemmParams: the generic kernel) or a
+// fixed value; fixing them removes the untaken branches from the instruction stream (the generic epilogue is ~160 KB of
+// SASS and was instruction-cache bound).  Hot estimator / HiFT epilogues get their own instantiation (see kSpecs).
+template <int ACT_, int BIAS_, int LN_, int ROWVEC_, int MASK_, int RES_, int RES2_, int OUT32_, int ACCUM_, int FLAT_,
+          int SCALE_, int EMIT0_, int EMIT1_, int EMIT2_, int QKV_>
+struct EpiCfg {
+  static constexpr int ACT = ACT_, BIAS = BIAS_, LN = LN_, ROWVEC = ROWVEC_, MASK = MASK_, RES = RES_, RES2 = RES2_,
+                       OUT32 = OUT32_, ACCUM = ACCUM_, FLAT = FLAT_, SCALE = SCALE_, EMIT0 = EMIT0_, EMIT1 = EMIT1_,
+                       EMIT2 = EMIT2_, QKV = QKV_;
+};
+using EpiGeneric = EpiCfg<-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1>;
+#define CFGB(field, rt) (Cfg::field < 0 ? (rt) : (Cfg::field != 0))
+
+template <int BN, class Cfg>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using SM = GemmSmem<BN>;
@@ -217,9 +230,22 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float* red_b = red + 256;
     float* red_c = red + 512;
     float* red_d = red + 768;
-    bool stat2 = false;
-#pragma unroll
-    for (int e = 0; e < 3; e++) stat2 |= (p.emit[e].kind == EMIT_LN);
+    const int ek0 = Cfg::EMIT0 < 0 ? p.emit[0].kind : Cfg::EMIT0;
+    const int ek1 = Cfg::EMIT1 < 0 ? p.emit[1].kind : Cfg::EMIT1;
+    const int ek2 = Cfg::EMIT2 < 0 ? p.emit[2].kind : Cfg::EMIT2;
+    const bool stat2 = ek0 == EMIT_LN || ek1 == EMIT_LN || ek2 == EMIT_LN;
+    const bool has_bias = CFGB(BIAS, p.bias != nullptr);
+    const bool has_ln = CFGB(LN, p.ln != 0);
+    const int act = Cfg::ACT < 0 ? p.act : Cfg::ACT;
+    const bool has_rv = CFGB(ROWVEC, p.rowvec != nullptr);
+    const bool has_mask = CFGB(MASK, p.mask_pre_res != 0);
+    const bool has_res = CFGB(RES, p.res != nullptr);
+    const bool has_res2 = CFGB(RES2, p.res2 != nullptr);
+    const bool has_out32 = CFGB(OUT32, p.out32 != nullptr);
+    const bool has_accum = CFGB(ACCUM, p.out32_accum != 0);
+    const bool is_flat = CFGB(FLAT, p.flat != 0);
+    const bool has_scale = CFGB(SCALE, p.out_scale != 1.f);
+    const bool has_qkv = CFGB(QKV, p.q != nullptr);
 
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -238,9 +264,9 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float mean = 0.f, rstd = 1.f;
       uint32_t raw[32];
       float v[32];
-      if (p.ln) {  // LayerNorm over the N columns of the row (whole row lives in this tile)
+      if (has_ln) {  // LayerNorm over the N columns of the row (whole row lives in this tile)
         float sum = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int ch = 0; ch < kChunks; ch++) {
           const int cl = my_c0 + ch * 32;
           const int nv = min(32, ncols - cl);
@@ -257,7 +283,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         epi_bar();
         mean = (red_a[r] + red_a[128 + r]) / (float)ncols;
         float sq = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int ch = 0; ch < kChunks; ch++) {
           const int cl = my_c0 + ch * 32;
           const int nv = min(32, ncols - cl);
@@ -279,8 +305,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
 
       float sum2 = 0.f;
-      const float* rv = p.rowvec ? p.rowvec + (long long)c.s * p.rowvec_ld : nullptr;
-#pragma unroll
+      const float* rv = has_rv ? p.rowvec + (long long)c.s * p.rowvec_ld : nullptr;
+#pragma unroll 1
       for (int ch = 0; ch < kChunks; ch++) {
         const int cl = my_c0 + ch * 32;          // column within the tile
         const int nv = min(32, ncols - cl);
@@ -289,15 +315,15 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int cbase = c.n0 + cl;              // global column
         tmem_ld32(taddr + ch * 32, raw);
         float tmp[32];
-        if (p.bias) load32(p.bias + cbase, tmp, full, nv);
+        if (has_bias) load32(p.bias + cbase, tmp, full, nv);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]);
-        if (p.bias) {
+        if (has_bias) {
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] += tmp[i];
         }
-        if (p.ln) {
+        if (has_ln) {
           load32(p.ln_g + cbase, tmp, full, nv);
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] = (v[i] - mean) * rstd * tmp[i];
@@ -305,7 +331,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] += tmp[i];
         }
-        switch (p.act) {
+        switch (act) {
           case ACT_MISH:
 #pragma unroll
             for (int i = 0; i < 32; i++) v[i] = fast_mish(v[i]);
@@ -333,26 +359,26 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             break;
           default: break;
         }
-        if (rv) {
+        if (has_rv) {
           load32(rv + cbase, tmp, full, nv);
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] += tmp[i];
         }
-        if (p.mask_pre_res && !valid) {
+        if (has_mask && !valid) {
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] = 0.f;
         }
-        if (p.res) {
+        if (has_res) {
           load32(p.res + row * p.res_ld + cbase, tmp, full, nv);
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] += tmp[i];
         }
-        if (p.res2) {
+        if (has_res2) {
           load32(p.res2 + row * p.res2_ld + cbase, tmp, full, nv);
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] += tmp[i];
         }
-        if (p.out_scale != 1.f) {
+        if (has_scale) {
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] *= p.out_scale;
         }
@@ -361,15 +387,15 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int i = 0; i < 32; i++)
             if (i >= nv) v[i] = 0.f;
         }
-        if (p.out32) {
-          if (p.flat) {
+        if (has_out32) {
+          if (is_flat) {
             // transposed conv: row t holds stride*Cout consecutive output elements of the sequence slab
             const long long e0 = (long long)t * p.out32_ld + cbase + p.flat_off;
             const long long hi = (long long)c.len * p.flat_hi_per_len + p.flat_hi_add;
             if (e0 >= p.flat_lo && e0 + nv <= hi) store32_f32(p.out32 + (long long)c.s * p.flat_seq_elems + e0, v, full, nv);
           } else {
             float* op = p.out32 + row * p.out32_ld + cbase;
-            if (p.out32_accum) {
+            if (has_accum) {
               load32(op, tmp, full, nv);
 #pragma unroll
               for (int i = 0; i < 32; i++) v[i] += tmp[i];
@@ -381,13 +407,14 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int e = 0; e < 3; e++) {
           const Emit& em = p.emit[e];
-          if (em.kind == EMIT_NONE || em.kind == EMIT_LN) continue;
+          const int ek = e == 0 ? ek0 : (e == 1 ? ek1 : ek2);
+          if (ek == EMIT_NONE || ek == EMIT_LN) continue;
           float w[32];
-          if (em.kind == EMIT_SNAKE) {
+          if (ek == EMIT_SNAKE) {
             load32(em.a + cbase, tmp, full, nv);
 #pragma unroll
             for (int i = 0; i < 32; i++) w[i] = fast_snake(v[i], tmp[i]);
-          } else if (em.kind == EMIT_LRELU) {
+          } else if (ek == EMIT_LRELU) {
 #pragma unroll
             for (int i = 0; i < 32; i++) w[i] = v[i] > 0.f ? v[i] : v[i] * em.f;
           } else {
@@ -399,7 +426,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int i = 0; i < 32; i++) w[i] *= sc;
           store32_f16(em.ptr + row * em.ld + em.col_off + cbase, w, full, nv);
         }
-        if (p.q) {  // attention operand split: q (pre-scaled) and k row-major per head, v transposed per head
+        if (has_qkv) {  // attention operand split: q (pre-scaled) and k row-major per head, v transposed per head
           const int hd = p.heads * 64;
           const int which = cbase / hd;            // 0 q, 1 k, 2 v (a 32-col chunk never straddles)
           const int cc = cbase - which * hd;
@@ -431,7 +458,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         epi_bar();
         const float mean2 = (red_c[r] + red_c[128 + r]) / (float)ncols;
         float sq2 = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int ch = 0; ch < kChunks; ch++) {
           const int nv = min(32, ncols - (my_c0 + ch * 32));
           if (nv <= 0) break;
@@ -447,7 +474,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         red_d[half * 128 + r] = sq2;
         epi_bar();
         const float var2 = (red_d[r] + red_d[128 + r]) / (float)ncols;
-#pragma unroll
+#pragma unroll 1
         for (int ch = 0; ch < kChunks; ch++) {
           const int cl = my_c0 + ch * 32;
           const int nv = min(32, ncols - cl);
@@ -458,7 +485,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int e = 0; e < 3; e++) {
             const Emit& em = p.emit[e];
-            if (em.kind != EMIT_LN) continue;
+            const int ek = e == 0 ? ek0 : (e == 1 ? ek1 : ek2);
+            if (ek != EMIT_LN) continue;
             const float rstd2 = rsqrtf(var2 + em.f);
             float g[32], w[32];
             load32(em.a + cbase, g, nv == 32, nv);
@@ -487,11 +515,11 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 static int g_num_sms = 0;
 
-template <int BN>
-static void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+template <int BN, class Cfg>
+static void launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    CV2_CUDA(cudaFuncSetAttribute(gemm_tap_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
+    CV2_CUDA(cudaFuncSetAttribute(gemm_tap_kernel<BN, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
     configured = true;
   }
   if (g_num_sms == 0) {
@@ -500,11 +528,50 @@ static void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
     CV2_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int total = ((p.N + BN - 1) / BN) * (p.T_alloc / kTileM) * p.S;
-  // persistent: one CTA per SM
-  const int per_sm = 1;
-  const int grid = total < g_num_sms * per_sm ? total : g_num_sms * per_sm;
-  gemm_tap_kernel<BN><<<grid, kThreads, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, p);
+  const int grid = total < g_num_sms ? total : g_num_sms;   // persistent: one CTA per SM
+  gemm_tap_kernel<BN, Cfg><<<grid, kThreads, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, p);
   CV2_LAUNCH_CHECK();
+}
+
+// Specialised epilogues.               ACT       B LN RV MK RS R2 O32 AC FL SC  EMIT0       EMIT1      EMIT2     QKV
+using EpiQkv      = EpiCfg<ACT_NONE,  0, 0, 0, 0, 0, 0, 0, 0, 0, 0, EMIT_NONE,  EMIT_NONE, EMIT_NONE, 1>;
+using EpiResLn    = EpiCfg<ACT_NONE,  1, 0, 0, 0, 1, 0, 1, 0, 0, 0, EMIT_LN,    EMIT_NONE, EMIT_NONE, 0>;   // out-proj / FF2
+using EpiResPlain = EpiCfg<ACT_NONE,  1, 0, 0, 0, 1, 0, 1, 0, 0, 0, EMIT_PLAIN, EMIT_NONE, EMIT_NONE, 0>;   // last FF2 of a group
+using EpiGelu     = EpiCfg<ACT_GELU,  1, 0, 0, 0, 0, 0, 0, 0, 0, 0, EMIT_PLAIN, EMIT_NONE, EMIT_NONE, 0>;   // FF1
+using EpiConv1    = EpiCfg<ACT_MISH,  1, 1, 1, 0, 0, 0, 0, 0, 0, 0, EMIT_PLAIN, EMIT_NONE, EMIT_NONE, 0>;   // resnet block1
+using EpiConv2    = EpiCfg<ACT_MISH,  1, 1, 0, 1, 1, 0, 1, 0, 0, 0, EMIT_LN,    EMIT_NONE, EMIT_NONE, 0>;   // resnet block2
+using EpiOut32    = EpiCfg<ACT_NONE,  1, 0, 0, 0, 0, 0, 1, 0, 0, 0, EMIT_NONE,  EMIT_NONE, EMIT_NONE, 0>;   // res_conv, projections
+using EpiPlain    = EpiCfg<ACT_NONE,  1, 0, 0, 0, 0, 0, 0, 0, 0, 0, EMIT_PLAIN, EMIT_NONE, EMIT_NONE, 0>;   // plain conv -> 16-bit
+using EpiSnake    = EpiCfg<ACT_SNAKE, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, EMIT_PLAIN, EMIT_NONE, EMIT_NONE, 0>;   // ResBlock conv1
+using EpiResSnake = EpiCfg<ACT_NONE,  1, 0, 0, 0, 1, 0, 1, 0, 0, 0, EMIT_SNAKE, EMIT_NONE, EMIT_NONE, 0>;   // ResBlock conv2
+using EpiResSum   = EpiCfg<ACT_NONE,  1, 0, 0, 0, 1, 0, 1, -1, 0, 1, -1,        EMIT_NONE, EMIT_NONE, 0>;   // ResBlock tail (x/3 sum)
+using EpiSilu     = EpiCfg<ACT_SILU,  1, 0, 0, 0, 0, 0, 0, 0, 0, 0, EMIT_PLAIN, EMIT_NONE, EMIT_NONE, 0>;   // encoder FFN w_1
+using EpiRes      = EpiCfg<ACT_NONE,  1, 0, 0, 0, 1, 0, 1, 0, 0, 0, EMIT_NONE,  EMIT_NONE, EMIT_NONE, 0>;   // encoder residual adds
+
+template <class Cfg>
+static bool cfg_matches(const GemmParams& p) {
+  auto ok = [](int want, int have) { return want < 0 || want == have; };
+  return ok(Cfg::ACT, p.act) && ok(Cfg::BIAS, p.bias != nullptr) && ok(Cfg::LN, p.ln != 0) && ok(Cfg::ROWVEC, p.rowvec != nullptr) &&
+         ok(Cfg::MASK, p.mask_pre_res != 0) && ok(Cfg::RES, p.res != nullptr) && ok(Cfg::RES2, p.res2 != nullptr) &&
+         ok(Cfg::OUT32, p.out32 != nullptr) && ok(Cfg::ACCUM, p.out32_accum != 0) && ok(Cfg::FLAT, p.flat != 0) &&
+         ok(Cfg::SCALE, p.out_scale != 1.f) && ok(Cfg::EMIT0, p.emit[0].kind) && ok(Cfg::EMIT1, p.emit[1].kind) &&
+         ok(Cfg::EMIT2, p.emit[2].kind) && ok(Cfg::QKV, p.q != nullptr);
+}
+
+template <int BN>
+static void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+#define TRY(CFG)                                  \
+  if (cfg_matches<CFG>(p)) {                      \
+    launch_cfg<BN, CFG>(tmA, tmB, p, stream);     \
+    return;                                       \
+  }
+  if constexpr (BN == 256) {
+    TRY(EpiQkv) TRY(EpiResLn) TRY(EpiGelu) TRY(EpiConv1) TRY(EpiConv2) TRY(EpiResPlain) TRY(EpiSilu) TRY(EpiRes)
+  }
+  TRY(EpiOut32) TRY(EpiPlain) TRY(EpiSnake) TRY(EpiResSnake)
+  if (p.emit[0].kind == EMIT_NONE || p.emit[0].kind == EMIT_LRELU) { TRY(EpiResSum) }
+#undef TRY
+  launch_cfg<BN, EpiGeneric>(tmA, tmB, p, stream);
 }
 
 void launch_gemm_tap(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
