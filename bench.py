@@ -36,6 +36,10 @@ N_PROMPT = 75
 BATCH = 64
 FAMILIES = ["gemm_tap<64>", "gemm_tap<128>", "gemm_tap<256>", "flash_attn", "rel_attn", "f0_conv_f32", "nsf_source", "source_stft",
             "source_down", "istft", "layernorm"]
+# gemm_tap<256> launches are additionally split by epilogue specialisation (engine families 11 + spec)
+G256 = ["generic", "qkv_split", "res+ln_emit", "gelu", "conv+ln+mish+temb", "conv+ln+mish+res+ln_emit", "res+plain_emit", "silu",
+        "res", "out32", "plain_emit", "snake", "res+snake_emit", "res_sum"]
+NFAM = len(FAMILIES) + len(G256)
 
 
 def workload(rank, batch=BATCH):
@@ -253,10 +257,15 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    fam_ms = (C.c_double * len(FAMILIES))()
-    fam_n = (C.c_longlong * len(FAMILIES))()
-    eng.lib.cv2_engine_read_profile(eng.h, fam_ms, fam_n, len(FAMILIES))
+    raw_ms = (C.c_double * NFAM)()
+    raw_n = (C.c_longlong * NFAM)()
+    eng.lib.cv2_engine_read_profile(eng.h, raw_ms, raw_n, NFAM)
     eng.lib.cv2_engine_set_profiling(eng.h, 0)
+    fam_ms, fam_n = list(raw_ms[:len(FAMILIES)]), list(raw_n[:len(FAMILIES)])
+    fam_ms[2] += sum(raw_ms[len(FAMILIES):])
+    fam_n[2] += sum(raw_n[len(FAMILIES):])
+    g256 = {G256[i]: {"ms_per_step": raw_ms[len(FAMILIES) + i] / args.steps, "launches_per_step": raw_n[len(FAMILIES) + i] / args.steps}
+            for i in range(len(G256)) if raw_n[len(FAMILIES) + i] > 0}
 
     # ---- timed region 2: end to end through the public API with host buffers ----
     for _ in range(2):
@@ -327,6 +336,7 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roofline,
             "families": fam,
+            "gemm256_by_epilogue": g256,
             "whole_step_tflops": total_flop / 1e12 / (ms / args.steps / 1e3) / world,
             "rtf_batch1": {"workload": "BASELINE configs[1]: single 10 s utterance (250 tokens + 75-token prompt), batch 1",
                            "latency_s": lat1, "rtf": lat1 / 10.0, "audio_s_per_s": 10.0 / lat1},

@@ -60,7 +60,7 @@ void Engine::gemm(cudaStream_t st, const __half* A, int S, int T_alloc, int Kc, 
     if (amap_cache.size() > 8192) amap_cache.clear();
     it = amap_cache.emplace(key, make_tmap_16b(A, 3, dims, strides, box)).first;
   }
-  prof_begin(st, bi);
+  prof_begin(st, bn == 256 ? F_COUNT + gemm_tap_spec(bn, p) : bi);
   launch_gemm_tap(bn, it->second, w.map[bi], p, st);
   prof_end(st);
 }

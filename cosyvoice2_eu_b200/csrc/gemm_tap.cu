@@ -574,6 +574,23 @@ static void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
   launch_cfg<BN, EpiGeneric>(tmA, tmB, p, stream);
 }
 
+// index of the epilogue specialisation launch_gemm_tap would pick (profiling labels only)
+int gemm_tap_spec(int bn, const GemmParams& p) {
+  int i = 1;
+#define TRYS(CFG)                 \
+  if (cfg_matches<CFG>(p)) return i; \
+  i++;
+  if (bn == 256) {
+    TRYS(EpiQkv) TRYS(EpiResLn) TRYS(EpiGelu) TRYS(EpiConv1) TRYS(EpiConv2) TRYS(EpiResPlain) TRYS(EpiSilu) TRYS(EpiRes)
+  } else {
+    i += 8;
+  }
+  TRYS(EpiOut32) TRYS(EpiPlain) TRYS(EpiSnake) TRYS(EpiResSnake)
+  if (p.emit[0].kind == EMIT_NONE || p.emit[0].kind == EMIT_LRELU) { TRYS(EpiResSum) }
+#undef TRYS
+  return 0;
+}
+
 void launch_gemm_tap(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   CV2_CHECK(p.T_alloc % kTileM == 0, "gemm_tap: T_alloc %d not a multiple of 128", p.T_alloc);
   CV2_CHECK(p.ntaps >= 1 && p.ntaps <= 16 && p.kb_per_tap >= 1, "gemm_tap: bad taps %d / kb %d", p.ntaps, p.kb_per_tap);

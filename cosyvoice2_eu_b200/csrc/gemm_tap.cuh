@@ -73,6 +73,7 @@ struct GemmParams {
 
 // Launch; tmA = 3-D map {Kc, T_alloc, S} box {64,128,1}; tmB = 2-D map {Ktot_pad, N} box {64, BN}.
 // bn in {64, 128, 256}.
+int gemm_tap_spec(int bn, const GemmParams& p);
 void launch_gemm_tap(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream);
 
 }  // namespace cv2
