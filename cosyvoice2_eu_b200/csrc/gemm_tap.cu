@@ -12,18 +12,20 @@
 
 namespace cv2 {
 
-static constexpr int kStages = 4;
 static constexpr int kTileM = 128;
 static constexpr int kKBlock = 64;                       // 64 x 16-bit = one 128B swizzle row
 static constexpr int kABytes = kTileM * kKBlock * 2;     // 16 KB
 static constexpr int kEpiWarps = 8;
 static constexpr int kThreads = 64 + kEpiWarps * 32;     // 320
 
+static constexpr int kStgFloats = 32 * 36;                 // per-warp transpose staging: 32 rows x (32 + 4 pad) floats
 template <int BN>
 struct GemmSmem {
+  static constexpr int kStages = BN == 256 ? 3 : 4;
   static constexpr int kBBytes = BN * kKBlock * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kRedOff = kStages * kStageBytes;           // 4 x [2][128] floats for LayerNorm exchanges
+  static constexpr int kStgOff = kStages * kStageBytes;           // 8 warps x 4608 B
+  static constexpr int kRedOff = kStgOff + kEpiWarps * kStgFloats * 4;   // 4 x [2][128] floats for LayerNorm exchanges
   static constexpr int kBarOff = kRedOff + 4 * 2 * 128 * 4;
   static constexpr int kTotal = kBarOff + 256 + 1024;             // barriers + alignment slack
 };
@@ -98,6 +100,63 @@ __device__ __forceinline__ void store32_f16(__half* __restrict__ p, const float*
   }
 }
 
+// ---- coalesced global I/O for the thread-per-row epilogue ----
+// A warp owns 32 consecutive rows x 32 columns.  Per-thread row segments (16 B pieces 32 rows apart) cost one L1 wavefront
+// per lane; instead the warp moves the 32x32 block with lanes running along the row (4 rows x 128 B per instruction) and
+// transposes it through a private, padded shared-memory staging tile.
+__device__ __forceinline__ void tile_load_f32(const float* __restrict__ g0, long long ld, float* stg, int lane, float* d) {
+  // g0 -> element (first row of the warp, first column of the chunk)
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int rr = 4 * i + (lane >> 3), c4 = (lane & 7) * 4;
+    const float4 f = __ldg(reinterpret_cast<const float4*>(g0 + rr * ld + c4));
+    *reinterpret_cast<float4*>(stg + rr * 36 + c4) = f;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float4 f = *reinterpret_cast<const float4*>(stg + lane * 36 + i * 4);
+    d[i * 4 + 0] = f.x; d[i * 4 + 1] = f.y; d[i * 4 + 2] = f.z; d[i * 4 + 3] = f.w;
+  }
+}
+__device__ __forceinline__ void tile_store_f32(float* __restrict__ g0, long long ld, float* stg, int lane, const float* v) {
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    *reinterpret_cast<float4*>(stg + lane * 36 + i * 4) = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int rr = 4 * i + (lane >> 3), c4 = (lane & 7) * 4;
+    *reinterpret_cast<float4*>(g0 + rr * ld + c4) = *reinterpret_cast<const float4*>(stg + rr * 36 + c4);
+  }
+}
+__device__ __forceinline__ void tile_store_f16(__half* __restrict__ g0, long long ld, float* stg, int lane, const float* v) {
+  // staging rows of 64 B payload + 16 B pad (20 words)
+  uint32_t* sw = reinterpret_cast<uint32_t*>(stg);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    __half2 h0 = __floats2half2_rn(v[i * 8 + 0], v[i * 8 + 1]);
+    __half2 h1 = __floats2half2_rn(v[i * 8 + 2], v[i * 8 + 3]);
+    __half2 h2 = __floats2half2_rn(v[i * 8 + 4], v[i * 8 + 5]);
+    __half2 h3 = __floats2half2_rn(v[i * 8 + 6], v[i * 8 + 7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2);
+    u.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(sw + lane * 20 + i * 4) = u;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int rr = 8 * i + (lane >> 2), pc = lane & 3;
+    *reinterpret_cast<uint4*>(g0 + rr * ld + pc * 8) = *reinterpret_cast<const uint4*>(sw + rr * 20 + pc * 4);
+  }
+}
+
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
 struct TileCoord {
@@ -132,6 +191,7 @@ template <int BN, class Cfg>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using SM = GemmSmem<BN>;
+  constexpr int kStages = SM::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* red = reinterpret_cast<float*>(smem + SM::kRedOff);
@@ -226,6 +286,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int r = q * 32 + lane;
     constexpr int kHalfCols = BN / 2;
     constexpr int kChunks = kHalfCols / 32;   // 4 / 2 / 1
+    float* stg = reinterpret_cast<float*>(smem + SM::kStgOff) + ew * kStgFloats;   // this warp's staging tile
     float* red_a = red;                  // [2][128] each
     float* red_b = red + 256;
     float* red_c = red + 512;
@@ -258,6 +319,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int my_c0 = half * kHalfCols;                            // first column (within tile) of this thread
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + my_c0;
       const long long row = (long long)c.s * p.T_alloc + t;
+      const long long row0 = row - lane;                              // first row of this warp's 32-row block
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after();
 
@@ -369,12 +431,14 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int i = 0; i < 32; i++) v[i] = 0.f;
         }
         if (has_res) {
-          load32(p.res + row * p.res_ld + cbase, tmp, full, nv);
+          if (full) tile_load_f32(p.res + row0 * p.res_ld + cbase, p.res_ld, stg, lane, tmp);
+          else load32(p.res + row * p.res_ld + cbase, tmp, full, nv);
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] += tmp[i];
         }
         if (has_res2) {
-          load32(p.res2 + row * p.res2_ld + cbase, tmp, full, nv);
+          if (full) tile_load_f32(p.res2 + row0 * p.res2_ld + cbase, p.res2_ld, stg, lane, tmp);
+          else load32(p.res2 + row * p.res2_ld + cbase, tmp, full, nv);
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] += tmp[i];
         }
@@ -395,12 +459,15 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (e0 >= p.flat_lo && e0 + nv <= hi) store32_f32(p.out32 + (long long)c.s * p.flat_seq_elems + e0, v, full, nv);
           } else {
             float* op = p.out32 + row * p.out32_ld + cbase;
+            float* op0 = p.out32 + row0 * p.out32_ld + cbase;
             if (has_accum) {
-              load32(op, tmp, full, nv);
+              if (full) tile_load_f32(op0, p.out32_ld, stg, lane, tmp);
+              else load32(op, tmp, full, nv);
 #pragma unroll
               for (int i = 0; i < 32; i++) v[i] += tmp[i];
             }
-            store32_f32(op, v, full, nv);
+            if (full) tile_store_f32(op0, p.out32_ld, stg, lane, v);
+            else store32_f32(op, v, full, nv);
           }
         }
         // 16-bit emits (the next contraction's A operand); padded rows are written as zeros
@@ -424,7 +491,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const float sc = valid ? em.scale : 0.f;
 #pragma unroll
           for (int i = 0; i < 32; i++) w[i] *= sc;
-          store32_f16(em.ptr + row * em.ld + em.col_off + cbase, w, full, nv);
+          if (full) tile_store_f16(em.ptr + row0 * em.ld + em.col_off + cbase, em.ld, stg, lane, w);
+          else store32_f16(em.ptr + row * em.ld + em.col_off + cbase, w, full, nv);
         }
         if (has_qkv) {  // attention operand split: q (pre-scaled) and k row-major per head, v transposed per head
           const int hd = p.heads * 64;
@@ -436,7 +504,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             float w[32];
 #pragma unroll
             for (int i = 0; i < 32; i++) w[i] = v[i] * sc;
-            store32_f16((which == 0 ? p.q : p.k) + (((long long)c.s * p.heads + h) * p.T_alloc + t) * 64 + d0, w, true, 32);
+            tile_store_f16((which == 0 ? p.q : p.k) + (((long long)c.s * p.heads + h) * p.T_alloc + (t - lane)) * 64 + d0, 64, stg, lane, w);
           } else {
             __half* dst = p.vt + (((long long)c.s * p.heads + h) * 64 + d0) * p.T_alloc + t;
 #pragma unroll
@@ -496,7 +564,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const float sc = valid ? em.scale : 0.f;
 #pragma unroll
             for (int i = 0; i < 32; i++) w[i] = (w[i] + g[i]) * sc;
-            store32_f16(em.ptr + row * em.ld + em.col_off + cbase, w, nv == 32, nv);
+            if (nv == 32) tile_store_f16(em.ptr + row0 * em.ld + em.col_off + cbase, em.ld, stg, lane, w);
+            else store32_f16(em.ptr + row * em.ld + em.col_off + cbase, w, false, nv);
           }
         }
       }
