@@ -15,18 +15,19 @@ namespace cv2 {
 static constexpr int kTileM = 128;
 static constexpr int kKBlock = 64;                       // 64 x 16-bit = one 128B swizzle row
 static constexpr int kABytes = kTileM * kKBlock * 2;     // 16 KB
-static constexpr int kEpiWarps = 8;
-static constexpr int kThreads = 64 + kEpiWarps * 32;     // 320
 
 static constexpr int kStgFloats = 32 * 36;                 // per-warp transpose staging: 32 rows x (32 + 4 pad) floats
 template <int BN>
 struct GemmSmem {
+  static constexpr int kParts = BN >= 128 ? 4 : 2;        // column parts of a tile = epilogue warps per TMEM lane quarter
+  static constexpr int kEpiWarps = 4 * kParts;            // 16 (8 for BN = 64): enough warps to hide TMEM / smem / MUFU latency
+  static constexpr int kThreads = 64 + kEpiWarps * 32;    // + TMA warp + MMA warp
   static constexpr int kStages = BN == 256 ? 3 : 4;
   static constexpr int kBBytes = BN * kKBlock * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStgOff = kStages * kStageBytes;           // 8 warps x 4608 B
-  static constexpr int kRedOff = kStgOff + kEpiWarps * kStgFloats * 4;   // 4 x [2][128] floats for LayerNorm exchanges
-  static constexpr int kBarOff = kRedOff + 4 * 2 * 128 * 4;
+  static constexpr int kRedOff = kStgOff + kEpiWarps * kStgFloats * 4;   // 4 x [kParts][128] floats for LayerNorm exchanges
+  static constexpr int kBarOff = kRedOff + 4 * kParts * 128 * 4;
   static constexpr int kTotal = kBarOff + 256 + 1024;             // barriers + alignment slack
 };
 
@@ -39,15 +40,17 @@ __device__ __forceinline__ float fast_mish(float x) {
   return x > 20.f ? x : y;
 }
 __device__ __forceinline__ float fast_gelu_erf(float x) {
-  // exact-erf GELU; erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7)
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erfz = 1.f - poly * t * __expf(-z * z);
-  return 0.5f * x * (1.f + copysignf(erfz, x));
+  // exact-erf GELU with erf(z) = 1 - 2^(-g(z)), g = log2(e) * (-ln erfc(z)) fitted by a degree-6 polynomial on [0,4]
+  // (|erf err| < 3e-7, |gelu err| < 7e-7 in fp32): one MUFU (ex2) and no division per element.
+  const float ax = fabsf(x);
+  const float z = fminf(ax * 0.70710678118654752440f, 4.0f);
+  float g = fmaf(-0.000158880008f, z, 0.00374658569f);
+  g = fmaf(g, z, -0.0310388152f);
+  g = fmaf(g, z, 0.149806067f);
+  g = fmaf(g, z, 0.918132424f);
+  g = fmaf(g, z, 1.62792826f);
+  const float e = fast_exp2(-g * z);
+  return fmaf(0.5f * ax, 1.f - e, 0.5f * x);
 }
 __device__ __forceinline__ float fast_silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_snake(float x, float a) {
@@ -157,7 +160,8 @@ __device__ __forceinline__ void tile_store_f16(__half* __restrict__ g0, long lon
   }
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+template <int NT>
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
 struct TileCoord {
   int n0, t0, s, len;
@@ -188,10 +192,12 @@ using EpiGeneric = EpiCfg<-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1
 #define CFGB(field, rt) (Cfg::field < 0 ? (rt) : (Cfg::field != 0))
 
 template <int BN, class Cfg>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(GemmSmem<BN>::kThreads, 1)
 gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using SM = GemmSmem<BN>;
   constexpr int kStages = SM::kStages;
+  constexpr int kEpiWarps = SM::kEpiWarps;
+  constexpr int kParts = SM::kParts;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* red = reinterpret_cast<float*>(smem + SM::kRedOff);
@@ -282,15 +288,21 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // --------------------------------- epilogue -----------------------------------
     const int ew = warp - 2;
     const int q = warp & 3;              // TMEM lane quarter accessible to this warp
-    const int half = ew >> 2;            // which half of the tile's columns this thread owns
+    const int half = ew >> 2;            // which part of the tile's columns this thread owns
     const int r = q * 32 + lane;
-    constexpr int kHalfCols = BN / 2;
-    constexpr int kChunks = kHalfCols / 32;   // 4 / 2 / 1
+    constexpr int kHalfCols = BN / kParts;    // 64 / 32 / 32
+    constexpr int kChunks = kHalfCols / 32;   // 2 / 1 / 1
     float* stg = reinterpret_cast<float*>(smem + SM::kStgOff) + ew * kStgFloats;   // this warp's staging tile
-    float* red_a = red;                  // [2][128] each
-    float* red_b = red + 256;
-    float* red_c = red + 512;
-    float* red_d = red + 768;
+    float* red_a = red;                  // [kParts][128] each
+    float* red_b = red + kParts * 128;
+    float* red_c = red + 2 * kParts * 128;
+    float* red_d = red + 3 * kParts * 128;
+    auto red_sum = [&](const float* a) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < kParts; k++) t += a[k * 128 + r];
+      return t;
+    };
     const int ek0 = Cfg::EMIT0 < 0 ? p.emit[0].kind : Cfg::EMIT0;
     const int ek1 = Cfg::EMIT1 < 0 ? p.emit[1].kind : Cfg::EMIT1;
     const int ek2 = Cfg::EMIT2 < 0 ? p.emit[2].kind : Cfg::EMIT2;
@@ -342,8 +354,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (i < nv) sum += __uint_as_float(raw[i]) + bch[i];
         }
         red_a[half * 128 + r] = sum;
-        epi_bar();
-        mean = (red_a[r] + red_a[128 + r]) / (float)ncols;
+        epi_bar<kEpiWarps * 32>();
+        mean = red_sum(red_a) / (float)ncols;
         float sq = 0.f;
 #pragma unroll 1
         for (int ch = 0; ch < kChunks; ch++) {
@@ -362,8 +374,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
         red_b[half * 128 + r] = sq;
-        epi_bar();
-        rstd = rsqrtf((red_b[r] + red_b[128 + r]) / (float)ncols + p.ln_eps);
+        epi_bar<kEpiWarps * 32>();
+        rstd = rsqrtf(red_sum(red_b) / (float)ncols + p.ln_eps);
       }
 
       float sum2 = 0.f;
@@ -523,8 +535,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (stat2) {  // LayerNorm of the final row value (pre-norm of the next sub-block), emitted as 16-bit
         tmem_st_wait();
         red_c[half * 128 + r] = sum2;
-        epi_bar();
-        const float mean2 = (red_c[r] + red_c[128 + r]) / (float)ncols;
+        epi_bar<kEpiWarps * 32>();
+        const float mean2 = red_sum(red_c) / (float)ncols;
         float sq2 = 0.f;
 #pragma unroll 1
         for (int ch = 0; ch < kChunks; ch++) {
@@ -540,8 +552,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
         red_d[half * 128 + r] = sq2;
-        epi_bar();
-        const float var2 = (red_d[r] + red_d[128 + r]) / (float)ncols;
+        epi_bar<kEpiWarps * 32>();
+        const float var2 = red_sum(red_d) / (float)ncols;
 #pragma unroll 1
         for (int ch = 0; ch < kChunks; ch++) {
           const int cl = my_c0 + ch * 32;
@@ -598,7 +610,7 @@ static void launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int total = ((p.N + BN - 1) / BN) * (p.T_alloc / kTileM) * p.S;
   const int grid = total < g_num_sms ? total : g_num_sms;   // persistent: one CTA per SM
-  gemm_tap_kernel<BN, Cfg><<<grid, kThreads, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, p);
+  gemm_tap_kernel<BN, Cfg><<<grid, GemmSmem<BN>::kThreads, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, p);
   CV2_LAUNCH_CHECK();
 }
 
