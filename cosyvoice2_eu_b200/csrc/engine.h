@@ -69,6 +69,16 @@ struct Engine {
   std::unordered_map<uint64_t, CUtensorMap> amap_cache;  // activation tensor maps
   long long launches = 0;                                // kernels launched by the last forward (claims for bench)
 
+  // compact active-tile lists keyed by (lens pointer, T_alloc): gemm() attaches them automatically
+  struct TileList { const int* list; const int* count; };
+  std::unordered_map<uint64_t, TileList> tile_lists;
+  static uint64_t tl_key(const int* lens, int T_alloc, int S) {
+    return ((uint64_t)(uintptr_t)lens * 1315423911ull + (uint64_t)T_alloc) * 2654435761ull + (uint64_t)S;
+  }
+  // builds the list for `lens` (S sequences) and registers it under lens and every alias pointer (same or shorter lengths)
+  void make_tile_list(cudaStream_t st, Arena& ws, const int* lens, int S, int T_alloc, int halo, bool dry,
+                      const int* alias0 = nullptr, const int* alias1 = nullptr);
+
   // ---- optional per-launch timing (CUDA events on the launching stream), grouped by kernel family ----
   enum Family { F_GEMM64 = 0, F_GEMM128, F_GEMM256, F_FLASH_ATTN, F_REL_ATTN, F_F0_CONV, F_NSF, F_STFT, F_SRC_DOWN, F_ISTFT,
                 F_LAYERNORM, F_COUNT };

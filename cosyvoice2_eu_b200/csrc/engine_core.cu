@@ -26,6 +26,19 @@ static inline uint64_t mix(uint64_t h, uint64_t v) {
   return h;
 }
 
+void Engine::make_tile_list(cudaStream_t st, Arena& ws, const int* lens, int S, int T_alloc, int halo, bool dry,
+                            const int* alias0, const int* alias1) {
+  int* list = ws.get<int>((size_t)2 * S * (T_alloc / 128));
+  int* count = ws.get<int>(1);
+  launches++;
+  if (dry) return;
+  launch_build_tile_list(lens, S, T_alloc, halo, list, count, st);
+  TileList tl{list, count};
+  tile_lists[tl_key(lens, T_alloc, S)] = tl;
+  if (alias0) tile_lists[tl_key(alias0, T_alloc, S)] = tl;
+  if (alias1) tile_lists[tl_key(alias1, T_alloc, S)] = tl;
+}
+
 void Engine::gemm(cudaStream_t st, const __half* A, int S, int T_alloc, int Kc, long long ldA, Weight& w, int bn, int ntaps,
                   const int* tap_off, GemmParams p, bool dry) {
   const int kb = (Kc + 63) / 64;
@@ -43,6 +56,13 @@ void Engine::gemm(cudaStream_t st, const __half* A, int S, int T_alloc, int Kc, 
     if (p.emit[e].kind != EMIT_NONE && p.emit[e].scale == 0.f) p.emit[e].scale = 1.f;
   launches++;
   if (dry) return;
+  if (p.lens && !p.tile_list) {
+    auto tl = tile_lists.find(tl_key(p.lens, T_alloc, S));
+    if (tl != tile_lists.end() && S > 1) {
+      p.tile_list = tl->second.list;
+      p.tile_count = tl->second.count;
+    }
+  }
   const int bi = bn == 64 ? 0 : (bn == 128 ? 1 : 2);
   if (!w.map_ok[bi]) {
     uint64_t dims[2] = {(uint64_t)w.Ktot, (uint64_t)w.N};

@@ -201,12 +201,14 @@ size_t estimator_forward(Engine& e, cudaStream_t st, const EstArgs& a, Arena& ws
   const bool dry = ws.measuring();
   const int S = a.B2, T = round_up(a.T, 128);
   int* lens = ws.get<int>(S);
+  e.tile_lists.clear();
   __half* xin = ws.get<__half>((size_t)S * T * 320);
   EstBuffers b = est_alloc(ws, S, T);
   float* tres = est_time(e, st, ws, a.t, S, dry);
   e.launches += 6;
+  if (!dry) launch_mask_to_lens(a.mask, a.T, lens, S, st);
+  e.make_tile_list(st, ws, lens, S, T, kHalo, dry);
   if (!dry) {
-    launch_mask_to_lens(a.mask, a.T, lens, S, st);
     launch_nct_to_ntc(a.x, (long long)80 * a.T, a.T, nullptr, xin, lens, 0, S, T, 80, 320, 0, 0, st);
     launch_nct_to_ntc(a.mu, (long long)80 * a.T, a.T, nullptr, xin, lens, 0, S, T, 80, 320, 80, 0, st);
     launch_bcast_rows16(a.spks, 80, xin, 320, 160, lens, S, T, st);
@@ -300,6 +302,10 @@ size_t flow_forward(Engine& e, cudaStream_t st, const FlowArgs& a, Arena& ws) {
     launch_lens_affine(len_enc, nullptr, 2, 0, len_mel, B, st);
     launch_lens_affine(len_enc, nullptr, 2, 0, len_mel + B, B, st);
   }
+  e.tile_lists.clear();
+  e.make_tile_list(st, ws, len_ctx, B, Tt, kHalo, dry, len_enc);        // token-rate encoder GEMMs
+  e.make_tile_list(st, ws, len_mel, 2 * B, Tm, kHalo, dry);             // estimator (both CFG rows)
+  e.make_tile_list(st, ws, len_mel, B, Tm, kHalo, dry);                 // mel-rate encoder GEMMs
 
   // ---- encoder, token rate ----
   EncBuffers eb;

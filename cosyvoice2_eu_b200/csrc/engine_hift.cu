@@ -55,6 +55,8 @@ size_t hift_forward(Engine& e, cudaStream_t st, const HiftArgs& a, Arena& ws) {
     launch_lens_affine(lens[0], nullptr, 40, 0, lens[2], B, st);
     launch_lens_affine(lens[0], nullptr, 120, 1, lens[3], B, st);
   }
+  e.tile_lists.clear();
+  for (int i = 0; i < 4; i++) e.make_tile_list(st, ws, lens[i], B, Ta[i], kHalo, dry);
 
   // ---- mel -> channels-last (fp32 for the F0 predictor, 16-bit for conv_pre) ----
   float* MEL32 = ws.get<float>((size_t)B * Ta[0] * 80);

@@ -170,6 +170,13 @@ struct TileCoord {
 __device__ __forceinline__ bool tile_coord(const GemmParams& p, int tile, int n_tiles, int t_tiles, int BN, TileCoord& c) {
   const int n = tile % n_tiles;
   const int rest = tile / n_tiles;
+  if (p.tile_list) {   // compacted list: every entry is active
+    c.s = __ldg(p.tile_list + 2 * rest);
+    c.t0 = __ldg(p.tile_list + 2 * rest + 1);
+    c.n0 = n * BN;
+    c.len = p.lens ? __ldg(p.lens + c.s) : p.len_all;
+    return true;
+  }
   const int tt = rest % t_tiles;
   c.s = rest / t_tiles;
   c.n0 = n * BN;
@@ -212,7 +219,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_it = p.ntaps * p.kb_per_tap;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int t_tiles = p.T_alloc / kTileM;
-  const int total_tiles = n_tiles * t_tiles * p.S;
+  const int total_tiles = p.tile_list ? n_tiles * __ldg(p.tile_count) : n_tiles * t_tiles * p.S;
   constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // 128 / 256 / 512
 
   if (warp == 0 && lane == 0) {
@@ -592,6 +599,34 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// Compact list of the (sequence, t0) row tiles that contain at least one row < len + halo, in (s, t) order.
+__global__ void build_tile_list_kernel(const int* __restrict__ lens, int S, int T_alloc, int halo, int* __restrict__ list,
+                                       int* __restrict__ count) {
+  extern __shared__ int offs[];   // [S + 1]
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const int rows = min(lens[s] + halo, T_alloc);
+    offs[s + 1] = rows > 0 ? (rows + kTileM - 1) / kTileM : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    offs[0] = 0;
+    for (int s = 0; s < S; s++) offs[s + 1] += offs[s];
+    *count = offs[S];
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const int n = offs[s + 1] - offs[s];
+    for (int k = 0; k < n; k++) {
+      list[2 * (offs[s] + k)] = s;
+      list[2 * (offs[s] + k) + 1] = k * kTileM;
+    }
+  }
+}
+void launch_build_tile_list(const int* lens, int S, int T_alloc, int halo, int* list, int* count, cudaStream_t stream) {
+  build_tile_list_kernel<<<1, 256, (S + 1) * sizeof(int), stream>>>(lens, S, T_alloc, halo, list, count);
+  CV2_LAUNCH_CHECK();
 }
 
 static int g_num_sms = 0;

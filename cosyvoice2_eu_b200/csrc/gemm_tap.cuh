@@ -38,6 +38,8 @@ struct GemmParams {
   const int* lens;     // [S] valid rows per sequence (nullptr: len_all)
   int len_all;
   int halo;            // a tile is computed iff t0 < len + halo
+  const int* tile_list;   // optional compact list of active (s, t0) pairs (device), balanced round-robin over CTAs
+  const int* tile_count;  // number of pairs in tile_list (device)
   // epilogue program: v = acc + bias -> LN -> act -> + rowvec[s] -> (mask) -> + res + res2 -> *scale (+= out32) -> store / emit
   const float* bias;   // [N] or null
   int ln;
@@ -74,6 +76,8 @@ struct GemmParams {
 // Launch; tmA = 3-D map {Kc, T_alloc, S} box {64,128,1}; tmB = 2-D map {Ktot_pad, N} box {64, BN}.
 // bn in {64, 128, 256}.
 int gemm_tap_spec(int bn, const GemmParams& p);
+// list: [2 * S * (T_alloc/128)] ints, count: 1 int (device)
+void launch_build_tile_list(const int* lens, int S, int T_alloc, int halo, int* list, int* count, cudaStream_t stream);
 void launch_gemm_tap(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream);
 
 }  // namespace cv2
