@@ -107,6 +107,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int j = 0; j < nkt; j++) {
         mbar_wait(p_full, j & 1);   // softmax j has consumed S_j and written P_j
         tc_fence_after();
+        if (j + 1 < nkt) issue_s(j + 1);   // S buffer is free again: next logits first, so softmax j+1 overlaps PV_j
         const int st = j % kKVStages;
         const uint32_t v_addr = smem_u32(smem + kOffV + st * kVBytes);
 #pragma unroll
@@ -119,7 +120,6 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         umma_commit(&kv_empty[st]);
         umma_commit(pv_done);
-        if (j + 1 < nkt) issue_s(j + 1);   // the co-resident CTA keeps the tensor pipe busy meanwhile
       }
     }
   } else {
@@ -138,24 +138,41 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_after();
       const uint32_t s_addr = lane_addr + kTmemS;
       const int kbase = j * 128;
-      // pass A: row max over the visible keys of this tile
-      float mx = -INFINITY;
+      // whole S row (128 visible-key logits) into registers: four TMEM loads in flight, one wait
+      uint32_t sr[128];
+#pragma unroll
+      for (int c = 0; c < 4; c++) tmem_ld32(s_addr + c * 32, sr + c * 32);
+      tmem_ld_wait();
       const bool all_visible = kbase + 128 <= kv_lim;   // no masking needed inside this tile for this row
+      if (!all_visible) {
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        tmem_ld32(s_addr + c * 32, raw);
-        tmem_ld_wait();
-        if (all_visible) {
-#pragma unroll
-          for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(raw[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i++)
-            if (kbase + c * 32 + i < kv_lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
-        }
+        for (int i = 0; i < 128; i++)
+          if (kbase + i >= kv_lim) sr[i] = 0xff800000u;   // -inf
       }
-      const float m_new = fmaxf(m, mx);
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sr[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sr[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sr[i + 3]));
+      }
+      const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
       const float alpha = (m == -INFINITY) ? 0.f : fast_exp2((m - m_new) * LOG2E);
+      const float mscaled = (m_new == -INFINITY) ? 0.f : m_new * LOG2E;
+      // probabilities in place (exp2(-inf) = 0 for masked keys)
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+        const float e0 = fast_exp2(fmaf(__uint_as_float(sr[i]), LOG2E, -mscaled));
+        const float e1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), LOG2E, -mscaled));
+        const float e2 = fast_exp2(fmaf(__uint_as_float(sr[i + 2]), LOG2E, -mscaled));
+        const float e3 = fast_exp2(fmaf(__uint_as_float(sr[i + 3]), LOG2E, -mscaled));
+        l0 += e0; l1 += e1; l2 += e2; l3 += e3;
+        __half2 h0 = __floats2half2_rn(e0, e1), h1 = __floats2half2_rn(e2, e3);
+        sr[i >> 1] = *reinterpret_cast<uint32_t*>(&h0);          // pack in place: 64 words of fp16 pairs
+        sr[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+      }
       // PV of the previous tile must be complete before O is rescaled or P overwritten
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);
@@ -171,41 +188,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           tmem_st_wait();
         }
       }
-      l *= alpha;
-      // pass B: probabilities -> 16-bit P tile in the swizzled K-major layout
-      const float mscaled = (m_new == -INFINITY) ? 0.f : m_new * LOG2E;
+      l = l * alpha + ((l0 + l1) + (l2 + l3));
+      // P tile, 16-bit, swizzled K-major: 16 x 16-byte groups per row
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        tmem_ld32(s_addr + c * 32, raw);
-        tmem_ld_wait();
-        float pv[32];
-        if (all_visible) {
-#pragma unroll
-          for (int i = 0; i < 32; i++) pv[i] = fast_exp2(fmaf(__uint_as_float(raw[i]), LOG2E, -mscaled));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i++)
-            pv[i] = (kbase + c * 32 + i < kv_lim) ? fast_exp2(fmaf(__uint_as_float(raw[i]), LOG2E, -mscaled)) : 0.f;
-        }
-        float ls = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; i++) ls += pv[i];
-        l += ls;
-        uint8_t* atom = prow + (c >> 1) * 16384;
-        const int g0 = (c & 1) * 4;
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-          __half2 h0 = __floats2half2_rn(pv[g * 8 + 0], pv[g * 8 + 1]);
-          __half2 h1 = __floats2half2_rn(pv[g * 8 + 2], pv[g * 8 + 3]);
-          __half2 h2 = __floats2half2_rn(pv[g * 8 + 4], pv[g * 8 + 5]);
-          __half2 h3 = __floats2half2_rn(pv[g * 8 + 6], pv[g * 8 + 7]);
-          uint4 u;
-          u.x = *reinterpret_cast<uint32_t*>(&h0);
-          u.y = *reinterpret_cast<uint32_t*>(&h1);
-          u.z = *reinterpret_cast<uint32_t*>(&h2);
-          u.w = *reinterpret_cast<uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(atom + (((g0 + g) ^ (r & 7)) << 4)) = u;
-        }
+      for (int g = 0; g < 16; g++) {
+        uint4 u;
+        u.x = sr[g * 4 + 0]; u.y = sr[g * 4 + 1]; u.z = sr[g * 4 + 2]; u.w = sr[g * 4 + 3];
+        *reinterpret_cast<uint4*>(prow + (g >> 3) * 16384 + (((g & 7) ^ (r & 7)) << 4)) = u;
       }
       m = m_new;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)

@@ -257,46 +257,72 @@ void launch_source_stft(const float* src, long long src_bstride, const int* lens
 // fp32 SIMT (K = 18*k is tiny).  w: [k][18][C] (C contiguous).  Emits the fp32 result and snake(alpha)(result)
 // in 16-bit as the A operand of the source ResBlock's first conv.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void source_down_kernel(const float* __restrict__ stft, int F_alloc, const float* __restrict__ w,
+// Register-blocked: each thread owns 4 channels x 4 output frames (16 FMAs per weight float4 + 4 broadcast spectrum loads).
+__global__ void __launch_bounds__(256) source_down_kernel(const float* __restrict__ stft, int F_alloc, const float* __restrict__ w,
                                    const float* __restrict__ bias, int k, int stride, int pad, int C, const int* __restrict__ lens,
                                    int len_all, int frames_per_len, int frames_add, float* __restrict__ out32,
                                    __half* __restrict__ out16, const float* __restrict__ alpha, int T_alloc) {
   const int b = blockIdx.y;
-  const int t = blockIdx.x * blockDim.y + threadIdx.y;
+  const int c4 = threadIdx.x * 4;
+  const int t0 = (blockIdx.x * blockDim.y + threadIdx.y) * 4;
   const int len = lens ? lens[b] : len_all;
   const int T_out = len * frames_per_len + frames_add;       // output frames of this stage
   const int F = len * 120 + 1;                               // stft frames
-  if (t >= T_alloc) return;
-  const long long orow = ((long long)b * T_alloc + t) * C;
-  if (t >= T_out) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      out32[orow + c] = 0.f;
-      out16[orow + c] = __float2half_rn(0.f);
-    }
-    return;
-  }
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = bias[c];
-    for (int j = 0; j < k; j++) {
-      const int f = t * stride + j - pad;
-      if (f < 0 || f >= F) continue;
-      const float* sp = stft + ((long long)b * F_alloc + f) * 18;
-      const float* wp = w + (long long)j * 18 * C + c;
+  if (t0 >= T_alloc || c4 >= C) return;
+  float acc[4][4];
+  const float4 bv = *reinterpret_cast<const float4*>(bias + c4);
 #pragma unroll
-      for (int ch = 0; ch < 18; ch++) acc += sp[ch] * wp[(long long)ch * C];
+  for (int f = 0; f < 4; f++) { acc[f][0] = bv.x; acc[f][1] = bv.y; acc[f][2] = bv.z; acc[f][3] = bv.w; }
+  if (t0 < T_out) {
+    const float* sb = stft + (long long)b * F_alloc * 18;
+    for (int j = 0; j < k; j++) {
+      int fr[4];
+      bool ok[4];
+#pragma unroll
+      for (int f = 0; f < 4; f++) {
+        fr[f] = (t0 + f) * stride + j - pad;
+        ok[f] = fr[f] >= 0 && fr[f] < F;
+      }
+      const float* wp = w + (long long)j * 18 * C + c4;
+#pragma unroll 6
+      for (int ch = 0; ch < 18; ch++) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wp + (long long)ch * C));
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+          const float sv = ok[f] ? __ldg(sb + (long long)fr[f] * 18 + ch) : 0.f;
+          acc[f][0] = fmaf(sv, wv.x, acc[f][0]);
+          acc[f][1] = fmaf(sv, wv.y, acc[f][1]);
+          acc[f][2] = fmaf(sv, wv.z, acc[f][2]);
+          acc[f][3] = fmaf(sv, wv.w, acc[f][3]);
+        }
+      }
     }
-    out32[orow + c] = acc;
-    out16[orow + c] = __float2half_rn(snake_f(acc, alpha[c]));
+  }
+  const float4 av = *reinterpret_cast<const float4*>(alpha + c4);
+#pragma unroll
+  for (int f = 0; f < 4; f++) {
+    const int t = t0 + f;
+    if (t >= T_alloc) break;
+    const bool valid = t < T_out;
+    const long long o = ((long long)b * T_alloc + t) * C + c4;
+    float4 v = valid ? make_float4(acc[f][0], acc[f][1], acc[f][2], acc[f][3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(out32 + o) = v;
+    __half2 h0 = __floats2half2_rn(valid ? snake_f(v.x, av.x) : 0.f, valid ? snake_f(v.y, av.y) : 0.f);
+    __half2 h1 = __floats2half2_rn(valid ? snake_f(v.z, av.z) : 0.f, valid ? snake_f(v.w, av.w) : 0.f);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(out16 + o) = u;
   }
 }
 void launch_source_down(const float* stft, int F_alloc, const float* w, const float* bias, int k, int stride, int pad, int C,
                         const int* lens, int len_all, int frames_per_len, int frames_add, float* out32, __half* out16,
                         const float* alpha, int B, int T_alloc, cudaStream_t st) {
-  const int tx = C >= 128 ? 128 : 64;
-  const int ty = 256 / tx;
-  source_down_kernel<<<dim3((T_alloc + ty - 1) / ty, B), dim3(tx, ty), 0, st>>>(stft, F_alloc, w, bias, k, stride, pad, C, lens,
-                                                                                  len_all, frames_per_len, frames_add, out32,
-                                                                                  out16, alpha, T_alloc);
+  const int tx = C / 4;            // 64 / 32 / 16 threads along channels
+  const int ty = 256 / tx;         // frames-of-4 per block
+  const int frames_per_block = ty * 4;
+  source_down_kernel<<<dim3((T_alloc + frames_per_block - 1) / frames_per_block, B), dim3(tx, ty), 0, st>>>(
+      stft, F_alloc, w, bias, k, stride, pad, C, lens, len_all, frames_per_len, frames_add, out32, out16, alpha, T_alloc);
   CV2_LAUNCH_CHECK();
 }
 
