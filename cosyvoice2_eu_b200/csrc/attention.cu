@@ -2,30 +2,33 @@
 // 8 heads x 64, softmax(q k^T / 8 + mask) v).  The mask is never materialised: it is generated from
 // integers (valid length per sequence; optional block-causal chunk) inside the kernel.
 //
-// One CTA = 128 query rows of one (sequence, head).  warp 0: TMA producer (Q once, K/V tiles through a
-// 3-stage ring), warp 1: tcgen05.mma issuer (S = Q K^T into a double-buffered TMEM tile, O += P V),
-// warps 2-5: online softmax, thread-per-row, P written 16-bit into 128B-swizzled smem as the A operand
-// of the PV MMA; O accumulates in TMEM and is rescaled in place when the running max moves.
+// One CTA = 128 query rows of one (sequence, head), key tiles of 64.  warp 0: TMA producer (Q once, K/V tiles through
+// a 2-stage ring), warp 1: tcgen05.mma issuer (S = Q K^T into TMEM, O += P V), warps 2-5: online softmax, thread-per-row
+// with the whole 64-logit row in registers, P written 16-bit into 128B-swizzled smem as the A operand of the PV MMA;
+// O accumulates in TMEM and is rescaled in place when the running max moves.
+// Small footprint on purpose (64 KB smem, 128 TMEM columns, <= 112 registers): THREE CTAs per SM, so that while one CTA
+// waits on its MMA / barrier round trip the others keep the MUFU (exp2) and tensor pipes busy -- the kernel is MUFU-bound
+// (head_dim 64: one exp2 per 256 MMA FLOPs).
 #include "attention.cuh"
 #include "common.cuh"
 #include "host_util.h"
 
 namespace cv2 {
 
-static constexpr int kQBytes = 128 * 64 * 2;   // 16 KB
-static constexpr int kKBytes = 128 * 64 * 2;   // 128 keys x 64 d
-static constexpr int kVBytes = 2 * 64 * 64 * 2;  // two [64 d x 64 keys] boxes
+static constexpr int kKT = 64;                          // keys per tile
+static constexpr int kQBytes = 128 * 64 * 2;            // 16 KB
+static constexpr int kKBytes = kKT * 64 * 2;            // 64 keys x 64 d   (B operand of S, K-major)
+static constexpr int kVBytes = 64 * kKT * 2;            // 64 d x 64 keys   (B operand of PV, K-major: v stored transposed)
 static constexpr int kKVStages = 2;
-static constexpr int kPBytes = 2 * 128 * 64 * 2;  // 128 rows x 128 keys, two K-atoms
+static constexpr int kPBytes = 128 * kKT * 2;           // 128 rows x 64 keys, one swizzle atom column
 static constexpr int kOffK = kQBytes;
 static constexpr int kOffV = kOffK + kKVStages * kKBytes;
 static constexpr int kOffP = kOffV + kKVStages * kVBytes;
 static constexpr int kOffBar = kOffP + kPBytes;
-static constexpr int kAttnSmem = kOffBar + 256;   // 112.25 KB: two CTAs per SM
+static constexpr int kAttnSmem = kOffBar + 256;         // 64.25 KB
+static constexpr uint32_t kTmemS = 0, kTmemO = 64;      // column offsets (128 allocated)
 
-static constexpr uint32_t kTmemS = 0, kTmemO = 128;   // column offsets (256 allocated: two CTAs share the SM's 512)
-
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(192, 3)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   const int t0 = blockIdx.x * 128;
@@ -37,7 +40,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   // number of key tiles this query tile can see
   int kv_end = len;
   if (p.chunk > 0) kv_end = min(len, ((t0 + 127) / p.chunk + 1) * p.chunk);
-  const int nkt = (kv_end + 127) / 128;
+  const int nkt = (kv_end + kKT - 1) / kKT;
 
   extern __shared__ __align__(1024) uint8_t smem[];   // swizzle-128B tiles need 1024 B alignment
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
@@ -66,7 +69,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -81,25 +84,24 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const uint32_t ph = (j / kKVStages) & 1;
         mbar_wait(&kv_empty[st], ph ^ 1);
         mbar_expect_tx(&kv_full[st], kKBytes + kVBytes);
-        tma_load_3d(smem + kOffK + st * kKBytes, &tmK, &kv_full[st], 0, j * 128, sh);
-        tma_load_3d(smem + kOffV + st * kVBytes, &tmV, &kv_full[st], j * 128, 0, sh);
-        tma_load_3d(smem + kOffV + st * kVBytes + 8192, &tmV, &kv_full[st], j * 128 + 64, 0, sh);
+        tma_load_3d(smem + kOffK + st * kKBytes, &tmK, &kv_full[st], 0, j * kKT, sh);
+        tma_load_3d(smem + kOffV + st * kVBytes, &tmV, &kv_full[st], j * kKT, 0, sh);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0);
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, kKT, 0);
       constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0);
       const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(smem));
-      const uint32_t p_addr = smem_u32(smem + kOffP);
+      const uint64_t p_desc = umma_smem_desc_sw128(smem_u32(smem + kOffP));
       auto issue_s = [&](int j) {
         const int st = j % kKVStages;
         mbar_wait(&kv_full[st], (j / kKVStages) & 1);
         tc_fence_after();
         const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(smem + kOffK + st * kKBytes));
-        const uint32_t d = tmem_base + kTmemS;
 #pragma unroll
-        for (int k = 0; k < 4; k++) umma_f16(d, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0);
+        for (int k = 0; k < 4; k++)
+          umma_f16(tmem_base + kTmemS, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0);
         umma_commit(s_full);
       };
       mbar_wait(q_full, 0);
@@ -109,15 +111,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc_fence_after();
         if (j + 1 < nkt) issue_s(j + 1);   // S buffer is free again: next logits first, so softmax j+1 overlaps PV_j
         const int st = j % kKVStages;
-        const uint32_t v_addr = smem_u32(smem + kOffV + st * kVBytes);
+        const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(smem + kOffV + st * kVBytes));
 #pragma unroll
-        for (int a = 0; a < 2; a++) {
-          const uint64_t pa = umma_smem_desc_sw128(p_addr + a * 16384);
-          const uint64_t vb = umma_smem_desc_sw128(v_addr + a * 8192);
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            umma_f16(tmem_base + kTmemO, pa + (uint64_t)(k * 2), vb + (uint64_t)(k * 2), idesc_o, (j | a | k) != 0);
-        }
+        for (int k = 0; k < kKT / 16; k++)
+          umma_f16(tmem_base + kTmemO, p_desc + (uint64_t)(k * 2), v_desc + (uint64_t)(k * 2), idesc_o, (j | k) != 0);
         umma_commit(&kv_empty[st]);
         umma_commit(pv_done);
       }
@@ -137,21 +134,20 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const uint32_t s_addr = lane_addr + kTmemS;
-      const int kbase = j * 128;
-      // whole S row (128 visible-key logits) into registers: four TMEM loads in flight, one wait
-      uint32_t sr[128];
+      const int kbase = j * kKT;
+      // whole S row (64 logits) into registers: two TMEM loads in flight, one wait
+      uint32_t sr[kKT];
 #pragma unroll
-      for (int c = 0; c < 4; c++) tmem_ld32(s_addr + c * 32, sr + c * 32);
+      for (int c = 0; c < kKT / 32; c++) tmem_ld32(s_addr + c * 32, sr + c * 32);
       tmem_ld_wait();
-      const bool all_visible = kbase + 128 <= kv_lim;   // no masking needed inside this tile for this row
-      if (!all_visible) {
+      if (kbase + kKT > kv_lim) {   // masking needed inside this tile for this row
 #pragma unroll
-        for (int i = 0; i < 128; i++)
+        for (int i = 0; i < kKT; i++)
           if (kbase + i >= kv_lim) sr[i] = 0xff800000u;   // -inf
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
+      for (int i = 0; i < kKT; i += 4) {
         mx0 = fmaxf(mx0, __uint_as_float(sr[i]));
         mx1 = fmaxf(mx1, __uint_as_float(sr[i + 1]));
         mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2]));
@@ -160,17 +156,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
       const float alpha = (m == -INFINITY) ? 0.f : fast_exp2((m - m_new) * LOG2E);
       const float mscaled = (m_new == -INFINITY) ? 0.f : m_new * LOG2E;
-      // probabilities in place (exp2(-inf) = 0 for masked keys)
+      // probabilities in place (exp2(-inf) = 0 for masked keys), packed to fp16 pairs
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
+      for (int i = 0; i < kKT; i += 4) {
         const float e0 = fast_exp2(fmaf(__uint_as_float(sr[i]), LOG2E, -mscaled));
         const float e1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), LOG2E, -mscaled));
         const float e2 = fast_exp2(fmaf(__uint_as_float(sr[i + 2]), LOG2E, -mscaled));
         const float e3 = fast_exp2(fmaf(__uint_as_float(sr[i + 3]), LOG2E, -mscaled));
         l0 += e0; l1 += e1; l2 += e2; l3 += e3;
         __half2 h0 = __floats2half2_rn(e0, e1), h1 = __floats2half2_rn(e2, e3);
-        sr[i >> 1] = *reinterpret_cast<uint32_t*>(&h0);          // pack in place: 64 words of fp16 pairs
+        sr[i >> 1] = *reinterpret_cast<uint32_t*>(&h0);
         sr[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
       }
       // PV of the previous tile must be complete before O is rescaled or P overwritten
@@ -189,12 +185,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
       }
       l = l * alpha + ((l0 + l1) + (l2 + l3));
-      // P tile, 16-bit, swizzled K-major: 16 x 16-byte groups per row
+      // P tile, 16-bit, swizzled K-major: 8 x 16-byte groups per row
 #pragma unroll
-      for (int g = 0; g < 16; g++) {
+      for (int g = 0; g < kKT / 8; g++) {
         uint4 u;
         u.x = sr[g * 4 + 0]; u.y = sr[g * 4 + 1]; u.z = sr[g * 4 + 2]; u.w = sr[g * 4 + 3];
-        *reinterpret_cast<uint4*>(prow + (g >> 3) * 16384 + (((g & 7) ^ (r & 7)) << 4)) = u;
+        *reinterpret_cast<uint4*>(prow + ((g ^ (r & 7)) << 4)) = u;
       }
       m = m_new;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -232,7 +228,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<256>(tmem_base);
+  if (warp == 1) tmem_dealloc<128>(tmem_base);
 }
 
 void launch_flash_attn(const AttnParams& p, cudaStream_t stream) {
@@ -246,11 +242,12 @@ void launch_flash_attn(const AttnParams& p, cudaStream_t stream) {
   uint64_t dq[3] = {64, (uint64_t)p.T_alloc, SH};
   uint64_t sq[2] = {128, (uint64_t)p.T_alloc * 128};
   uint32_t bq[3] = {64, 128, 1};
+  uint32_t bk[3] = {64, (uint32_t)kKT, 1};
   CUtensorMap tmQ = make_tmap_16b(p.q, 3, dq, sq, bq);
-  CUtensorMap tmK = make_tmap_16b(p.k, 3, dq, sq, bq);
+  CUtensorMap tmK = make_tmap_16b(p.k, 3, dq, sq, bk);
   uint64_t dv[3] = {(uint64_t)p.T_alloc, 64, SH};
   uint64_t sv[2] = {(uint64_t)p.T_alloc * 2, (uint64_t)p.T_alloc * 128};
-  uint32_t bv[3] = {64, 64, 1};
+  uint32_t bv[3] = {(uint32_t)kKT, 64, 1};
   CUtensorMap tmV = make_tmap_16b(p.vt, 3, dv, sv, bv);
   dim3 grid(p.T_alloc / 128, p.heads, p.S);
   flash_attn_kernel<<<grid, 192, kAttnSmem, stream>>>(tmQ, tmK, tmV, p);
