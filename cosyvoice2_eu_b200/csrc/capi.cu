@@ -94,6 +94,13 @@ int cv2_engine_finalize(cv2_engine* h, int need_flow, int need_hift) {
 
 long long cv2_engine_last_launches(cv2_engine* h) { return h ? h->e.launches : -1; }
 
+int cv2_engine_set_seed_ptr(cv2_engine* h, const unsigned long long* seed_dev) {
+  CV2_API_BEGIN
+  CV2_CHECK(h, "null engine");
+  h->e.seed_dev = seed_dev;
+  CV2_API_END
+}
+
 int cv2_engine_set_profiling(cv2_engine* h, int on) {
   CV2_API_BEGIN
   CV2_CHECK(h, "null engine");
@@ -308,7 +315,7 @@ int cv2_op_istft(void* stream, const float* cp, int F_alloc, const int32_t* lens
 int cv2_op_nsf_source(void* stream, const float* f0, int mel_T, const int32_t* lens, const float* noise, unsigned long long seed,
                       const float* lw, const float* lb, float* phase_ws, float* src, int B) {
   CV2_API_BEGIN
-  launch_nsf_source(f0, mel_T, phase_ws, mel_T, lens, mel_T, noise, (long long)480 * mel_T * 9, seed, lw, lb, nullptr, 0, 0, src,
+  launch_nsf_source(f0, mel_T, phase_ws, mel_T, lens, mel_T, noise, (long long)480 * mel_T * 9, seed, nullptr, lw, lb, nullptr, 0, 0, src,
                     (long long)480 * mel_T, B, mel_T, (cudaStream_t)stream);
   CV2_API_END
 }

@@ -65,6 +65,7 @@ struct Engine {
   std::unordered_map<std::string, TensorRef> tensors;
   bool finalized = false;
   bool has_flow = false, has_hift = false;
+  const unsigned long long* seed_dev = nullptr;   // optional device-resident NSF noise seed (CUDA-graph replays)
   std::unordered_map<std::string, Weight> weights;      // lazily built from tensors
   std::unordered_map<uint64_t, CUtensorMap> amap_cache;  // activation tensor maps
   long long launches = 0;                                // kernels launched by the last forward (claims for bench)

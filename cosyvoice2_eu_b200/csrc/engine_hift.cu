@@ -84,7 +84,7 @@ size_t hift_forward(Engine& e, cudaStream_t st, const HiftArgs& a, Arena& ws) {
     if (a.f0_out) CV2_CUDA(cudaMemcpy2DAsync(a.f0_out, (size_t)a.mel_T * 4, F0, (size_t)Ta[0] * 4, (size_t)a.mel_T * 4, B,
                                              cudaMemcpyDeviceToDevice, st));
     e.prof_begin(st, Engine::F_NSF);
-    launch_nsf_source(F0, Ta[0], PH, Ta[0], lens[0], 0, a.noise, (long long)480 * a.mel_T * 9, a.seed, e.f32("hift.src.lw"),
+    launch_nsf_source(F0, Ta[0], PH, Ta[0], lens[0], 0, a.noise, (long long)480 * a.mel_T * 9, a.seed, e.seed_dev, e.f32("hift.src.lw"),
                       e.f32("hift.src.lb"), a.cache_source, a.cache_len, a.cache_len, a.source, (long long)480 * a.mel_T, B,
                       a.mel_T, st);
     e.prof_end(st);

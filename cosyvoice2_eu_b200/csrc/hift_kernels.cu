@@ -137,7 +137,8 @@ __device__ __forceinline__ float gauss_hash(unsigned long long seed, unsigned lo
 
 __global__ void nsf_source_kernel(const float* __restrict__ f0, int f0_stride, const float* __restrict__ P, int T_alloc,
                                   const int* __restrict__ lens, int len_all, const float* __restrict__ noise,
-                                  long long noise_bstride, unsigned long long seed, const float* __restrict__ lw,
+                                  long long noise_bstride, unsigned long long seed, const unsigned long long* __restrict__ seed_ptr,
+                                  const float* __restrict__ lw,
                                   const float* __restrict__ lb, const float* __restrict__ cache, int cache_len,
                                   long long cache_bstride, float* __restrict__ src, long long src_bstride) {
   const int b = blockIdx.y;
@@ -163,6 +164,7 @@ __global__ void nsf_source_kernel(const float* __restrict__ f0, int f0_stride, c
   const float* p0 = P + ((long long)b * T_alloc + i0) * 9;
   const float* p1 = P + ((long long)b * T_alloc + i1) * 9;
   const float* nz = noise ? noise + (long long)b * noise_bstride + j * 9 : nullptr;
+  if (seed_ptr) seed = *seed_ptr;   // device-resident seed: a captured CUDA graph still draws fresh noise per replay
   float acc = lb[0];
 #pragma unroll
   for (int h = 0; h < 9; h++) {
@@ -174,14 +176,15 @@ __global__ void nsf_source_kernel(const float* __restrict__ f0, int f0_stride, c
   src[(long long)b * src_bstride + j] = tanhf(acc);
 }
 void launch_nsf_source(const float* f0, int f0_stride, float* P, int T_alloc, const int* lens, int len_all, const float* noise,
-                       long long noise_bstride, unsigned long long seed, const float* lw, const float* lb, const float* cache,
+                       long long noise_bstride, unsigned long long seed, const unsigned long long* seed_ptr, const float* lw,
+                       const float* lb, const float* cache,
                        int cache_len, long long cache_bstride, float* src, long long src_bstride, int B, int max_len,
                        cudaStream_t st) {
   nsf_phase_kernel<<<B, 32, 0, st>>>(f0, f0_stride, lens, len_all, P, T_alloc);
   CV2_LAUNCH_CHECK();
   const long long Lmax = (long long)max_len * 480;
   nsf_source_kernel<<<dim3((unsigned)((Lmax + 255) / 256), B), 256, 0, st>>>(f0, f0_stride, P, T_alloc, lens, len_all, noise,
-                                                                             noise_bstride, seed, lw, lb, cache, cache_len,
+                                                                             noise_bstride, seed, seed_ptr, lw, lb, cache, cache_len,
                                                                              cache_bstride, src, src_bstride);
   CV2_LAUNCH_CHECK();
 }

@@ -341,3 +341,83 @@ class B200Token2Wav:
                 noise[b, :nz.shape[-2]] = nz.reshape(-1, 9)
         speech, _ = self.hift.inference(mel, noise=noise, lens=mel_lens)
         return speech, mel_lens * 480
+
+
+class GraphedToken2Wav:
+    """Offline token2wav replayed from a CUDA graph (latency path, BASELINE configs[1]).
+
+    A whole flow.inference + hift.inference is ~3.6 k kernel launches and no host synchronisation, so it is captured once
+    per shape bucket (batch size, token capacity, prompt capacity) and replayed: per-utterance lengths live on the device,
+    so one graph serves every utterance that fits the bucket.  The NSF noise seed is device resident and bumped per replay."""
+
+    def __init__(self, t2w: B200Token2Wav, bucket=32):
+        self.t2w, self.flow, self.hift = t2w, t2w.flow, t2w.hift
+        self.dev = t2w.device
+        self.bucket = bucket
+        self.graphs = {}
+        self.seed = torch.zeros(1, dtype=torch.int64, device=self.dev)
+
+    def _key(self, tl, pl):
+        up = lambda x: (x + self.bucket - 1) // self.bucket * self.bucket
+        return (len(tl), up(max(tl)), up(max(pl)))
+
+    def _build(self, key):
+        B, cap_t, cap_p = key
+        dev = self.dev
+        st = dict(tok=torch.zeros(B, cap_t, dtype=torch.int32, device=dev), ptk=torch.zeros(B, cap_p, dtype=torch.int32, device=dev),
+                  pf=torch.zeros(B, 2 * cap_p, 80, device=dev), emb=torch.zeros(B, 192, device=dev),
+                  lens=torch.ones(3, B, dtype=torch.int32, device=dev) * 8, mel_lens=torch.ones(B, dtype=torch.int32, device=dev) * 8)
+        st["lens"][2] = 16
+        st["host"] = dict(tok=torch.zeros(B, cap_t, dtype=torch.int32).pin_memory(), ptk=torch.zeros(B, cap_p, dtype=torch.int32).pin_memory(),
+                          pf=torch.zeros(B, 2 * cap_p, 80).pin_memory(), emb=torch.zeros(B, 192).pin_memory(),
+                          lens=torch.zeros(3, B, dtype=torch.int32).pin_memory(), mel_lens=torch.zeros(B, dtype=torch.int32).pin_memory())
+        max_total, mel_T = cap_t + cap_p, 2 * cap_t
+        eng = self.flow.eng
+
+        def run():
+            (mel,) = self.flow._forward_device(st["tok"], st["lens"][0], st["ptk"], st["lens"][1], st["pf"], st["lens"][2], st["emb"],
+                                               B, max_total, mel_T, False, True)
+            speech, _ = self.hift.inference(mel, lens=st["mel_lens"])
+            return speech, mel
+
+        _lib.check(eng.lib.cv2_engine_set_seed_ptr(eng.h, _lib.ptr(self.seed)))
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up on the capture stream: workspaces, func attributes, tensor-map caches
+            run()
+            run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            st["speech"], st["mel"] = run()
+        st["graph"] = g
+        _lib.check(eng.lib.cv2_engine_set_seed_ptr(eng.h, None))
+        return st
+
+    @torch.inference_mode()
+    def __call__(self, tokens, prompt_tokens, prompt_feats, embeddings):
+        """Same contract as B200Token2Wav.token2wav_batch; the returned tensor is overwritten by the next call."""
+        tl = [int(t.numel()) for t in tokens]
+        pl = [int(t.numel()) for t in prompt_tokens]
+        key = self._key(tl, pl)
+        st = self.graphs.get(key)
+        if st is None:
+            st = self.graphs[key] = self._build(key)
+        h = st["host"]
+        for k in ("tok", "ptk", "pf", "emb"):
+            h[k].zero_()
+        for b in range(len(tl)):
+            h["tok"][b, :tl[b]] = tokens[b].reshape(-1).to(torch.int32)
+            h["ptk"][b, :pl[b]] = prompt_tokens[b].reshape(-1).to(torch.int32)
+            h["pf"][b, :prompt_feats[b].shape[0]] = prompt_feats[b].reshape(-1, 80)
+            h["emb"][b] = embeddings[b].reshape(192)
+        h["lens"].copy_(torch.tensor([tl, pl, [int(f.shape[0]) for f in prompt_feats]], dtype=torch.int32))
+        mel_lens = [2 * a for a in tl]
+        h["mel_lens"].copy_(torch.tensor(mel_lens, dtype=torch.int32))
+        for k in ("tok", "ptk", "pf", "emb", "lens", "mel_lens"):
+            st[k].copy_(h[k], non_blocking=True)
+        self.seed += 1
+        st["graph"].replay()
+        self.last_mel = st["mel"]
+        return st["speech"], torch.tensor(mel_lens, dtype=torch.int32) * 480

@@ -42,6 +42,9 @@ long long cv2_engine_last_launches(cv2_engine* e);
 
 /* per-launch CUDA-event timing on the launching stream, summed per kernel family (bench.py roofline):
  * 0 gemm<64> 1 gemm<128> 2 gemm<256> 3 flash_attn 4 rel_attn 5 f0_conv 6 nsf_source 7 source_stft 8 source_down 9 istft 10 layernorm */
+/* optional device-resident seed of the in-kernel NSF noise generator (read at kernel run time, so a captured CUDA graph
+ * draws fresh noise on every replay); NULL restores the by-value `seed` argument of cv2_hift_forward */
+int cv2_engine_set_seed_ptr(cv2_engine* e, const unsigned long long* seed_dev);
 int cv2_engine_set_profiling(cv2_engine* e, int on);
 int cv2_engine_read_profile(cv2_engine* e, double* ms_per_family, long long* launches_per_family, int n_families);
 

@@ -170,3 +170,21 @@ def test_streaming_schedule(engine, golden):
         ref = g[f"chunk{ci}"]
         assert tuple(w.shape) == ref.shape
         print("stream chunk", ci, "shape", tuple(w.shape), "e2e SNR", snr_db(ref, w.cpu().numpy()))
+
+
+def test_cuda_graph_replay_matches_eager(engine):
+    """One captured graph serves every utterance of its shape bucket (lengths are device side)."""
+    from cosyvoice2_eu_b200 import GraphedToken2Wav
+    flow, hift, t2w = engine
+    g = GraphedToken2Wav(t2w)
+    for n, p, s in ((30, 10, 1), (25, 12, 6), (31, 9, 7)):       # same (32, 32) bucket
+        u = _utt(dict(n_tok=n, n_prompt=p, seed=s))
+        wav, lens = g([u["token"][0]], [u["prompt_token"][0]], [u["prompt_feat"][0]], [u["embedding"][0]])
+        torch.cuda.synchronize()
+        mel_e, _ = flow.inference(u["token"], None, u["prompt_token"], None, u["prompt_feat"], None, u["embedding"], False, True)
+        n_mel = 2 * n
+        assert int(lens[0]) == 480 * n_mel
+        assert float((g.last_mel[0, :, :n_mel] - mel_e[0]).abs().max()) < 1e-5
+        assert bool(torch.isfinite(wav).all()) and float(wav[0, :480 * n_mel].abs().max()) > 1e-3
+        assert float(wav[0, 480 * n_mel:].abs().max()) == 0.0
+    assert len(g.graphs) == 1
