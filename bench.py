@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 N_PROMPT = 75
 BATCH = 64
 FAMILIES = ["gemm_tap<64>", "gemm_tap<128>", "gemm_tap<256>", "flash_attn", "rel_attn", "f0_conv_f32", "nsf_source", "source_stft",
-            "source_down", "istft", "layernorm"]
+            "source_down", "istft", "ffn_fused"]
 # gemm_tap<256> launches are additionally split by epilogue specialisation (engine families 11 + spec)
 G256 = ["generic", "qkv_split", "res+ln_emit", "gelu", "conv+ln+mish+temb", "conv+ln+mish+res+ln_emit", "res+plain_emit", "silu",
         "res", "out32", "plain_emit", "snake", "res+snake_emit", "res_sum"]
@@ -58,7 +58,10 @@ def algorithmic_flops(n_tokens, n_prompt=N_PROMPT):
         T = 2 * tt                 # mel frames seen by the estimator
         tg = 2 * n                 # generated mel frames (hift)
         est_lin = 132161536.0
-        f["gemm_tap<256>"] += 20 * T * (est_lin - 40960.0)
+        ffn = 56 * 2 * 2 * 256 * 1024.0          # FF1 + FF2 of the 56 transformer blocks, per frame per CFG row
+        fused = os.environ.get("CV2_NO_FFN_FUSION") is None
+        f["gemm_tap<256>"] += 20 * T * (est_lin - 40960.0 - (ffn if fused else 0.0))
+        f["ffn_fused"] += 20 * T * (ffn if fused else 0.0)
         f["gemm_tap<128>"] += 20 * T * 40960.0
         f["flash_attn"] += 20 * T * 114688.0 * T
         f["gemm_tap<256>"] += tt * (4.194304e6 + 6 * 7.340032e6) + T * (3.227648e6 - 81920.0 + 4 * 7.340032e6)

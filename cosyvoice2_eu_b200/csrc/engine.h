@@ -6,11 +6,13 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <string>
 #include <unordered_map>
 #include <vector>
 
+#include "ffn_fused.cuh"
 #include "gemm_tap.cuh"
 #include "host_util.h"
 
@@ -65,6 +67,7 @@ struct Engine {
   std::unordered_map<std::string, TensorRef> tensors;
   bool finalized = false;
   bool has_flow = false, has_hift = false;
+  bool fuse_ffn = getenv("CV2_NO_FFN_FUSION") == nullptr;   // estimator FF1+GELU+FF2 in one kernel (ffn_fused.cu)
   const unsigned long long* seed_dev = nullptr;   // optional device-resident NSF noise seed (CUDA-graph replays)
   std::unordered_map<std::string, Weight> weights;      // lazily built from tensors
   std::unordered_map<uint64_t, CUtensorMap> amap_cache;  // activation tensor maps
@@ -82,7 +85,7 @@ struct Engine {
 
   // ---- optional per-launch timing (CUDA events on the launching stream), grouped by kernel family ----
   enum Family { F_GEMM64 = 0, F_GEMM128, F_GEMM256, F_FLASH_ATTN, F_REL_ATTN, F_F0_CONV, F_NSF, F_STFT, F_SRC_DOWN, F_ISTFT,
-                F_LAYERNORM, F_COUNT };
+                F_FFN_FUSED, F_COUNT };
   bool profiling = false;
   struct ProfRec { int family; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
@@ -124,6 +127,10 @@ struct Engine {
   // A: 16-bit [S, T_alloc, ld] (first Kc columns used).  Remaining epilogue fields come in through `p`.
   void gemm(cudaStream_t st, const __half* A, int S, int T_alloc, int Kc, long long ldA, Weight& w, int bn, int ntaps,
             const int* tap_off, GemmParams p, bool dry);
+  // fused FF1 -> GELU -> FF2 -> +residual -> emits (H: 16-bit [S, T_alloc, 256])
+  void ffn(cudaStream_t st, const __half* H, int S, int T_alloc, Weight& w1, Weight& w2, FfnParams p, bool dry);
+  const CUtensorMap& amap(const __half* A, int S, int T_alloc, int Kc, long long ldA);
+  const CUtensorMap& wmap(Weight& w, int bn);
 };
 
 // forward passes (engine_flow.cu / engine_hift.cu)

@@ -39,6 +39,54 @@ void Engine::make_tile_list(cudaStream_t st, Arena& ws, const int* lens, int S, 
   if (alias1) tile_lists[tl_key(alias1, T_alloc, S)] = tl;
 }
 
+const CUtensorMap& Engine::wmap(Weight& w, int bn) {
+  const int bi = bn == 64 ? 0 : (bn == 128 ? 1 : 2);
+  if (!w.map_ok[bi]) {
+    uint64_t dims[2] = {(uint64_t)w.Ktot, (uint64_t)w.N};
+    uint64_t strides[1] = {(uint64_t)w.Ktot * 2};
+    uint32_t box[2] = {64, (uint32_t)bn};
+    w.map[bi] = make_tmap_16b(w.w, 2, dims, strides, box);
+    w.map_ok[bi] = true;
+  }
+  return w.map[bi];
+}
+
+const CUtensorMap& Engine::amap(const __half* A, int S, int T_alloc, int Kc, long long ldA) {
+  uint64_t key = mix(mix(mix(mix(mix(0x1234, (uint64_t)(uintptr_t)A), (uint64_t)Kc), (uint64_t)ldA), (uint64_t)T_alloc), (uint64_t)S);
+  auto it = amap_cache.find(key);
+  if (it == amap_cache.end()) {
+    uint64_t dims[3] = {(uint64_t)Kc, (uint64_t)T_alloc, (uint64_t)S};
+    uint64_t strides[2] = {(uint64_t)ldA * 2, (uint64_t)T_alloc * (uint64_t)ldA * 2};
+    uint32_t box[3] = {64, 128, 1};
+    if (amap_cache.size() > 8192) amap_cache.clear();
+    it = amap_cache.emplace(key, make_tmap_16b(A, 3, dims, strides, box)).first;
+  }
+  return it->second;
+}
+
+void Engine::ffn(cudaStream_t st, const __half* H, int S, int T_alloc, Weight& w1, Weight& w2, FfnParams p, bool dry) {
+  CV2_CHECK(w1.N == 1024 && w1.Ktot == 256 && w2.N == 256 && w2.Ktot == 1024, "ffn: unexpected weight shapes");
+  p.S = S;
+  p.T_alloc = T_alloc;
+  p.b1 = w1.b;
+  p.b2 = w2.b;
+  launches++;
+  if (dry) return;
+  if (p.lens && !p.tile_list && S > 1) {
+    auto tl = tile_lists.find(tl_key(p.lens, T_alloc, S));
+    if (tl != tile_lists.end()) {
+      p.tile_list = tl->second.list;
+      p.tile_count = tl->second.count;
+    }
+  }
+  const CUtensorMap& th = amap(H, S, T_alloc, 256, 256);
+  const CUtensorMap& t1 = wmap(w1, 128);
+  const CUtensorMap& t2 = wmap(w2, 128);
+  prof_begin(st, F_FFN_FUSED);
+  launch_ffn_fused(th, t1, t2, p, st);
+  prof_end(st);
+}
+
 void Engine::gemm(cudaStream_t st, const __half* A, int S, int T_alloc, int Kc, long long ldA, Weight& w, int bn, int ntaps,
                   const int* tap_off, GemmParams p, bool dry) {
   const int kb = (Kc + 63) / 64;
@@ -64,24 +112,10 @@ void Engine::gemm(cudaStream_t st, const __half* A, int S, int T_alloc, int Kc, 
     }
   }
   const int bi = bn == 64 ? 0 : (bn == 128 ? 1 : 2);
-  if (!w.map_ok[bi]) {
-    uint64_t dims[2] = {(uint64_t)w.Ktot, (uint64_t)w.N};
-    uint64_t strides[1] = {(uint64_t)w.Ktot * 2};
-    uint32_t box[2] = {64, (uint32_t)bn};
-    w.map[bi] = make_tmap_16b(w.w, 2, dims, strides, box);
-    w.map_ok[bi] = true;
-  }
-  uint64_t key = mix(mix(mix(mix(mix(0x1234, (uint64_t)(uintptr_t)A), (uint64_t)Kc), (uint64_t)ldA), (uint64_t)T_alloc), (uint64_t)S);
-  auto it = amap_cache.find(key);
-  if (it == amap_cache.end()) {
-    uint64_t dims[3] = {(uint64_t)Kc, (uint64_t)T_alloc, (uint64_t)S};
-    uint64_t strides[2] = {(uint64_t)ldA * 2, (uint64_t)T_alloc * (uint64_t)ldA * 2};
-    uint32_t box[3] = {64, 128, 1};
-    if (amap_cache.size() > 8192) amap_cache.clear();
-    it = amap_cache.emplace(key, make_tmap_16b(A, 3, dims, strides, box)).first;
-  }
+  const CUtensorMap& tb = wmap(w, bn);
+  const CUtensorMap& ta = amap(A, S, T_alloc, Kc, ldA);
   prof_begin(st, bn == 256 ? F_COUNT + gemm_tap_spec(bn, p) : bi);
-  launch_gemm_tap(bn, it->second, w.map[bi], p, st);
+  launch_gemm_tap(bn, ta, tb, p, st);
   prof_end(st);
 }
 

@@ -124,6 +124,23 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
         p.emit[0] = emit_ln(b.H16, 256, e.ln(tp + ".ln3"), 1e-5f);
         e.gemm(st, b.ATT16, S, T, 512, 512, e.W(tp + ".o"), 256, 1, tap1, p, dry);
       }
+      if (e.fuse_ffn) {  // FF1 -> GELU -> FF2 -> + residual -> next pre-norm / masked block output, one kernel
+        FfnParams fp;
+        memset(&fp, 0, sizeof(fp));
+        fp.lens = lens; fp.halo = kHalo; fp.x32 = b.X32;
+        if (j < 3) {
+          fp.emit_ln = emit_ln(b.H16, 256, e.ln("est.tfm." + std::to_string(r) + "." + std::to_string(j + 1) + ".ln1"), 1e-5f);
+        } else if (r == 0) {
+          fp.emit_plain[0] = emit_plain(b.CAT16, 512, 256);
+          fp.emit_plain[1] = emit_plain(b.M16, 256);
+        } else if (r == 12) {
+          fp.emit_plain[0] = emit_plain(b.CAT16, 512, 0);
+        } else {
+          fp.emit_plain[0] = emit_plain(b.M16, 256);
+        }
+        e.ffn(st, b.H16, S, T, e.W(tp + ".ff1"), e.W(tp + ".ff2"), fp, dry);
+        continue;
+      }
       {  // FF1 + exact GELU
         GemmParams p = base_params(lens);
         p.act = ACT_GELU;

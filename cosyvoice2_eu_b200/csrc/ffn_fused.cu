@@ -1,0 +1,351 @@
+// Fused transformer feed-forward of the CFM estimator (BasicTransformerBlock FeedForward, matcha transformer.py:83-134,
+// 291-314):   x <- x + W2 * gelu(W1 * h + b1) + b2 ,  h = LayerNorm3(x) (16-bit, produced by the out-proj epilogue),
+// then emit the next block's pre-norm LayerNorm1'(x) (or the masked plain block output) as the next 16-bit A operand.
+//
+// The 1024-wide GELU activation never leaves the SM: per 128-row tile the hidden dimension is processed in 8 chunks of
+// 128; FF1(c) accumulates into a double-buffered 128-column TMEM tile, the epilogue warps apply bias + GELU and write the
+// 16-bit chunk straight into 128B-swizzled shared memory, where it is the A operand of FF2(c), which accumulates the
+// 256-column output tile in TMEM across the 8 chunks.  Weights stream through a 5-slot TMA ring (16 KB slots).
+//   warp 0: TMA (H tile + weight stream)   warp 1: tcgen05.mma issuer   warps 2-9: epilogue
+// Saves the [rows,1024] 16-bit round trip through HBM (4 KB/row of the 18 KB/row a transformer block moves) and one launch.
+#include "common.cuh"
+#include "epi_util.cuh"
+#include "ffn_fused.cuh"
+#include "host_util.h"
+
+namespace cv2 {
+
+static constexpr int kHBytes = 4 * 16384;       // [128 x 256] 16-bit, four 64-column swizzle atoms
+static constexpr int kFBytes = 2 * 16384;       // [128 x 128] 16-bit GELU chunk
+static constexpr int kSlots = 5;
+static constexpr int kSlotBytes = 16384;        // one [128 x 64] weight tile
+static constexpr int kOffF = kHBytes;
+static constexpr int kOffW = kOffF + kFBytes;
+static constexpr int kOffStg = kOffW + kSlots * kSlotBytes;
+static constexpr int kOffRed = kOffStg + 8 * kStgFloats * 4;
+static constexpr int kOffBar = kOffRed + 2 * 2 * 128 * 4;
+static constexpr int kFfnSmem = kOffBar + 256 + 1024;
+static constexpr int kFfnThreads = 64 + 8 * 32;
+static constexpr uint32_t kAcc1 = 0, kAcc2 = 256;   // TMEM columns: acc1 = 2 x 128, acc2 = 256
+
+__device__ __forceinline__ void ffn_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ bool ffn_tile(const FfnParams& p, int tile, int t_tiles, int& s, int& t0, int& len) {
+  if (p.tile_list) {
+    s = __ldg(p.tile_list + 2 * tile);
+    t0 = __ldg(p.tile_list + 2 * tile + 1);
+    len = __ldg(p.lens + s);
+    return true;
+  }
+  s = tile / t_tiles;
+  t0 = (tile % t_tiles) * 128;
+  len = p.lens ? __ldg(p.lens + s) : p.len_all;
+  return t0 < len + p.halo;
+}
+
+// op o of a tile's schedule: FF1(0), FF1(1), FF2(0), FF1(2), FF2(1), ..., FF1(7), FF2(6), FF2(7)
+__device__ __forceinline__ void ffn_op(int o, bool& is_ff2, int& c) {
+  if (o < 2) { is_ff2 = false; c = o; }
+  else if (o == 15) { is_ff2 = true; c = 7; }
+  else if (o & 1) { is_ff2 = false; c = (o + 1) >> 1; }
+  else { is_ff2 = true; c = (o >> 1) - 1; }
+}
+
+__global__ void __launch_bounds__(kFfnThreads, 1)
+ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const FfnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* red = reinterpret_cast<float*>(smem + kOffRed);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* h_full = bars + 0;
+  uint64_t* h_empty = bars + 1;
+  uint64_t* w_full = bars + 2;             // [5]
+  uint64_t* w_empty = bars + 7;            // [5]
+  uint64_t* acc1_full = bars + 12;         // [2]
+  uint64_t* acc1_empty = bars + 14;        // [2]
+  uint64_t* f_full = bars + 16;
+  uint64_t* f_empty = bars + 17;
+  uint64_t* acc2_full = bars + 18;
+  uint64_t* acc2_empty = bars + 19;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int t_tiles = p.T_alloc / 128;
+  const int total_tiles = p.tile_list ? __ldg(p.tile_count) : t_tiles * p.S;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmH);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    mbar_init(h_full, 1);
+    mbar_init(h_empty, 1);
+    for (int i = 0; i < kSlots; i++) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&acc1_full[i], 1);
+      mbar_init(&acc1_empty[i], 8);
+    }
+    mbar_init(f_full, 8);
+    mbar_init(f_empty, 1);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------- TMA producer -------------------------------
+      int lt = 0, wit = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int s, t0, len;
+        if (!ffn_tile(p, tile, t_tiles, s, t0, len)) continue;
+        mbar_wait(h_empty, (lt & 1) ^ 1);
+        mbar_expect_tx(h_full, kHBytes);
+#pragma unroll
+        for (int kb = 0; kb < 4; kb++) tma_load_3d(smem + kb * 16384, &tmH, h_full, kb * 64, t0, s);
+        for (int o = 0; o < 16; o++) {
+          bool is_ff2;
+          int c;
+          ffn_op(o, is_ff2, c);
+          for (int i = 0; i < 4; i++, wit++) {
+            const int st = wit % kSlots;
+            mbar_wait(&w_empty[st], ((wit / kSlots) & 1) ^ 1);
+            mbar_expect_tx(&w_full[st], kSlotBytes);
+            uint8_t* dst = smem + kOffW + st * kSlotBytes;
+            if (!is_ff2) tma_load_2d(dst, &tmW1, &w_full[st], i * 64, c * 128);                       // W1[c*128.., kb*64..]
+            else tma_load_2d(dst, &tmW2, &w_full[st], c * 128 + (i >> 1) * 64, (i & 1) * 128);       // W2[half*128.., c*128+kb*64..]
+          }
+        }
+        lt++;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------- MMA issuer ---------------------------------
+      constexpr uint32_t idesc = umma_idesc_f16(128, 128, 0);
+      const uint32_t h_addr = smem_u32(smem);
+      const uint32_t f_addr = smem_u32(smem + kOffF);
+      int lt = 0, wit = 0, use1[2] = {0, 0}, fcnt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int s, t0, len;
+        if (!ffn_tile(p, tile, t_tiles, s, t0, len)) continue;
+        mbar_wait(h_full, lt & 1);
+        tc_fence_after();
+        for (int o = 0; o < 16; o++) {
+          bool is_ff2;
+          int c;
+          ffn_op(o, is_ff2, c);
+          if (!is_ff2) {
+            const int b = c & 1;
+            mbar_wait(&acc1_empty[b], (use1[b] & 1) ^ 1);       // GELU epilogue has drained this accumulator
+            tc_fence_after();
+            for (int kb = 0; kb < 4; kb++, wit++) {
+              const int st = wit % kSlots;
+              mbar_wait(&w_full[st], (wit / kSlots) & 1);
+              tc_fence_after();
+              const uint64_t a_desc = umma_smem_desc_sw128(h_addr + kb * 16384);
+              const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(smem + kOffW + st * kSlotBytes));
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                umma_f16(tmem_base + kAcc1 + b * 128, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              umma_commit(&w_empty[st]);
+            }
+            umma_commit(&acc1_full[b]);
+            use1[b]++;
+            if (c == 7) umma_commit(h_empty);                  // all FF1 MMAs of this tile issued: H tile may be refilled
+          } else {
+            if (c == 0) {
+              mbar_wait(acc2_empty, (lt & 1) ^ 1);              // previous tile's output epilogue has drained acc2
+              tc_fence_after();
+            }
+            mbar_wait(f_full, fcnt & 1);                        // GELU chunk c is in shared memory
+            tc_fence_after();
+            for (int i = 0; i < 4; i++, wit++) {
+              const int st = wit % kSlots;
+              const int kb = i >> 1, half = i & 1;
+              mbar_wait(&w_full[st], (wit / kSlots) & 1);
+              tc_fence_after();
+              const uint64_t a_desc = umma_smem_desc_sw128(f_addr + kb * 16384);
+              const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(smem + kOffW + st * kSlotBytes));
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                umma_f16(tmem_base + kAcc2 + half * 128, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                         (c | kb | k) != 0);
+              umma_commit(&w_empty[st]);
+            }
+            umma_commit(f_empty);                               // F chunk consumed
+            fcnt++;
+            if (c == 7) umma_commit(acc2_full);
+          }
+        }
+        lt++;
+      }
+    }
+  } else {
+    // --------------------------------- epilogue -----------------------------------
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int part = ew >> 2;                // 0 / 1: which half of the columns
+    const int r = q * 32 + lane;
+    float* stg = reinterpret_cast<float*>(smem + kOffStg) + ew * kStgFloats;
+    float* red_c = red;                      // [2][128]
+    float* red_d = red + 256;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* frow = smem + kOffF + part * 16384 + r * 128;
+    int lt = 0, use1[2] = {0, 0}, g = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int s, t0, len;
+      if (!ffn_tile(p, tile, t_tiles, s, t0, len)) continue;
+      const int t = t0 + r;
+      const bool valid = t < len;
+      const long long row = (long long)s * p.T_alloc + t;
+      const long long row0 = row - lane;
+      // ---- 8 hidden chunks: bias + GELU -> 16-bit chunk in shared memory (A operand of FF2) ----
+      for (int c = 0; c < 8; c++, g++) {
+        const int b = c & 1;
+        mbar_wait(&acc1_full[b], use1[b] & 1);
+        use1[b]++;
+        tc_fence_after();
+        uint32_t raw[64];
+        tmem_ld32(lane_addr + kAcc1 + b * 128 + part * 64, raw);
+        tmem_ld32(lane_addr + kAcc1 + b * 128 + part * 64 + 32, raw + 32);
+        float bv[32];
+        load32(p.b1 + c * 128 + part * 64, bv, true, 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc1_empty[b]);            // accumulator is in registers: release it to the MMA warp
+#pragma unroll
+        for (int i = 0; i < 32; i++) raw[i] = __float_as_uint(fast_gelu_erf(__uint_as_float(raw[i]) + bv[i]));
+        load32(p.b1 + c * 128 + part * 64 + 32, bv, true, 32);
+#pragma unroll
+        for (int i = 0; i < 32; i++) raw[32 + i] = __float_as_uint(fast_gelu_erf(__uint_as_float(raw[32 + i]) + bv[i]));
+        // pack to fp16 pairs in place
+#pragma unroll
+        for (int i = 0; i < 64; i += 2) {
+          __half2 h2 = __floats2half2_rn(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+          raw[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        mbar_wait(f_empty, (g & 1) ^ 1);                        // FF2 of the previous chunk has finished reading F
+#pragma unroll
+        for (int gq = 0; gq < 8; gq++) {
+          uint4 u;
+          u.x = raw[gq * 4 + 0]; u.y = raw[gq * 4 + 1]; u.z = raw[gq * 4 + 2]; u.w = raw[gq * 4 + 3];
+          *reinterpret_cast<uint4*>(frow + ((gq ^ (r & 7)) << 4)) = u;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(f_full);
+      }
+      // ---- output tile: + b2 + residual -> X32 ; LayerNorm / plain emits ----
+      mbar_wait(acc2_full, lt & 1);
+      tc_fence_after();
+      const uint32_t taddr = lane_addr + kAcc2 + part * 128;
+      const bool want_ln = p.emit_ln.ptr != nullptr;
+      float sum2 = 0.f;
+      uint32_t raw[32];
+      float v[32], tmp[32];
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ch++) {
+        const int cbase = part * 128 + ch * 32;
+        tmem_ld32(taddr + ch * 32, raw);
+        load32(p.b2 + cbase, tmp, true, 32);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]) + tmp[i];
+        tile_load_f32(p.x32 + row0 * 256 + cbase, 256, stg, lane, tmp);
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] += tmp[i];
+        tile_store_f32(p.x32 + row0 * 256 + cbase, 256, stg, lane, v);
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const Emit& em = p.emit_plain[e];
+          if (!em.ptr) continue;
+          float w[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) w[i] = valid ? v[i] : 0.f;
+          tile_store_f16(em.ptr + row0 * em.ld + em.col_off + cbase, em.ld, stg, lane, w);
+        }
+        if (want_ln) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            sum2 += v[i];
+            raw[i] = __float_as_uint(v[i]);
+          }
+          tmem_st32(taddr + ch * 32, raw);
+        }
+      }
+      if (want_ln) {
+        tmem_st_wait();
+        red_c[part * 128 + r] = sum2;
+        ffn_bar();
+        const float mean2 = (red_c[r] + red_c[128 + r]) * (1.f / 256.f);
+        float sq2 = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ch++) {
+          tmem_ld32(taddr + ch * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const float d = __uint_as_float(raw[i]) - mean2;
+            sq2 = fmaf(d, d, sq2);
+          }
+        }
+        red_d[part * 128 + r] = sq2;
+        ffn_bar();
+        const float rstd2 = rsqrtf((red_d[r] + red_d[128 + r]) * (1.f / 256.f) + p.emit_ln.f);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ch++) {
+          const int cbase = part * 128 + ch * 32;
+          tmem_ld32(taddr + ch * 32, raw);
+          float gg[32], w[32];
+          load32(p.emit_ln.a + cbase, gg, true, 32);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) w[i] = (__uint_as_float(raw[i]) - mean2) * rstd2 * gg[i];
+          load32(p.emit_ln.b + cbase, gg, true, 32);
+#pragma unroll
+          for (int i = 0; i < 32; i++) w[i] = valid ? (w[i] + gg[i]) : 0.f;
+          tile_store_f16(p.emit_ln.ptr + row0 * p.emit_ln.ld + p.emit_ln.col_off + cbase, p.emit_ln.ld, stg, lane, w);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc2_empty);
+      lt++;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+void launch_ffn_fused(const CUtensorMap& tmH, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const FfnParams& p,
+                      cudaStream_t stream) {
+  static bool configured = false;
+  static int num_sms = 0;
+  if (!configured) {
+    CV2_CUDA(cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem));
+    int dev = 0;
+    CV2_CUDA(cudaGetDevice(&dev));
+    CV2_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    configured = true;
+  }
+  CV2_CHECK(p.T_alloc % 128 == 0, "ffn_fused: T_alloc %d not a multiple of 128", p.T_alloc);
+  const int total = (p.T_alloc / 128) * p.S;
+  const int grid = total < num_sms ? total : num_sms;
+  ffn_fused_kernel<<<grid, kFfnThreads, kFfnSmem, stream>>>(tmH, tmW1, tmW2, p);
+  CV2_LAUNCH_CHECK();
+}
+
+}  // namespace cv2

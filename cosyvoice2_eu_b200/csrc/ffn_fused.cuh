@@ -1,0 +1,28 @@
+// Fused FF1 -> GELU -> FF2 -> residual -> LayerNorm/plain emit of one estimator transformer block (ffn_fused.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "gemm_tap.cuh"
+
+namespace cv2 {
+
+struct FfnParams {
+  int S, T_alloc;
+  const int* lens;          // [S] valid rows (null: len_all)
+  int len_all;
+  int halo;
+  const int* tile_list;     // optional compact (s, t0) list + count (device)
+  const int* tile_count;
+  const float* b1;          // [1024]
+  const float* b2;          // [256]
+  float* x32;               // [S*T_alloc, 256] residual stream, updated in place
+  Emit emit_ln;             // ptr != null: LayerNorm(x; a = gamma, b = beta, f = eps) -> 16-bit
+  Emit emit_plain[2];       // ptr != null: masked x -> 16-bit (ld / col_off honoured)
+};
+
+// tmH: 3-D {256, T_alloc, S} box {64,128,1};  tmW1: 2-D {256, 1024} box {64,128};  tmW2: 2-D {1024, 256} box {64,128}
+void launch_ffn_fused(const CUtensorMap& tmH, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const FfnParams& p,
+                      cudaStream_t stream);
+
+}  // namespace cv2

@@ -7,6 +7,7 @@
 // Each CTA walks tiles blockIdx.x, +gridDim.x, ... in (n fastest, then t, then sequence) order and skips tiles that lie
 // entirely in a sequence's padding.
 #include "common.cuh"
+#include "epi_util.cuh"
 #include "gemm_tap.cuh"
 #include "host_util.h"
 
@@ -16,7 +17,6 @@ static constexpr int kTileM = 128;
 static constexpr int kKBlock = 64;                       // 64 x 16-bit = one 128B swizzle row
 static constexpr int kABytes = kTileM * kKBlock * 2;     // 16 KB
 
-static constexpr int kStgFloats = 32 * 36;                 // per-warp transpose staging: 32 rows x (32 + 4 pad) floats
 template <int BN>
 struct GemmSmem {
   static constexpr int kParts = BN >= 128 ? 4 : 2;        // column parts of a tile = epilogue warps per TMEM lane quarter
@@ -30,133 +30,6 @@ struct GemmSmem {
   static constexpr int kBarOff = kRedOff + 4 * kParts * 128 * 4;
   static constexpr int kTotal = kBarOff + 256 + 1024;             // barriers + alignment slack
 };
-
-// ---- fast epilogue math (fp32) ----
-__device__ __forceinline__ float fast_mish(float x) {
-  // x * tanh(softplus(x)) = x * n / (n + 2), n = e^x (e^x + 2)
-  const float e = __expf(fminf(x, 20.f));
-  const float n = e * (e + 2.f);
-  const float y = __fdividef(x * n, n + 2.f);
-  return x > 20.f ? x : y;
-}
-__device__ __forceinline__ float fast_gelu_erf(float x) {
-  // exact-erf GELU = x * Phi(x), Phi(-|x|) = 0.5 erfc(|x|/sqrt 2) = 2^(-g(z) - 1), g = log2(e) * (-ln erfc(z)) fitted by a
-  // degree-4 polynomial on z in [0,4] (|gelu err| < 2.6e-5, an order below the fp16 rounding of the emitted value).
-  // 10 instructions, one MUFU (ex2), no division: gelu = max(x,0) - |x| * 2^(-g-1).
-  const float z = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
-  float g = fmaf(-0.0192909595f, z, 0.136979282f);
-  g = fmaf(g, z, 0.923393071f);
-  g = fmaf(g, z, 1.6273005f);
-  const float e = fast_exp2(fmaf(-g, z, -1.f));
-  return fmaf(-fabsf(x), e, fmaxf(x, 0.f));
-}
-__device__ __forceinline__ float fast_silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
-__device__ __forceinline__ float fast_snake(float x, float a) {
-  const float s = __sinf(x * a);
-  return fmaf(s * s, __fdividef(1.f, a + 1e-9f), x);
-}
-
-// 32 consecutive floats starting at p (p 16B aligned when full)
-__device__ __forceinline__ void load32(const float* __restrict__ p, float* d, bool full, int nv) {
-  if (full) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const float4 f = __ldg(reinterpret_cast<const float4*>(p) + i);
-      d[i * 4 + 0] = f.x; d[i * 4 + 1] = f.y; d[i * 4 + 2] = f.z; d[i * 4 + 3] = f.w;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; i++) d[i] = (i < nv) ? __ldg(p + i) : 0.f;
-  }
-}
-__device__ __forceinline__ void store32_f32(float* __restrict__ p, const float* v, bool full, int nv) {
-  if (full) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) reinterpret_cast<float4*>(p)[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; i++)
-      if (i < nv) p[i] = v[i];
-  }
-}
-__device__ __forceinline__ void store32_f16(__half* __restrict__ p, const float* v, bool full, int nv) {
-  if (full) {
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      __half2 h0 = __floats2half2_rn(v[i * 8 + 0], v[i * 8 + 1]);
-      __half2 h1 = __floats2half2_rn(v[i * 8 + 2], v[i * 8 + 3]);
-      __half2 h2 = __floats2half2_rn(v[i * 8 + 4], v[i * 8 + 5]);
-      __half2 h3 = __floats2half2_rn(v[i * 8 + 6], v[i * 8 + 7]);
-      uint4 u;
-      u.x = *reinterpret_cast<uint32_t*>(&h0);
-      u.y = *reinterpret_cast<uint32_t*>(&h1);
-      u.z = *reinterpret_cast<uint32_t*>(&h2);
-      u.w = *reinterpret_cast<uint32_t*>(&h3);
-      reinterpret_cast<uint4*>(p)[i] = u;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; i++)
-      if (i < nv) p[i] = __float2half_rn(v[i]);
-  }
-}
-
-// ---- coalesced global I/O for the thread-per-row epilogue ----
-// A warp owns 32 consecutive rows x 32 columns.  Per-thread row segments (16 B pieces 32 rows apart) cost one L1 wavefront
-// per lane; instead the warp moves the 32x32 block with lanes running along the row (4 rows x 128 B per instruction) and
-// transposes it through a private, padded shared-memory staging tile.
-__device__ __forceinline__ void tile_load_f32(const float* __restrict__ g0, long long ld, float* stg, int lane, float* d) {
-  // g0 -> element (first row of the warp, first column of the chunk)
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const int rr = 4 * i + (lane >> 3), c4 = (lane & 7) * 4;
-    const float4 f = __ldg(reinterpret_cast<const float4*>(g0 + rr * ld + c4));
-    *reinterpret_cast<float4*>(stg + rr * 36 + c4) = f;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const float4 f = *reinterpret_cast<const float4*>(stg + lane * 36 + i * 4);
-    d[i * 4 + 0] = f.x; d[i * 4 + 1] = f.y; d[i * 4 + 2] = f.z; d[i * 4 + 3] = f.w;
-  }
-}
-__device__ __forceinline__ void tile_store_f32(float* __restrict__ g0, long long ld, float* stg, int lane, const float* v) {
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 8; i++)
-    *reinterpret_cast<float4*>(stg + lane * 36 + i * 4) = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const int rr = 4 * i + (lane >> 3), c4 = (lane & 7) * 4;
-    *reinterpret_cast<float4*>(g0 + rr * ld + c4) = *reinterpret_cast<const float4*>(stg + rr * 36 + c4);
-  }
-}
-__device__ __forceinline__ void tile_store_f16(__half* __restrict__ g0, long long ld, float* stg, int lane, const float* v) {
-  // staging rows of 64 B payload + 16 B pad (20 words)
-  uint32_t* sw = reinterpret_cast<uint32_t*>(stg);
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    __half2 h0 = __floats2half2_rn(v[i * 8 + 0], v[i * 8 + 1]);
-    __half2 h1 = __floats2half2_rn(v[i * 8 + 2], v[i * 8 + 3]);
-    __half2 h2 = __floats2half2_rn(v[i * 8 + 4], v[i * 8 + 5]);
-    __half2 h3 = __floats2half2_rn(v[i * 8 + 6], v[i * 8 + 7]);
-    uint4 u;
-    u.x = *reinterpret_cast<uint32_t*>(&h0);
-    u.y = *reinterpret_cast<uint32_t*>(&h1);
-    u.z = *reinterpret_cast<uint32_t*>(&h2);
-    u.w = *reinterpret_cast<uint32_t*>(&h3);
-    *reinterpret_cast<uint4*>(sw + lane * 20 + i * 4) = u;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int rr = 8 * i + (lane >> 2), pc = lane & 3;
-    *reinterpret_cast<uint4*>(g0 + rr * ld + pc * 8) = *reinterpret_cast<const uint4*>(sw + rr * 20 + pc * 4);
-  }
-}
 
 template <int NT>
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
