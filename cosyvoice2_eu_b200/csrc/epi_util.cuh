@@ -135,4 +135,75 @@ __device__ __forceinline__ void tile_store_f16(__half* __restrict__ g0, long lon
 }
 
 
+// ---- half-height variants: the same 32-row block moved in two passes of 16 rows through a 16 x 32-float staging tile
+// (2048 B per warp, XOR-swizzled instead of padded: float4 column j of row r lives at column j ^ (r & 7)), for kernels
+// that run 16 epilogue warps and must fit their staging into 32 KB ----
+__device__ __forceinline__ void tile_load_f32_h16(const float* __restrict__ g0, long long ld, float* stg, int lane, float* d) {
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int rr = 4 * i + (lane >> 3), j = lane & 7;
+      const float4 f = __ldg(reinterpret_cast<const float4*>(g0 + (16 * h + rr) * ld + j * 4));
+      *reinterpret_cast<float4*>(stg + rr * 32 + ((j ^ (rr & 7)) << 2)) = f;
+    }
+    __syncwarp();
+    if ((lane >> 4) == h) {
+      const int rr = lane & 15;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float4 f = *reinterpret_cast<const float4*>(stg + rr * 32 + ((i ^ (rr & 7)) << 2));
+        d[i * 4 + 0] = f.x; d[i * 4 + 1] = f.y; d[i * 4 + 2] = f.z; d[i * 4 + 3] = f.w;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tile_store_f32_h16(float* __restrict__ g0, long long ld, float* stg, int lane, const float* v) {
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    __syncwarp();
+    if ((lane >> 4) == h) {
+      const int rr = lane & 15;
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        *reinterpret_cast<float4*>(stg + rr * 32 + ((i ^ (rr & 7)) << 2)) = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int rr = 4 * i + (lane >> 3), j = lane & 7;
+      *reinterpret_cast<float4*>(g0 + (16 * h + rr) * ld + j * 4) = *reinterpret_cast<const float4*>(stg + rr * 32 + ((j ^ (rr & 7)) << 2));
+    }
+  }
+}
+__device__ __forceinline__ void tile_store_f16_h16(__half* __restrict__ g0, long long ld, float* stg, int lane, const float* v) {
+  uint32_t* sw = reinterpret_cast<uint32_t*>(stg);   // 16 rows x 20 words (64 B payload + 16 B pad)
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    __syncwarp();
+    if ((lane >> 4) == h) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        __half2 h0 = __floats2half2_rn(v[i * 8 + 0], v[i * 8 + 1]);
+        __half2 h1 = __floats2half2_rn(v[i * 8 + 2], v[i * 8 + 3]);
+        __half2 h2 = __floats2half2_rn(v[i * 8 + 4], v[i * 8 + 5]);
+        __half2 h3 = __floats2half2_rn(v[i * 8 + 6], v[i * 8 + 7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2);
+        u.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(sw + (lane & 15) * 20 + i * 4) = u;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const int rr = 8 * i + (lane >> 2), pc = lane & 3;
+      *reinterpret_cast<uint4*>(g0 + (16 * h + rr) * ld + pc * 8) = *reinterpret_cast<const uint4*>(sw + rr * 20 + pc * 4);
+    }
+  }
+}
+
 }  // namespace cv2

@@ -6,7 +6,7 @@
 // 128; FF1(c) accumulates into a double-buffered 128-column TMEM tile, the epilogue warps apply bias + GELU and write the
 // 16-bit chunk straight into 128B-swizzled shared memory, where it is the A operand of FF2(c), which accumulates the
 // 256-column output tile in TMEM across the 8 chunks.  Weights stream through a 5-slot TMA ring (16 KB slots).
-//   warp 0: TMA (H tile + weight stream)   warp 1: tcgen05.mma issuer   warps 2-9: epilogue
+//   warp 0: TMA (H tile + weight stream)   warp 1: tcgen05.mma issuer   warps 2-17: epilogue (four per TMEM lane quarter)
 // Saves the [rows,1024] 16-bit round trip through HBM (4 KB/row of the 18 KB/row a transformer block moves) and one launch.
 #include "common.cuh"
 #include "epi_util.cuh"
@@ -17,18 +17,20 @@ namespace cv2 {
 
 static constexpr int kHBytes = 4 * 16384;       // [128 x 256] 16-bit, four 64-column swizzle atoms
 static constexpr int kFBytes = 2 * 16384;       // [128 x 128] 16-bit GELU chunk
-static constexpr int kSlots = 5;
+static constexpr int kSlots = 7;
 static constexpr int kSlotBytes = 16384;        // one [128 x 64] weight tile
 static constexpr int kOffF = kHBytes;
 static constexpr int kOffW = kOffF + kFBytes;
-static constexpr int kOffStg = kOffW + kSlots * kSlotBytes;
-static constexpr int kOffRed = kOffStg + 8 * kStgFloats * 4;
-static constexpr int kOffBar = kOffRed + 2 * 2 * 128 * 4;
-static constexpr int kFfnSmem = kOffBar + 256 + 1024;
-static constexpr int kFfnThreads = 64 + 8 * 32;
+static constexpr int kOffStg = kOffF;            // the output epilogue stages through the (then idle) F buffer
+static constexpr int kEpiW = 16;                 // epilogue warps: four per TMEM lane quarter
+static constexpr int kStgH = 16 * 32;            // swizzled half-height staging tile per warp (floats): 16 x 2 KB = 32 KB
+static constexpr int kOffRed = kOffW + kSlots * kSlotBytes;
+static constexpr int kOffBar = kOffRed + 2 * 4 * 128 * 4;
+static constexpr int kFfnSmem = kOffBar + 256;
+static constexpr int kFfnThreads = 64 + kEpiW * 32;
 static constexpr uint32_t kAcc1 = 0, kAcc2 = 256;   // TMEM columns: acc1 = 2 x 128, acc2 = 256
 
-__device__ __forceinline__ void ffn_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void ffn_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __device__ __forceinline__ bool ffn_tile(const FfnParams& p, int tile, int t_tiles, int& s, int& t0, int& len) {
   if (p.tile_list) {
@@ -54,21 +56,20 @@ __device__ __forceinline__ void ffn_op(int o, bool& is_ff2, int& c) {
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const FfnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // 1024 B alignment for the 128B-swizzle atoms
   float* red = reinterpret_cast<float*>(smem + kOffRed);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* h_full = bars + 0;
   uint64_t* h_empty = bars + 1;
-  uint64_t* w_full = bars + 2;             // [5]
-  uint64_t* w_empty = bars + 7;            // [5]
-  uint64_t* acc1_full = bars + 12;         // [2]
-  uint64_t* acc1_empty = bars + 14;        // [2]
-  uint64_t* f_full = bars + 16;
-  uint64_t* f_empty = bars + 17;
-  uint64_t* acc2_full = bars + 18;
-  uint64_t* acc2_empty = bars + 19;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* w_full = bars + 2;             // [kSlots]
+  uint64_t* w_empty = w_full + kSlots;     // [kSlots]
+  uint64_t* acc1_full = w_empty + kSlots;  // [2]
+  uint64_t* acc1_empty = acc1_full + 2;    // [2]
+  uint64_t* f_full = acc1_empty + 2;
+  uint64_t* f_empty = f_full + 1;
+  uint64_t* acc2_full = f_empty + 1;
+  uint64_t* acc2_empty = acc2_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,12 +88,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(&acc1_full[i], 1);
-      mbar_init(&acc1_empty[i], 8);
+      mbar_init(&acc1_empty[i], kEpiW);
     }
-    mbar_init(f_full, 8);
+    mbar_init(f_full, kEpiW);
     mbar_init(f_empty, 1);
     mbar_init(acc2_full, 1);
-    mbar_init(acc2_empty, 8);
+    mbar_init(acc2_empty, kEpiW);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -194,13 +195,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
     // --------------------------------- epilogue -----------------------------------
     const int ew = warp - 2;
     const int q = warp & 3;
-    const int part = ew >> 2;                // 0 / 1: which half of the columns
+    const int part = ew >> 2;                // 0..3: which quarter of the columns
     const int r = q * 32 + lane;
-    float* stg = reinterpret_cast<float*>(smem + kOffStg) + ew * kStgFloats;
-    float* red_c = red;                      // [2][128]
-    float* red_d = red + 256;
+    float* stg = reinterpret_cast<float*>(smem + kOffStg) + ew * kStgH;
+    float* red_c = red;                      // [4][128]
+    float* red_d = red + 512;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint8_t* frow = smem + kOffF + part * 16384 + r * 128;
+    uint8_t* frow = smem + kOffF + (part >> 1) * 16384 + r * 128;   // atom = 64 columns; this thread writes 32 of them
     int lt = 0, use1[2] = {0, 0}, g = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int s, t0, len;
@@ -212,35 +213,31 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
       // ---- 8 hidden chunks: bias + GELU -> 16-bit chunk in shared memory (A operand of FF2) ----
       for (int c = 0; c < 8; c++, g++) {
         const int b = c & 1;
+        float bv[32];
+        load32(p.b1 + c * 128 + part * 32, bv, true, 32);      // bias first: its latency hides behind the accumulator wait
         mbar_wait(&acc1_full[b], use1[b] & 1);
         use1[b]++;
         tc_fence_after();
-        uint32_t raw[64];
-        tmem_ld32(lane_addr + kAcc1 + b * 128 + part * 64, raw);
-        tmem_ld32(lane_addr + kAcc1 + b * 128 + part * 64 + 32, raw + 32);
-        float bv[32];
-        load32(p.b1 + c * 128 + part * 64, bv, true, 32);
+        uint32_t raw[32];
+        tmem_ld32(lane_addr + kAcc1 + b * 128 + part * 32, raw);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc1_empty[b]);            // accumulator is in registers: release it to the MMA warp
 #pragma unroll
-        for (int i = 0; i < 32; i++) raw[i] = __float_as_uint(fast_gelu_erf(__uint_as_float(raw[i]) + bv[i]));
-        load32(p.b1 + c * 128 + part * 64 + 32, bv, true, 32);
+        for (int i = 0; i < 32; i++) bv[i] = fast_gelu_erf(__uint_as_float(raw[i]) + bv[i]);
 #pragma unroll
-        for (int i = 0; i < 32; i++) raw[32 + i] = __float_as_uint(fast_gelu_erf(__uint_as_float(raw[32 + i]) + bv[i]));
-        // pack to fp16 pairs in place
-#pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          __half2 h2 = __floats2half2_rn(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+        for (int i = 0; i < 32; i += 2) {
+          __half2 h2 = __floats2half2_rn(bv[i], bv[i + 1]);
           raw[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
         }
+        if (c == 0) ffn_bar();                                  // every warp has left the previous tile's output staging (= F)
         mbar_wait(f_empty, (g & 1) ^ 1);                        // FF2 of the previous chunk has finished reading F
 #pragma unroll
-        for (int gq = 0; gq < 8; gq++) {
+        for (int gq = 0; gq < 4; gq++) {
           uint4 u;
           u.x = raw[gq * 4 + 0]; u.y = raw[gq * 4 + 1]; u.z = raw[gq * 4 + 2]; u.w = raw[gq * 4 + 3];
-          *reinterpret_cast<uint4*>(frow + ((gq ^ (r & 7)) << 4)) = u;
+          *reinterpret_cast<uint4*>(frow + ((((part & 1) * 4 + gq) ^ (r & 7)) << 4)) = u;
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -249,23 +246,23 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
       // ---- output tile: + b2 + residual -> X32 ; LayerNorm / plain emits ----
       mbar_wait(acc2_full, lt & 1);
       tc_fence_after();
-      const uint32_t taddr = lane_addr + kAcc2 + part * 128;
+      const uint32_t taddr = lane_addr + kAcc2 + part * 64;
       const bool want_ln = p.emit_ln.ptr != nullptr;
       float sum2 = 0.f;
       uint32_t raw[32];
       float v[32], tmp[32];
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ch++) {
-        const int cbase = part * 128 + ch * 32;
+      for (int ch = 0; ch < 2; ch++) {
+        const int cbase = part * 64 + ch * 32;
         tmem_ld32(taddr + ch * 32, raw);
         load32(p.b2 + cbase, tmp, true, 32);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]) + tmp[i];
-        tile_load_f32(p.x32 + row0 * 256 + cbase, 256, stg, lane, tmp);
+        tile_load_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, tmp);
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] += tmp[i];
-        tile_store_f32(p.x32 + row0 * 256 + cbase, 256, stg, lane, v);
+        tile_store_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, v);
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const Emit& em = p.emit_plain[e];
@@ -273,7 +270,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
           float w[32];
 #pragma unroll
           for (int i = 0; i < 32; i++) w[i] = valid ? v[i] : 0.f;
-          tile_store_f16(em.ptr + row0 * em.ld + em.col_off + cbase, em.ld, stg, lane, w);
+          tile_store_f16_h16(em.ptr + row0 * em.ld + em.col_off + cbase, em.ld, stg, lane, w);
         }
         if (want_ln) {
 #pragma unroll
@@ -288,10 +285,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
         tmem_st_wait();
         red_c[part * 128 + r] = sum2;
         ffn_bar();
-        const float mean2 = (red_c[r] + red_c[128 + r]) * (1.f / 256.f);
+        const float mean2 = (red_c[r] + red_c[128 + r] + red_c[256 + r] + red_c[384 + r]) * (1.f / 256.f);
         float sq2 = 0.f;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ch++) {
+        for (int ch = 0; ch < 2; ch++) {
           tmem_ld32(taddr + ch * 32, raw);
           tmem_ld_wait();
 #pragma unroll
@@ -302,10 +299,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
         }
         red_d[part * 128 + r] = sq2;
         ffn_bar();
-        const float rstd2 = rsqrtf((red_d[r] + red_d[128 + r]) * (1.f / 256.f) + p.emit_ln.f);
+        const float rstd2 = rsqrtf((red_d[r] + red_d[128 + r] + red_d[256 + r] + red_d[384 + r]) * (1.f / 256.f) + p.emit_ln.f);
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ch++) {
-          const int cbase = part * 128 + ch * 32;
+        for (int ch = 0; ch < 2; ch++) {
+          const int cbase = part * 64 + ch * 32;
           tmem_ld32(taddr + ch * 32, raw);
           float gg[32], w[32];
           load32(p.emit_ln.a + cbase, gg, true, 32);
@@ -315,7 +312,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
           load32(p.emit_ln.b + cbase, gg, true, 32);
 #pragma unroll
           for (int i = 0; i < 32; i++) w[i] = valid ? (w[i] + gg[i]) : 0.f;
-          tile_store_f16(p.emit_ln.ptr + row0 * p.emit_ln.ld + p.emit_ln.col_off + cbase, p.emit_ln.ld, stg, lane, w);
+          tile_store_f16_h16(p.emit_ln.ptr + row0 * p.emit_ln.ld + p.emit_ln.col_off + cbase, p.emit_ln.ld, stg, lane, w);
         }
       }
       tc_fence_before();

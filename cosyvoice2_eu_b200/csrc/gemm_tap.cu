@@ -28,7 +28,7 @@ struct GemmSmem {
   static constexpr int kStgOff = kStages * kStageBytes;           // 8 warps x 4608 B
   static constexpr int kRedOff = kStgOff + kEpiWarps * kStgFloats * 4;   // 4 x [kParts][128] floats for LayerNorm exchanges
   static constexpr int kBarOff = kRedOff + 4 * kParts * 128 * 4;
-  static constexpr int kTotal = kBarOff + 256 + 1024;             // barriers + alignment slack
+  static constexpr int kTotal = kBarOff + 256;                    // + barriers
 };
 
 template <int NT>
@@ -76,8 +76,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr int kStages = SM::kStages;
   constexpr int kEpiWarps = SM::kEpiWarps;
   constexpr int kParts = SM::kParts;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // 1024 B alignment for the 128B-swizzle atoms; keeps STS/LDS addressing
   float* red = reinterpret_cast<float*>(smem + SM::kRedOff);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::kBarOff);
   uint64_t* empty_bar = full_bar + kStages;
