@@ -2,9 +2,9 @@
 // 8 heads x 64, softmax(q k^T / 8 + mask) v).  The mask is never materialised: it is generated from
 // integers (valid length per sequence; optional block-causal chunk) inside the kernel.
 //
-// One CTA = 128 query rows of one (sequence, head), key tiles of 64.  warp 0: TMA producer (Q once, K/V tiles through
-// a 2-stage ring), warp 1: tcgen05.mma issuer (S = Q K^T into TMEM, O += P V), warps 2-5: online softmax, thread-per-row
-// with the whole 64-logit row in registers, P written 16-bit into 128B-swizzled smem as the A operand of the PV MMA;
+// One CTA = 128 query rows of one (sequence, head), key tiles of 64.  warp 8: TMA producer (Q once, K/V tiles through
+// a 2-stage ring), warp 9: tcgen05.mma issuer (S = Q K^T into TMEM, O += P V), warps 0-7: online softmax, two threads per row
+// (32 logits each, in registers), P written 16-bit into 128B-swizzled smem as the A operand of the PV MMA;
 // O accumulates in TMEM and is rescaled in place when the running max moves.
 // Small footprint on purpose (64 KB smem, 128 TMEM columns, <= 112 registers): THREE CTAs per SM, so that while one CTA
 // waits on its MMA / barrier round trip the others keep the MUFU (exp2) and tensor pipes busy -- the kernel is MUFU-bound
@@ -25,10 +25,12 @@ static constexpr int kOffK = kQBytes;
 static constexpr int kOffV = kOffK + kKVStages * kKBytes;
 static constexpr int kOffP = kOffV + kKVStages * kVBytes;
 static constexpr int kOffBar = kOffP + kPBytes;
-static constexpr int kAttnSmem = kOffBar + 256;         // 64.25 KB
+static constexpr int kOffXch = kOffBar + 256;           // softmax exchange: 2x2x128 maxima + 2x128 row sums (floats)
+static constexpr int kAttnSmem = kOffXch + 3 * 1024;    // 67.25 KB
+static constexpr int kAttnThreads = 10 * 32;            // 8 softmax warps + TMA warp + MMA warp
 static constexpr uint32_t kTmemS = 0, kTmemO = 64;      // column offsets (128 allocated)
 
-__global__ void __launch_bounds__(192, 3)
+__global__ void __launch_bounds__(kAttnThreads, 3)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   const int t0 = blockIdx.x * 128;
@@ -55,7 +57,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -65,17 +67,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_init(&kv_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  if (warp == 9) tmem_alloc<128>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_expect_tx(q_full, kQBytes);
       tma_load_3d(smem, &tmQ, q_full, 0, t0, sh);
@@ -88,7 +90,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tma_load_3d(smem + kOffV + st * kVBytes, &tmV, &kv_full[st], j * kKT, 0, sh);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_f16(128, kKT, 0);
       constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0);
@@ -120,7 +122,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
     }
   } else {
+    // ---- softmax: 8 warps, TWO threads per query row (warp w and w+4 share TMEM lane quarter w&3); thread `half`
+    //      owns keys [32*half, 32*half+32) of every tile and columns [32*half, +32) of O ----
     const int q = warp & 3;
+    const int half = warp >> 2;
     const int r = q * 32 + lane;
     const int t = t0 + r;
     int kv_lim = len;
@@ -128,38 +133,39 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float LOG2E = 1.4426950408889634f;
     float m = -INFINITY, l = 0.f;
-    uint32_t raw[32];
+    float* xch = reinterpret_cast<float*>(smem + kOffXch);       // [2 parity][2 half][128 rows] partial maxima
     uint8_t* prow = smem + kOffP + r * 128;
     for (int j = 0; j < nkt; j++) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const uint32_t s_addr = lane_addr + kTmemS;
-      const int kbase = j * kKT;
-      // whole S row (64 logits) into registers: two TMEM loads in flight, one wait
-      uint32_t sr[kKT];
-#pragma unroll
-      for (int c = 0; c < kKT / 32; c++) tmem_ld32(s_addr + c * 32, sr + c * 32);
+      const int kbase = j * kKT + half * 32;
+      uint32_t sr[32];
+      tmem_ld32(lane_addr + kTmemS + half * 32, sr);
       tmem_ld_wait();
-      if (kbase + kKT > kv_lim) {   // masking needed inside this tile for this row
+      if (kbase + 32 > kv_lim) {   // masking needed inside this half tile for this row
 #pragma unroll
-        for (int i = 0; i < kKT; i++)
+        for (int i = 0; i < 32; i++)
           if (kbase + i >= kv_lim) sr[i] = 0xff800000u;   // -inf
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < kKT; i += 4) {
+      for (int i = 0; i < 32; i += 4) {
         mx0 = fmaxf(mx0, __uint_as_float(sr[i]));
         mx1 = fmaxf(mx1, __uint_as_float(sr[i + 1]));
         mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2]));
         mx3 = fmaxf(mx3, __uint_as_float(sr[i + 3]));
       }
-      const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float* xc = xch + (j & 1) * 256;
+      xc[half * 128 + r] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the two warps of this lane quarter
+      const float m_new = fmaxf(m, fmaxf(mx, xc[(half ^ 1) * 128 + r]));
       const float alpha = (m == -INFINITY) ? 0.f : fast_exp2((m - m_new) * LOG2E);
       const float mscaled = (m_new == -INFINITY) ? 0.f : m_new * LOG2E;
       // probabilities in place (exp2(-inf) = 0 for masked keys), packed to fp16 pairs
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-      for (int i = 0; i < kKT; i += 4) {
+      for (int i = 0; i < 32; i += 4) {
         const float e0 = fast_exp2(fmaf(__uint_as_float(sr[i]), LOG2E, -mscaled));
         const float e1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), LOG2E, -mscaled));
         const float e2 = fast_exp2(fmaf(__uint_as_float(sr[i + 2]), LOG2E, -mscaled));
@@ -169,66 +175,66 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         sr[i >> 1] = *reinterpret_cast<uint32_t*>(&h0);
         sr[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
       }
-      // PV of the previous tile must be complete before O is rescaled or P overwritten
+      l = l * alpha + ((l0 + l1) + (l2 + l3));
+      // PV of the previous tile must be complete before P is overwritten or O rescaled
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.f)) {
-          for (int c = 0; c < 2; c++) {
-            tmem_ld32(lane_addr + kTmemO + c * 32, raw);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; i++) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
-            tmem_st32(lane_addr + kTmemO + c * 32, raw);
-          }
-          tmem_st_wait();
-        }
       }
-      l = l * alpha + ((l0 + l1) + (l2 + l3));
-      // P tile, 16-bit, swizzled K-major: 8 x 16-byte groups per row
+      // P half tile, 16-bit, swizzled K-major: 4 x 16-byte groups per row
 #pragma unroll
-      for (int g = 0; g < kKT / 8; g++) {
+      for (int g = 0; g < 4; g++) {
         uint4 u;
         u.x = sr[g * 4 + 0]; u.y = sr[g * 4 + 1]; u.z = sr[g * 4 + 2]; u.w = sr[g * 4 + 3];
-        *reinterpret_cast<uint4*>(prow + ((g ^ (r & 7)) << 4)) = u;
+        *reinterpret_cast<uint4*>(prow + (((half * 4 + g) ^ (r & 7)) << 4)) = u;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {   // rescale this thread's 32 columns of O
+        tmem_ld32(lane_addr + kTmemO + half * 32, sr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) sr[i] = __float_as_uint(__uint_as_float(sr[i]) * alpha);
+        tmem_st32(lane_addr + kTmemO + half * 32, sr);
+        tmem_st_wait();
       }
       m = m_new;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    // final: O / l -> 16-bit [S, T_alloc, heads*64]
+    // final: O / l -> 16-bit [S, T_alloc, heads*64]; the row sum is split over the two threads of the row
+    float* lx = xch + 512;
+    lx[half * 128 + r] = l;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+    const float inv = 1.f / (l + lx[(half ^ 1) * 128 + r]);
     mbar_wait(pv_done, (nkt - 1) & 1);
     tc_fence_after();
-    const float inv = 1.f / l;
-    __half* dst = p.out + ((long long)s * p.T_alloc + t) * (p.heads * 64) + h * 64;
+    __half* dst = p.out + ((long long)s * p.T_alloc + t) * (p.heads * 64) + h * 64 + half * 32;
     const bool valid = t < len;
-    for (int c = 0; c < 2; c++) {
-      tmem_ld32(lane_addr + kTmemO + c * 32, raw);
-      tmem_ld_wait();
-      uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+    uint32_t raw[32];
+    tmem_ld32(lane_addr + kTmemO + half * 32, raw);
+    tmem_ld_wait();
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        float f[8];
+    for (int i = 0; i < 4; i++) {
+      float f[8];
 #pragma unroll
-        for (int e = 0; e < 8; e++) f[e] = valid ? __uint_as_float(raw[i * 8 + e]) * inv : 0.f;
-        __half2 h0 = __floats2half2_rn(f[0], f[1]);
-        __half2 h1 = __floats2half2_rn(f[2], f[3]);
-        __half2 h2 = __floats2half2_rn(f[4], f[5]);
-        __half2 h3 = __floats2half2_rn(f[6], f[7]);
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&h0);
-        u.y = *reinterpret_cast<uint32_t*>(&h1);
-        u.z = *reinterpret_cast<uint32_t*>(&h2);
-        u.w = *reinterpret_cast<uint32_t*>(&h3);
-        d4[i] = u;
-      }
+      for (int e = 0; e < 8; e++) f[e] = valid ? __uint_as_float(raw[i * 8 + e]) * inv : 0.f;
+      __half2 h0 = __floats2half2_rn(f[0], f[1]);
+      __half2 h1 = __floats2half2_rn(f[2], f[3]);
+      __half2 h2 = __floats2half2_rn(f[4], f[5]);
+      __half2 h3 = __floats2half2_rn(f[6], f[7]);
+      uint4 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      u.z = *reinterpret_cast<uint32_t*>(&h2);
+      u.w = *reinterpret_cast<uint32_t*>(&h3);
+      d4[i] = u;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<128>(tmem_base);
+  if (warp == 9) tmem_dealloc<128>(tmem_base);
 }
 
 void launch_flash_attn(const AttnParams& p, cudaStream_t stream) {
@@ -250,7 +256,7 @@ void launch_flash_attn(const AttnParams& p, cudaStream_t stream) {
   uint32_t bv[3] = {(uint32_t)kKT, 64, 1};
   CUtensorMap tmV = make_tmap_16b(p.vt, 3, dv, sv, bv);
   dim3 grid(p.T_alloc / 128, p.heads, p.S);
-  flash_attn_kernel<<<grid, 192, kAttnSmem, stream>>>(tmQ, tmK, tmV, p);
+  flash_attn_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tmQ, tmK, tmV, p);
   CV2_LAUNCH_CHECK();
 }
 
