@@ -6,9 +6,9 @@
 // a 2-stage ring), warp 9: tcgen05.mma issuer (S = Q K^T into TMEM, O += P V), warps 0-7: online softmax, two threads per row
 // (32 logits each, in registers), P written 16-bit into 128B-swizzled smem as the A operand of the PV MMA;
 // O accumulates in TMEM and is rescaled in place when the running max moves.
-// Small footprint on purpose (64 KB smem, 128 TMEM columns, <= 112 registers): THREE CTAs per SM, so that while one CTA
-// waits on its MMA / barrier round trip the others keep the MUFU (exp2) and tensor pipes busy -- the kernel is MUFU-bound
-// (head_dim 64: one exp2 per 256 MMA FLOPs).
+// The logits tile is double-buffered in TMEM so S(j+1) is computed while softmax j runs (the softmax warps otherwise
+// spend most of their time waiting for the S MMA round trip); two CTAs per SM (100 KB smem, 256 TMEM columns each).
+// The kernel is MUFU-bound in the limit (head_dim 64: one exp2 per 256 MMA FLOPs).
 #include "attention.cuh"
 #include "common.cuh"
 #include "host_util.h"
@@ -19,7 +19,7 @@ static constexpr int kKT = 64;                          // keys per tile
 static constexpr int kQBytes = 128 * 64 * 2;            // 16 KB
 static constexpr int kKBytes = kKT * 64 * 2;            // 64 keys x 64 d   (B operand of S, K-major)
 static constexpr int kVBytes = 64 * kKT * 2;            // 64 d x 64 keys   (B operand of PV, K-major: v stored transposed)
-static constexpr int kKVStages = 2;
+static constexpr int kKVStages = 4;
 static constexpr int kPBytes = 128 * kKT * 2;           // 128 rows x 64 keys, one swizzle atom column
 static constexpr int kOffK = kQBytes;
 static constexpr int kOffV = kOffK + kKVStages * kKBytes;
@@ -28,9 +28,9 @@ static constexpr int kOffBar = kOffP + kPBytes;
 static constexpr int kOffXch = kOffBar + 256;           // softmax exchange: 2x2x128 maxima + 2x128 row sums (floats)
 static constexpr int kAttnSmem = kOffXch + 3 * 1024;    // 67.25 KB
 static constexpr int kAttnThreads = 10 * 32;            // 8 softmax warps + TMA warp + MMA warp
-static constexpr uint32_t kTmemS = 0, kTmemO = 64;      // column offsets (128 allocated)
+static constexpr uint32_t kTmemS = 0, kTmemO = 128;     // S double-buffered (2 x 64 columns), O 64 columns (256 allocated)
 
-__global__ void __launch_bounds__(kAttnThreads, 3)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   const int t0 = blockIdx.x * 128;
@@ -47,12 +47,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem[];   // swizzle-128B tiles need 1024 B alignment
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars;              // 1
-  uint64_t* kv_full = bars + 1;         // 2  (K and V of a stage land on the same barrier)
-  uint64_t* kv_empty = bars + 3;        // 2
-  uint64_t* s_full = bars + 5;          // 1
-  uint64_t* p_full = bars + 6;          // 1 (128 arrivals)
-  uint64_t* pv_done = bars + 7;         // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* kv_full = bars + 1;                 // [kKVStages]  (K and V of a stage land on the same barrier)
+  uint64_t* kv_empty = kv_full + kKVStages;     // [kKVStages]
+  uint64_t* s_full = kv_empty + kKVStages;      // [2]
+  uint64_t* p_full = s_full + 2;                // 1 (256 arrivals)
+  uint64_t* pv_done = p_full + 1;               // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -66,12 +66,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    mbar_init(s_full, 1);
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
     mbar_init(p_full, 256);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<128>(tmem_slot);
+  if (warp == 9) tmem_alloc<256>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -103,15 +104,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(smem + kOffK + st * kKBytes));
 #pragma unroll
         for (int k = 0; k < 4; k++)
-          umma_f16(tmem_base + kTmemS, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0);
-        umma_commit(s_full);
+          umma_f16(tmem_base + kTmemS + (j & 1) * 64, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0);
+        umma_commit(&s_full[j & 1]);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
+      if (nkt > 1) issue_s(1);      // logits run one tile ahead of the softmax (double-buffered S)
       for (int j = 0; j < nkt; j++) {
         mbar_wait(p_full, j & 1);   // softmax j has consumed S_j and written P_j
         tc_fence_after();
-        if (j + 1 < nkt) issue_s(j + 1);   // S buffer is free again: next logits first, so softmax j+1 overlaps PV_j
         const int st = j % kKVStages;
         const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(smem + kOffV + st * kVBytes));
 #pragma unroll
@@ -119,6 +120,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           umma_f16(tmem_base + kTmemO, p_desc + (uint64_t)(k * 2), v_desc + (uint64_t)(k * 2), idesc_o, (j | k) != 0);
         umma_commit(&kv_empty[st]);
         umma_commit(pv_done);
+        if (j + 2 < nkt) issue_s(j + 2);   // S buffer j&1 is free again
       }
     }
   } else {
@@ -136,11 +138,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     float* xch = reinterpret_cast<float*>(smem + kOffXch);       // [2 parity][2 half][128 rows] partial maxima
     uint8_t* prow = smem + kOffP + r * 128;
     for (int j = 0; j < nkt; j++) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       const int kbase = j * kKT + half * 32;
       uint32_t sr[32];
-      tmem_ld32(lane_addr + kTmemS + half * 32, sr);
+      tmem_ld32(lane_addr + kTmemS + (j & 1) * 64 + half * 32, sr);
       tmem_ld_wait();
       if (kbase + 32 > kv_lim) {   // masking needed inside this half tile for this row
 #pragma unroll
@@ -234,7 +236,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<128>(tmem_base);
+  if (warp == 9) tmem_dealloc<256>(tmem_base);
 }
 
 void launch_flash_attn(const AttnParams& p, cudaStream_t stream) {
