@@ -342,6 +342,59 @@ class B200Token2Wav:
         speech, _ = self.hift.inference(mel, noise=noise, lens=mel_lens)
         return speech, mel_lens * 480
 
+    @torch.inference_mode()
+    def token2wav_stream_batch(self, requests, finalize, noises=None):
+        """One streaming step for many concurrent sessions at once (BASELINE configs[3]): every request is what
+        CosyVoice2Model.tts(stream=True) would pass to token2wav for that session at this step (model.py:358-380):
+            dict(token=[1,n_visible], prompt_token, prompt_feat, embedding, token_offset, uuid)
+        All requests of one call share `finalize` (non-final chunks run with streaming masks, the final chunk with
+        streaming=False, exactly like the reference: model.py:373-380 does not pass `stream`).  The flow runs as ONE ragged
+        batch, the vocoder as one batch per cache state (sessions with / without an hift cache), the crossfade and cache
+        update per session on the device.  Returns a list of speech tensors [1, L_b] (same values as per-session calls)."""
+        stream = not finalize
+        mel, mel_lens = self.flow.inference_batch([r["token"][0] for r in requests], [r["prompt_token"][0] for r in requests],
+                                                  [r["prompt_feat"][0] for r in requests], [r["embedding"][0] for r in requests],
+                                                  streaming=stream, finalize=finalize)
+        mels = []
+        for b, r in enumerate(requests):
+            m = mel[b:b + 1, :, r["token_offset"] * self.flow.token_mel_ratio:int(mel_lens[b])]
+            cache = self.hift_cache_dict.get(r["uuid"])
+            if cache is not None:
+                m = torch.concat([cache["mel"], m], dim=2)
+            mels.append(m)
+        out = [None] * len(requests)
+        cached = [self.hift_cache_dict.get(r["uuid"]) is not None for r in requests]   # decided once: the loop updates the caches
+        for has_cache in (False, True):
+            idx = [b for b in range(len(requests)) if cached[b] == has_cache]
+            if not idx:
+                continue
+            T = max(mels[b].shape[2] for b in idx)
+            mb = torch.zeros(len(idx), 80, T, device=self.device)
+            lens = torch.tensor([mels[b].shape[2] for b in idx], dtype=torch.int32)
+            for k, b in enumerate(idx):
+                mb[k, :, :mels[b].shape[2]] = mels[b][0]
+            cs = torch.cat([self.hift_cache_dict[requests[b]["uuid"]]["source"] for b in idx], dim=0) if has_cache \
+                else torch.zeros(len(idx), 1, 0)
+            nz = None
+            if noises is not None:
+                nz = torch.zeros(len(idx), 480 * T, 9)
+                for k, b in enumerate(idx):
+                    nz[k, :noises[b].shape[-2]] = noises[b].reshape(-1, 9)
+            speech, source = self.hift.inference(mb, cache_source=cs, noise=nz, lens=lens)
+            for k, b in enumerate(idx):
+                L = 480 * int(lens[k])
+                sp, so = speech[k:k + 1, :L], source[k:k + 1, :, :L]
+                uuid = requests[b]["uuid"]
+                if has_cache:
+                    sp = self._fade_in_out(sp.contiguous(), self.hift_cache_dict[uuid]["speech"])
+                if not finalize:
+                    self.hift_cache_dict[uuid] = {"mel": mels[b][:, :, -self.mel_cache_len:].clone(),
+                                                  "source": so[:, :, -self.source_cache_len:].clone(),
+                                                  "speech": sp[:, -self.source_cache_len:].clone()}
+                    sp = sp[:, :-self.source_cache_len]
+                out[b] = sp
+        return out
+
 
 class GraphedToken2Wav:
     """Offline token2wav replayed from a CUDA graph (latency path, BASELINE configs[1]).

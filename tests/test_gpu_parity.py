@@ -188,3 +188,55 @@ def test_cuda_graph_replay_matches_eager(engine):
         assert bool(torch.isfinite(wav).all()) and float(wav[0, :480 * n_mel].abs().max()) > 1e-3
         assert float(wav[0, 480 * n_mel:].abs().max()) == 0.0
     assert len(g.graphs) == 1
+
+
+def test_streaming_batched_sessions_equal_single_sessions(engine, golden):
+    """configs[3]-style concurrency: several sessions stepped together through token2wav_stream_batch give exactly what each
+    session gives alone through token2wav (and the golden chunk shapes for the (70, 10) session)."""
+    import token2wav_oracle as O
+    from cosyvoice2_eu_b200 import B200Token2Wav
+    flow, hift, t2w = engine
+    g = golden("stream")
+    specs = [(70, 10, 3), (95, 25, 8), (55, 12, 9)]
+    utts = [_utt(dict(n_tok=n, n_prompt=p, seed=s)) for n, p, s in specs]
+    scheds = [O.stream_schedule(n, p) for n, p, _ in specs]
+    noise_of = lambda si, ci, mel_len: T(weights.make_nsf_noise(mel_len * 480, 1000 * si + ci))
+    # reference: each session alone
+    solo = []
+    for si, (u, sched) in enumerate(zip(utts, scheds)):
+        one = B200Token2Wav(flow, hift)
+        one.hift_cache_dict["x"] = None
+        chunks = []
+        for ci, (n_vis, off, fin) in enumerate(sched):
+            n_new = (n_vis - (0 if fin else 3)) * 2 - off * 2
+            mel_len = n_new + (8 if one.hift_cache_dict["x"] is not None else 0)
+            chunks.append(one.token2wav(u["token"][:, :n_vis], u["prompt_token"], u["prompt_feat"], u["embedding"], off, "x",
+                                        stream=not fin, finalize=fin, noise=noise_of(si, ci, mel_len)).cpu())
+        solo.append(chunks)
+    assert [tuple(c.shape) for c in solo[0]] == [g[f"chunk{i}"].shape for i in range(len(scheds[0]))]
+    # batched: all sessions advance together
+    multi = B200Token2Wav(flow, hift)
+    for si in range(len(specs)):
+        multi.hift_cache_dict[f"s{si}"] = None
+    got = [[] for _ in specs]
+    for step in range(max(len(s) for s in scheds)):
+        for fin in (False, True):
+            reqs, who, nz = [], [], []
+            for si, (u, sched) in enumerate(zip(utts, scheds)):
+                if step < len(sched) and sched[step][2] == fin:
+                    n_vis, off, _ = sched[step]
+                    n_new = (n_vis - (0 if fin else 3)) * 2 - off * 2
+                    mel_len = n_new + (8 if multi.hift_cache_dict[f"s{si}"] is not None else 0)
+                    reqs.append(dict(token=u["token"][:, :n_vis], prompt_token=u["prompt_token"], prompt_feat=u["prompt_feat"],
+                                     embedding=u["embedding"], token_offset=off, uuid=f"s{si}"))
+                    who.append(si)
+                    nz.append(noise_of(si, step, mel_len))
+            if reqs:
+                outs = multi.token2wav_stream_batch(reqs, finalize=fin, noises=nz)
+                for si, o in zip(who, outs):
+                    got[si].append(o.cpu())
+    for si in range(len(specs)):
+        assert len(got[si]) == len(solo[si])
+        for a, b in zip(got[si], solo[si]):
+            assert a.shape == b.shape
+            assert snr_db(b.numpy(), a.numpy()) > 60
