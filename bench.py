@@ -368,8 +368,11 @@ def main():
         d = fam[dom]
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         ach = d["tflops"] or 0.0
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` on this very command
+        # (profiles/README.md, round 1): only captured for flash_attn and the QKV GEMM
+        ncu_traffic = {"flash_attn": 414.8e6}
         roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src + " sustained dense bf16 (kernel timed inside a long step)",
+                    "traffic": ncu_traffic.get(dom), "peak_source": peak_src + " sustained dense bf16 (kernel timed inside a long step)",
                     "avg_launch_ms": d["ms_per_step"] / d["launches_per_step"],
                     "algorithmic_gflop_per_launch": 1e3 * d["algorithmic_tflop_per_step"] / d["launches_per_step"],
                     "share_of_step": d["ms_per_step"] / (ms / args.steps)}
