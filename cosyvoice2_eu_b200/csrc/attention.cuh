@@ -18,17 +18,19 @@ struct AttnParams {
 };
 void launch_flash_attn(const AttnParams& p, cudaStream_t stream);
 
-// Encoder: Transformer-XL relative-position attention, fp32 SIMT (1.5 % of the path's FLOPs).
+// Encoder: Transformer-XL relative-position attention on tcgen05 (encoder_attention.cu).
 struct RelAttnParams {
-  const float* qkv;     // [S, T_alloc, 1536] (q | k | v, bias already added)
-  const float* pos;     // [2*Tmax-1, 512] = linear_pos(PE), row (rel + Tmax - 1) <-> relative position rel = i - j
-  const float* bias_u;  // [8, 64]
-  const float* bias_v;  // [8, 64]
+  const __half* qu;     // [S, 8, T_alloc, 64]  (q + bias + pos_bias_u) / 8
+  const __half* qv;     // [S, 8, T_alloc, 64]  (q + bias + pos_bias_v) / 8
+  const __half* k;      // [S, 8, T_alloc, 64]
+  const __half* vt;     // [S, 8, 64, T_alloc]
+  const __half* pos;    // [R_alloc, 512] = linear_pos(PE), row (rel + Tmax - 1) <-> relative position rel = i - j
   __half* out;          // [S, T_alloc, 512]
   const int* lens;
   int len_all;
-  int S, T_alloc, Tmax;
+  int S, T_alloc, Tmax, R_alloc;
   int chunk;
+  int halo;
 };
 void launch_rel_attn(const RelAttnParams& p, cudaStream_t stream);
 

@@ -289,13 +289,14 @@ int cv2_op_flash_attn(void* stream, const void* q, const void* k, const void* vt
   CV2_API_END
 }
 
-int cv2_op_rel_attn(void* stream, const float* qkv, const float* pos, const float* bias_u, const float* bias_v, void* out,
-                    const int32_t* lens, int len_all, int S, int T_alloc, int Tmax, int chunk) {
+int cv2_op_rel_attn(void* stream, const void* qu, const void* qv, const void* k, const void* vt, const void* pos, void* out,
+                    const int32_t* lens, int len_all, int S, int T_alloc, int Tmax, int R_alloc, int chunk) {
   CV2_API_BEGIN
   RelAttnParams p;
   memset(&p, 0, sizeof(p));
-  p.qkv = qkv; p.pos = pos; p.bias_u = bias_u; p.bias_v = bias_v; p.out = static_cast<__half*>(out); p.lens = lens;
-  p.len_all = len_all; p.S = S; p.T_alloc = T_alloc; p.Tmax = Tmax; p.chunk = chunk;
+  p.qu = static_cast<const __half*>(qu); p.qv = static_cast<const __half*>(qv); p.k = static_cast<const __half*>(k);
+  p.vt = static_cast<const __half*>(vt); p.pos = static_cast<const __half*>(pos); p.out = static_cast<__half*>(out); p.lens = lens;
+  p.len_all = len_all; p.S = S; p.T_alloc = T_alloc; p.Tmax = Tmax; p.R_alloc = R_alloc; p.chunk = chunk; p.halo = 32;
   launch_rel_attn(p, (cudaStream_t)stream);
   CV2_API_END
 }

@@ -240,30 +240,30 @@ size_t estimator_forward(Engine& e, cudaStream_t st, const EstArgs& a, Arena& ws
 // Encoder layer (ConformerEncoderLayer without macaron / conv module, encoder_layer.py:160-236)
 // ---------------------------------------------------------------------------------------------------------
 struct EncBuffers {
-  float *X32, *QKV32, *POS32;
-  __half *H16, *ATT16, *F16, *PE16;
+  float* X32;
+  __half *H16, *ATT16, *F16, *PE16, *POS16, *QU16, *QV16, *K16, *VT16;
   int R_alloc;
 };
 
 static void enc_layer(Engine& e, cudaStream_t st, const EncBuffers& b, const std::string& lp, const int* lens, int S, int T,
                       int chunk, const LN* next_norm, __half* plain_out, bool dry) {
   static const int tap1[1] = {0};
-  {  // q | k | v with bias -> fp32
+  {  // (q + u)/8 | (q + v)/8 | k | v with bias -> per-head 16-bit attention operands (pos_bias_u / v folded into the bias)
     GemmParams p = base_params(lens);
-    p.out32 = b.QKV32; p.out32_ld = 1536;
+    p.q = b.QU16; p.q2 = b.QV16; p.k = b.K16; p.vt = b.VT16; p.heads = 8; p.q_scale = 0.125f;
     e.gemm(st, b.H16, S, T, 512, 512, e.W(lp + ".qkv"), 256, 1, tap1, p, dry);
   }
   {  // linear_pos on the relative-position table (no bias)
     GemmParams p = base_params(nullptr);
     p.len_all = 2 * T - 1;
-    p.out32 = b.POS32; p.out32_ld = 512;
+    p.emit[0] = emit_plain(b.POS16, 512);
     e.gemm(st, b.PE16, 1, b.R_alloc, 512, 512, e.W(lp + ".pos"), 256, 1, tap1, p, dry);
   }
   {
     RelAttnParams ap;
     memset(&ap, 0, sizeof(ap));
-    ap.qkv = b.QKV32; ap.pos = b.POS32; ap.bias_u = e.f32(lp + ".bias_u"); ap.bias_v = e.f32(lp + ".bias_v");
-    ap.out = b.ATT16; ap.lens = lens; ap.S = S; ap.T_alloc = T; ap.Tmax = T; ap.chunk = chunk;
+    ap.qu = b.QU16; ap.qv = b.QV16; ap.k = b.K16; ap.vt = b.VT16; ap.pos = b.POS16;
+    ap.out = b.ATT16; ap.lens = lens; ap.S = S; ap.T_alloc = T; ap.Tmax = T; ap.R_alloc = b.R_alloc; ap.chunk = chunk; ap.halo = kHalo;
     e.launches++;
     if (!dry) {
       e.prof_begin(st, Engine::F_REL_ATTN);
@@ -331,9 +331,12 @@ size_t flow_forward(Engine& e, cudaStream_t st, const FlowArgs& a, Arena& ws) {
   __half* X16 = ws.get<__half>((size_t)B * Tm * 512);
   __half* Y16 = ws.get<__half>((size_t)B * Tm * 512);
   eb.X32 = ws.get<float>((size_t)B * Tm * 512);
-  eb.QKV32 = ws.get<float>((size_t)B * Tm * 1536);
+  eb.QU16 = ws.get<__half>((size_t)B * Tm * 512);
+  eb.QV16 = ws.get<__half>((size_t)B * Tm * 512);
+  eb.K16 = ws.get<__half>((size_t)B * Tm * 512);
+  eb.VT16 = ws.get<__half>((size_t)B * Tm * 512);
   eb.R_alloc = round_up(2 * Tm - 1, 128);
-  eb.POS32 = ws.get<float>((size_t)eb.R_alloc * 512);
+  eb.POS16 = ws.get<__half>((size_t)eb.R_alloc * 512);
   eb.PE16 = ws.get<__half>((size_t)eb.R_alloc * 512);
   __half* PE16_t = ws.get<__half>((size_t)round_up(2 * Tt - 1, 128) * 512);
   eb.H16 = ws.get<__half>((size_t)B * Tm * 512);

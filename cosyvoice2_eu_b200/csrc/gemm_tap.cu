@@ -390,15 +390,20 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if (has_qkv) {  // attention operand split: q (pre-scaled) and k row-major per head, v transposed per head
           const int hd = p.heads * 64;
-          const int which = cbase / hd;            // 0 q, 1 k, 2 v (a 32-col chunk never straddles)
+          int which = cbase / hd;                  // 0 q, 1 k, 2 v (a 32-col chunk never straddles); with q2: 0 q, 1 q2, 2 k, 3 v
           const int cc = cbase - which * hd;
           const int h = cc >> 6, d0 = cc & 63;
+          __half* qdst = p.q;
+          if (p.q2) {
+            if (which == 1) qdst = p.q2;
+            which = which < 2 ? 0 : which - 1;
+          }
           if (which < 2) {
             const float sc = valid ? (which == 0 ? p.q_scale : 1.f) : 0.f;
             float w[32];
 #pragma unroll
             for (int i = 0; i < 32; i++) w[i] = v[i] * sc;
-            tile_store_f16((which == 0 ? p.q : p.k) + (((long long)c.s * p.heads + h) * p.T_alloc + (t - lane)) * 64 + d0, 64, stg, lane, w);
+            tile_store_f16((which == 0 ? qdst : p.k) + (((long long)c.s * p.heads + h) * p.T_alloc + (t - lane)) * 64 + d0, 64, stg, lane, w);
           } else {
             __half* dst = p.vt + (((long long)c.s * p.heads + h) * 64 + d0) * p.T_alloc + t;
 #pragma unroll
@@ -526,6 +531,7 @@ static void launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 
 // Specialised epilogues.               ACT       B LN RV MK RS R2 O32 AC FL SC  EMIT0       EMIT1      EMIT2     QKV
 using EpiQkv      = EpiCfg<ACT_NONE,  0, 0, 0, 0, 0, 0, 0, 0, 0, 0, EMIT_NONE,  EMIT_NONE, EMIT_NONE, 1>;
+using EpiQkvB     = EpiCfg<ACT_NONE,  1, 0, 0, 0, 0, 0, 0, 0, 0, 0, EMIT_NONE,  EMIT_NONE, EMIT_NONE, 1>;   // encoder q|q2|k|v
 using EpiResLn    = EpiCfg<ACT_NONE,  1, 0, 0, 0, 1, 0, 1, 0, 0, 0, EMIT_LN,    EMIT_NONE, EMIT_NONE, 0>;   // out-proj / FF2
 using EpiResPlain = EpiCfg<ACT_NONE,  1, 0, 0, 0, 1, 0, 1, 0, 0, 0, EMIT_PLAIN, EMIT_NONE, EMIT_NONE, 0>;   // last FF2 of a group
 using EpiGelu     = EpiCfg<ACT_GELU,  1, 0, 0, 0, 0, 0, 0, 0, 0, 0, EMIT_PLAIN, EMIT_NONE, EMIT_NONE, 0>;   // FF1
@@ -557,7 +563,7 @@ static void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
     return;                                       \
   }
   if constexpr (BN == 256) {
-    TRY(EpiQkv) TRY(EpiResLn) TRY(EpiGelu) TRY(EpiConv1) TRY(EpiConv2) TRY(EpiResPlain) TRY(EpiSilu) TRY(EpiRes)
+    TRY(EpiQkv) TRY(EpiResLn) TRY(EpiGelu) TRY(EpiConv1) TRY(EpiConv2) TRY(EpiResPlain) TRY(EpiSilu) TRY(EpiRes) TRY(EpiQkvB)
   }
   TRY(EpiOut32) TRY(EpiPlain) TRY(EpiSnake) TRY(EpiResSnake)
   if (p.emit[0].kind == EMIT_NONE || p.emit[0].kind == EMIT_LRELU) { TRY(EpiResSum) }
@@ -589,7 +595,7 @@ void launch_gemm_tap(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, con
   for (int e = 0; e < 3; e++) wants_row |= (p.emit[e].kind == EMIT_LN);
   CV2_CHECK(!wants_row || p.N <= bn, "gemm_tap: LayerNorm epilogue needs the full row in one tile (N=%d, BN=%d)", p.N, bn);
   CV2_CHECK(!p.ln || p.bias, "gemm_tap: LayerNorm epilogue expects a bias");
-  CV2_CHECK(!p.q || (p.N == 3 * p.heads * 64), "gemm_tap: qkv split needs N == 3*heads*64");
+  CV2_CHECK(!p.q || (p.N == (p.q2 ? 4 : 3) * p.heads * 64), "gemm_tap: qkv split needs N == 3*heads*64 (4*heads*64 with q2)");
   switch (bn) {
     case 64: launch_bn<64>(tmA, tmB, p, stream); break;
     case 128: launch_bn<128>(tmA, tmB, p, stream); break;

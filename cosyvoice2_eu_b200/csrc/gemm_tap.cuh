@@ -65,8 +65,10 @@ struct GemmParams {
   int flat;
   long long flat_off, flat_lo, flat_hi_per_len, flat_hi_add, flat_seq_elems;
   Emit emit[3];
-  // attention split (N = 3*heads*64): q*q_scale -> [S,H,T_alloc,64], k -> same, v -> transposed [S,H,64,T_alloc]
+  // attention split (N = 3*heads*64): q*q_scale -> [S,H,T_alloc,64], k -> same, v -> transposed [S,H,64,T_alloc];
+  // with q2 != null N = 4*heads*64 and the column blocks are q | q2 | k | v (both q blocks scaled)
   __half* q;
+  __half* q2;
   __half* k;
   __half* vt;
   int heads;

@@ -57,7 +57,7 @@ def load():
     lib.cv2_op_gemm_tap.argtypes = [vp, vp, i32, i32, i32, i64, vp, i32, i32, vp, i32, i32, C.POINTER(i32), vp, i32, vp, vp, f32,
                                     i32, f32, vp, vp, i32, i32, vp, f32, vp, i32, vp, vp, vp, vp]
     lib.cv2_op_flash_attn.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]
-    lib.cv2_op_rel_attn.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]
+    lib.cv2_op_rel_attn.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32]
     lib.cv2_op_source_stft.argtypes = [vp, vp, i32, vp, vp, i32, i32]
     lib.cv2_op_istft.argtypes = [vp, vp, i32, vp, i32, vp, i32]
     lib.cv2_op_nsf_source.argtypes = [vp, vp, i32, vp, vp, u64, vp, vp, vp, vp, i32]

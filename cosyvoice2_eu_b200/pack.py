@@ -71,11 +71,13 @@ def pack_flow(sd):
         for i in range(n):
             s, d = f"{src}.{i}", f"{dst}.{i}"
             a = s + ".self_attn"
-            o[d + ".qkv.w"] = _lin_w(torch.cat([sd[a + ".linear_q.weight"], sd[a + ".linear_k.weight"], sd[a + ".linear_v.weight"]], 0))
-            o[d + ".qkv.b"] = _f32(torch.cat([sd[a + ".linear_q.bias"], sd[a + ".linear_k.bias"], sd[a + ".linear_v.bias"]], 0))
+            # column blocks (q + u) | (q + v) | k | v: the Transformer-XL biases pos_bias_u / pos_bias_v (attention.py:308-311)
+            # are added to q before the two score matmuls, so they fold into the bias of two copies of linear_q
+            wq, bq = sd[a + ".linear_q.weight"], sd[a + ".linear_q.bias"].float()
+            o[d + ".qkv.w"] = _lin_w(torch.cat([wq, wq, sd[a + ".linear_k.weight"], sd[a + ".linear_v.weight"]], 0))
+            o[d + ".qkv.b"] = _f32(torch.cat([bq + sd[a + ".pos_bias_u"].float().reshape(-1), bq + sd[a + ".pos_bias_v"].float().reshape(-1),
+                                              sd[a + ".linear_k.bias"].float(), sd[a + ".linear_v.bias"].float()], 0))
             o[d + ".pos.w"] = _lin_w(sd[a + ".linear_pos.weight"])
-            o[d + ".bias_u"] = _f32(sd[a + ".pos_bias_u"].reshape(-1))
-            o[d + ".bias_v"] = _f32(sd[a + ".pos_bias_v"].reshape(-1))
             o[d + ".o.w"] = _lin_w(sd[a + ".linear_out.weight"])
             o[d + ".o.b"] = _f32(sd[a + ".linear_out.bias"])
             o[d + ".ff1.w"] = _lin_w(sd[s + ".feed_forward.w_1.weight"])

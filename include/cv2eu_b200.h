@@ -97,9 +97,11 @@ int cv2_op_gemm_tap(void* stream, const void* A, int S, int T_alloc, int Kc, lon
 /* q,k [S,H,T_alloc,64], vt [S,H,64,T_alloc] 16-bit -> out [S,T_alloc,H*64] 16-bit */
 int cv2_op_flash_attn(void* stream, const void* q, const void* k, const void* vt, void* out, const int32_t* lens, int len_all,
                       int S, int heads, int T_alloc, int chunk);
-/* encoder relative-position attention, fp32 qkv [S,T_alloc,1536], pos [2*Tmax-1,512] */
-int cv2_op_rel_attn(void* stream, const float* qkv, const float* pos, const float* bias_u, const float* bias_v, void* out,
-                    const int32_t* lens, int len_all, int S, int T_alloc, int Tmax, int chunk);
+/* encoder relative-position attention (RelPositionMultiHeadedAttention, cosyvoice/transformer/attention.py:249-330):
+ * 16-bit qu = (q+pos_bias_u)/8, qv = (q+pos_bias_v)/8, k [S,8,T_alloc,64], vt [S,8,64,T_alloc],
+ * pos [R_alloc,512] = linear_pos(table), row (rel + Tmax - 1) <-> relative position rel = i - j  -> out [S,T_alloc,512] */
+int cv2_op_rel_attn(void* stream, const void* qu, const void* qv, const void* k, const void* vt, const void* pos, void* out,
+                    const int32_t* lens, int len_all, int S, int T_alloc, int Tmax, int R_alloc, int chunk);
 /* source STFT: src [B, 480*mel_T] -> out [B, F_alloc, 18] */
 int cv2_op_source_stft(void* stream, const float* src, int mel_T, const int32_t* lens, float* out, int F_alloc, int B);
 /* iSTFT head: conv_post output [B, F_alloc, 18] -> wav [B, 480*mel_T] */

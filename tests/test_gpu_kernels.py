@@ -183,13 +183,13 @@ def test_flash_attention(chunk):
     assert err < 5e-3, err
 
 
-@pytest.mark.parametrize("chunk", [0, 25])
-def test_rel_attention(chunk):
+@pytest.mark.parametrize("chunk,T,Tal,len1", [(0, 100, 128, 61), (25, 100, 128, 61), (0, 300, 384, 170), (50, 300, 384, 257)])
+def test_rel_attention(chunk, T, Tal, len1):
     import token2wav_oracle as O
     lib, L = _lib()
     g = torch.Generator().manual_seed(5)
-    S, T, Tal = 2, 100, 128
-    lens = torch.tensor([100, 61], dtype=torch.int32)
+    S = 2
+    lens = torch.tensor([T, len1], dtype=torch.int32)
     x = torch.randn(S, T, 512, generator=g)
     p = {n: torch.randn(512, 512, generator=g) / math.sqrt(512) for n in
          ("linear_q.weight", "linear_k.weight", "linear_v.weight", "linear_out.weight", "linear_pos.weight")}
@@ -199,17 +199,26 @@ def test_rel_attention(chunk):
     p["pos_bias_v"] = torch.randn(8, 64, generator=g) * 0.1
     p["linear_out.weight"] = torch.eye(512)
     p["linear_out.bias"] = torch.zeros(512)
-    qkv = torch.zeros(S, Tal, 1536)
     F = torch.nn.functional
-    qkv[:, :T] = torch.cat([F.linear(x, p["linear_q.weight"], p["linear_q.bias"]), F.linear(x, p["linear_k.weight"], p["linear_k.bias"]),
-                            F.linear(x, p["linear_v.weight"], p["linear_v.bias"])], -1)
+    q = F.linear(x, p["linear_q.weight"], p["linear_q.bias"]).view(S, T, 8, 64)
+    k = F.linear(x, p["linear_k.weight"], p["linear_k.bias"]).view(S, T, 8, 64)
+    v = F.linear(x, p["linear_v.weight"], p["linear_v.bias"]).view(S, T, 8, 64)
+
+    def heads(a):                                   # [S,T,8,64] -> [S,8,Tal,64] 16-bit
+        o = torch.zeros(S, 8, Tal, 64)
+        o[:, :, :T] = a.permute(0, 2, 1, 3)
+        return o.half()
+    qu, qv, kk = heads((q + p["pos_bias_u"]) * 0.125), heads((q + p["pos_bias_v"]) * 0.125), heads(k)
+    vt = heads(v).transpose(2, 3).contiguous()     # [S,8,64,Tal]
     # table by relative position for Tmax = Tal: row (rel + Tal - 1)
+    R_alloc = (2 * Tal - 1 + 127) // 128 * 128
     pos = F.linear(O.rel_pos_table(Tal)[0], p["linear_pos.weight"])          # rows: rel = Tal-1 ... -(Tal-1)
-    pos = torch.flip(pos, [0]).contiguous()                                  # -> row r <-> rel = r - (Tal-1)
+    pos16 = torch.zeros(R_alloc, 512, dtype=torch.float16)
+    pos16[:2 * Tal - 1] = torch.flip(pos, [0]).half()                        # -> row r <-> rel = r - (Tal-1)
     out = torch.zeros(S, Tal, 512, dtype=torch.float16, device="cuda")
-    keep = [qkv.cuda(), pos.cuda(), p["pos_bias_u"].reshape(-1).cuda(), p["pos_bias_v"].reshape(-1).cuda(), lens.cuda()]
-    lib.check(L.cv2_op_rel_attn(_s(), lib.ptr(keep[0]), lib.ptr(keep[1]), lib.ptr(keep[2]), lib.ptr(keep[3]), lib.ptr(out),
-                                lib.ptr(keep[4]), 0, S, Tal, Tal, chunk))
+    keep = [qu.cuda(), qv.cuda(), kk.cuda(), vt.cuda(), pos16.cuda(), lens.cuda()]
+    lib.check(L.cv2_op_rel_attn(_s(), lib.ptr(keep[0]), lib.ptr(keep[1]), lib.ptr(keep[2]), lib.ptr(keep[3]), lib.ptr(keep[4]),
+                                lib.ptr(out), lib.ptr(keep[5]), 0, S, Tal, Tal, R_alloc, chunk))
     torch.cuda.synchronize()
     for s in range(S):
         n = int(lens[s])
