@@ -9,6 +9,8 @@
 // The logits tile is double-buffered in TMEM so S(j+1) is computed while softmax j runs (the softmax warps otherwise
 // spend most of their time waiting for the S MMA round trip); two CTAs per SM (100 KB smem, 256 TMEM columns each).
 // The kernel is MUFU-bound in the limit (head_dim 64: one exp2 per 256 MMA FLOPs).
+#include <stdlib.h>
+
 #include "attention.cuh"
 #include "common.cuh"
 #include "host_util.h"
@@ -239,8 +241,527 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   if (warp == 9) tmem_dealloc<256>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// v8: one softmax thread per query row, P kept in tensor memory, logits double-buffered.
+//   * each of the 128 softmax threads owns one row of the 128 x 64 logits tile: no cross-thread max / sum exchange;
+//   * P (16-bit) overwrites the first 32 columns of its own S buffer in place and is the A operand of the PV MMA straight
+//     from TMEM (tcgen05.mma with a tensor-memory A operand): no shared-memory P tile, no generic->async proxy fence, and
+//     the P store never waits for the previous PV;
+//   * S is double-buffered in TMEM and issued one tile ahead (S(j+2) right behind PV(j)), so the softmax threads do not wait
+//     for the S MMA round trip;
+//   * the running max is only raised when the tile max exceeds it by more than 2^8 (P stays < 2^8 in fp16; the row sum and
+//     O use the same stale reference, so the result is exact), which removes almost all O rescales;
+//   * 192 threads (4 softmax warps + TMA + MMA), 80 KB smem, 256 TMEM columns: two CTAs per SM.
+//   (Measured and rejected: row sums from a ones-row appended to V^T (PV with N = 80) -- 5 % slower than 64 FADDs per tile.)
+// ---------------------------------------------------------------------------------------------------------
+static constexpr int k8Stages = 4;
+static constexpr int k8OffK = kQBytes;
+static constexpr int k8OffV = k8OffK + k8Stages * kKBytes;
+static constexpr int k8VStage = kVBytes;
+static constexpr int k8OffBar = k8OffV + k8Stages * k8VStage;
+static constexpr int k8Smem = k8OffBar + 256;
+static constexpr int k8Threads = 6 * 32;
+static constexpr uint32_t k8TmemS = 0, k8TmemO = 128;
+
+// MODE: 0 = every exp2 on the MUFU; 2 = every exp2 as an FMA-pipe polynomial; 3 / 4 = every 2nd / 4th group of four
+// elements on the polynomial (splits the work between the XU and FMA pipes); 1 = no exp at all (timing experiments only)
+template <int MODE>
+__global__ void __launch_bounds__(k8Threads, 2)
+flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  const int t0 = blockIdx.x * 128;
+  const int h = blockIdx.y;
+  const int s = blockIdx.z;
+  const int len = p.lens ? p.lens[s] : p.len_all;
+  if (t0 >= len + p.halo) return;
+  const int sh = s * p.heads + h;
+  int kv_end = len;
+  if (p.chunk > 0) kv_end = min(len, ((t0 + 127) / p.chunk + 1) * p.chunk);
+  const int nkt = (kv_end + kKT - 1) / kKT;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k8OffBar);
+  uint64_t* q_full = bars;                      // 1
+  uint64_t* kv_full = bars + 1;                 // [k8Stages]
+  uint64_t* kv_empty = kv_full + k8Stages;      // [k8Stages]
+  uint64_t* s_full = kv_empty + k8Stages;       // [2]
+  uint64_t* p_full = s_full + 2;                // 1 (128 arrivals)
+  uint64_t* pv_done = p_full + 1;               // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < k8Stages; i++) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kQBytes);
+      tma_load_3d(smem, &tmQ, q_full, 0, t0, sh);
+      for (int j = 0; j < nkt; j++) {
+        const int st = j % k8Stages;
+        const uint32_t ph = (j / k8Stages) & 1;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_expect_tx(&kv_full[st], kKBytes + kVBytes);
+        tma_load_3d(smem + k8OffK + st * kKBytes, &tmK, &kv_full[st], 0, j * kKT, sh);
+        tma_load_3d(smem + k8OffV + st * k8VStage, &tmV, &kv_full[st], j * kKT, 0, sh);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, kKT, 0);
+      constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0);
+      const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(smem));
+      auto issue_s = [&](int j) {
+        const int st = j % k8Stages;
+        mbar_wait(&kv_full[st], (j / k8Stages) & 1);
+        tc_fence_after();
+        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(smem + k8OffK + st * kKBytes));
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          umma_f16(tmem_base + k8TmemS + (j & 1) * 64, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      if (nkt > 1) issue_s(1);
+      for (int j = 0; j < nkt; j++) {
+        mbar_wait(p_full, j & 1);   // softmax j has replaced S_j by P_j in tensor memory
+        tc_fence_after();
+        const int st = j % k8Stages;
+        const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(smem + k8OffV + st * k8VStage));
+#pragma unroll
+        for (int k = 0; k < kKT / 16; k++)
+          umma_f16_ts(tmem_base + k8TmemO, tmem_base + k8TmemS + (j & 1) * 64 + k * 8, v_desc + (uint64_t)(k * 2), idesc_o, (j | k) != 0);
+        umma_commit(&kv_empty[st]);
+        umma_commit(pv_done);
+        if (j + 2 < nkt) issue_s(j + 2);   // in order behind PV(j): overwrites P_j only after it was consumed
+      }
+    }
+  } else {
+    const int r = warp * 32 + lane;
+    const int t = t0 + r;
+    int kv_lim = len;
+    if (p.chunk > 0) kv_lim = min(len, (t / p.chunk + 1) * p.chunk);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const float LOG2E = 1.4426950408889634f;
+    float mref = 0.f, l = 0.f;     // reference max in log2 units
+    for (int j = 0; j < nkt; j++) {
+      const uint32_t s_addr = lane_addr + k8TmemS + (j & 1) * 64;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const int kbase = j * kKT;
+      uint32_t sr[64];
+      tmem_ld32(s_addr, sr);
+      tmem_ld32(s_addr + 32, sr + 32);
+      tmem_ld_wait();
+      if (kbase + kKT > kv_lim) {
+#pragma unroll
+        for (int i = 0; i < 64; i++)
+          if (kbase + i >= kv_lim) sr[i] = 0xff800000u;   // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; i += 8) {
+        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sr[i]), __uint_as_float(sr[i + 4])));
+        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sr[i + 1]), __uint_as_float(sr[i + 5])));
+        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 6])));
+        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sr[i + 3]), __uint_as_float(sr[i + 7])));
+      }
+      const float mxl = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * LOG2E;
+      float alpha = 1.f;
+      if (j == 0) {
+        mref = mxl;                       // tile 0 always holds a visible key for every row
+      } else if (mxl > mref + 8.f) {      // lazy: P <= 2^8 otherwise
+        alpha = fast_exp2(mref - mxl);
+        mref = mxl;
+      }
+      bool pv_seen = j == 0;
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        pv_seen = true;
+        uint32_t o[32];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          tmem_ld32(lane_addr + k8TmemO + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(lane_addr + k8TmemO + c * 32, o);
+        }
+        l *= alpha;
+      }
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float x0 = fmaf(__uint_as_float(sr[c * 32 + i]), LOG2E, -mref);
+          const float x1 = fmaf(__uint_as_float(sr[c * 32 + i + 1]), LOG2E, -mref);
+          const float x2 = fmaf(__uint_as_float(sr[c * 32 + i + 2]), LOG2E, -mref);
+          const float x3 = fmaf(__uint_as_float(sr[c * 32 + i + 3]), LOG2E, -mref);
+          const bool poly = MODE == 2 || (MODE == 3 && (i & 4)) || (MODE == 4 && (i & 12) == 12);
+          float e0, e1, e2, e3;
+          if (MODE == 1) {
+            e0 = x0; e1 = x1; e2 = x2; e3 = x3;
+          } else if (poly) {
+            e0 = poly_exp2(x0); e1 = poly_exp2(x1); e2 = poly_exp2(x2); e3 = poly_exp2(x3);
+          } else {
+            e0 = fast_exp2(x0); e1 = fast_exp2(x1); e2 = fast_exp2(x2); e3 = fast_exp2(x3);
+          }
+          l0 += e0; l1 += e1; l2 += e2; l3 += e3;
+          __half2 h0 = __floats2half2_rn(e0, e1), h1 = __floats2half2_rn(e2, e3);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h0);
+          pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+        }
+        tmem_st16(s_addr + c * 16, pk);   // P columns [16c, 16c+16) of this S buffer (all 64 logits are in registers)
+      }
+      l += (l0 + l1) + (l2 + l3);
+      if (!pv_seen) mbar_wait(pv_done, (j - 1) & 1);   // every thread observes every phase of pv_done (PV(j-1) is long done here)
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // final: O / l -> 16-bit [S, T_alloc, heads*64]
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    mbar_wait(pv_done, (nkt - 1) & 1);
+    tc_fence_after();
+    __half* dst = p.out + ((long long)s * p.T_alloc + t) * (p.heads * 64) + h * 64;
+    const bool valid = t < len;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      uint32_t raw[32];
+      tmem_ld32(lane_addr + k8TmemO + c * 32, raw);
+      tmem_ld_wait();
+      uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) f[e] = valid ? __uint_as_float(raw[i * 8 + e]) * inv : 0.f;
+        __half2 h0 = __floats2half2_rn(f[0], f[1]);
+        __half2 h1 = __floats2half2_rn(f[2], f[3]);
+        __half2 h2 = __floats2half2_rn(f[4], f[5]);
+        __half2 h3 = __floats2half2_rn(f[6], f[7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2);
+        u.w = *reinterpret_cast<uint32_t*>(&h3);
+        d4[i] = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<256>(tmem_base);
+}
+
+static void launch_flash_attn_v8(const AttnParams& p, cudaStream_t stream) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("CV2_ATTN_MODE");
+    mode = e ? atoi(e) : 0;
+    CV2_CUDA(cudaFuncSetAttribute(flash_attn_v8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, k8Smem));
+    CV2_CUDA(cudaFuncSetAttribute(flash_attn_v8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, k8Smem));
+    CV2_CUDA(cudaFuncSetAttribute(flash_attn_v8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, k8Smem));
+    CV2_CUDA(cudaFuncSetAttribute(flash_attn_v8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, k8Smem));
+    CV2_CUDA(cudaFuncSetAttribute(flash_attn_v8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, k8Smem));
+  }
+  const uint64_t SH = (uint64_t)p.S * p.heads;
+  uint64_t dq[3] = {64, (uint64_t)p.T_alloc, SH};
+  uint64_t sq[2] = {128, (uint64_t)p.T_alloc * 128};
+  uint32_t bq[3] = {64, 128, 1};
+  uint32_t bk[3] = {64, (uint32_t)kKT, 1};
+  CUtensorMap tmQ = make_tmap_16b(p.q, 3, dq, sq, bq);
+  CUtensorMap tmK = make_tmap_16b(p.k, 3, dq, sq, bk);
+  uint64_t dv[3] = {(uint64_t)p.T_alloc, 64, SH};
+  uint64_t sv[2] = {(uint64_t)p.T_alloc * 2, (uint64_t)p.T_alloc * 128};
+  uint32_t bv[3] = {(uint32_t)kKT, 64, 1};
+  CUtensorMap tmV = make_tmap_16b(p.vt, 3, dv, sv, bv);
+  dim3 grid(p.T_alloc / 128, p.heads, p.S);
+  switch (mode) {
+    case 1: flash_attn_v8_kernel<1><<<grid, k8Threads, k8Smem, stream>>>(tmQ, tmK, tmV, p); break;
+    case 2: flash_attn_v8_kernel<2><<<grid, k8Threads, k8Smem, stream>>>(tmQ, tmK, tmV, p); break;
+    case 3: flash_attn_v8_kernel<3><<<grid, k8Threads, k8Smem, stream>>>(tmQ, tmK, tmV, p); break;
+    case 4: flash_attn_v8_kernel<4><<<grid, k8Threads, k8Smem, stream>>>(tmQ, tmK, tmV, p); break;
+    default: flash_attn_v8_kernel<0><<<grid, k8Threads, k8Smem, stream>>>(tmQ, tmK, tmV, p); break;
+  }
+  CV2_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// v9: the v8 softmax (one thread per row, P in tensor memory, lazy rescale) at FOUR CTAs per SM.
+//   The v8 profile shows two softmax warps per scheduler, each latency bound (MUFU issue spacing, TMEM round trips) and in
+//   phase with each other; more resident warps is what fills the XU pipe.  To fit four CTAs: 128 TMEM columns per CTA
+//   (S single-buffered with P aliased on top, O), 48 KB smem (2 K/V stages), and <= 80 registers per thread by walking
+//   the 64 logits of a row in two 32-column passes (max, then probabilities) instead of holding the row.  The per-CTA
+//   chain S(j) -> softmax(j) -> PV(j) -> S(j+1) is serial; the other three CTAs of the SM fill the gaps.
+// ---------------------------------------------------------------------------------------------------------
+static constexpr int k9Stages = 2;
+static constexpr int k9OffK = kQBytes;
+static constexpr int k9OffV = k9OffK + k9Stages * kKBytes;
+static constexpr int k9OffBar = k9OffV + k9Stages * kVBytes;
+static constexpr int k9Smem = k9OffBar + 128;
+static constexpr int k9Threads = 6 * 32;
+static constexpr uint32_t k9TmemS = 0, k9TmemO = 64;
+
+__global__ void __launch_bounds__(k9Threads, 4)
+flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  const int t0 = blockIdx.x * 128;
+  const int h = blockIdx.y;
+  const int s = blockIdx.z;
+  const int len = p.lens ? p.lens[s] : p.len_all;
+  if (t0 >= len + p.halo) return;
+  const int sh = s * p.heads + h;
+  int kv_end = len;
+  if (p.chunk > 0) kv_end = min(len, ((t0 + 127) / p.chunk + 1) * p.chunk);
+  const int nkt = (kv_end + kKT - 1) / kKT;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k9OffBar);
+  uint64_t* q_full = bars;                      // 1
+  uint64_t* kv_full = bars + 1;                 // [k9Stages]
+  uint64_t* kv_empty = kv_full + k9Stages;      // [k9Stages]
+  uint64_t* s_full = kv_empty + k9Stages;       // 1
+  uint64_t* p_full = s_full + 1;                // 1 (128 arrivals)
+  uint64_t* o_done = p_full + 1;                // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < k9Stages; i++) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kQBytes);
+      tma_load_3d(smem, &tmQ, q_full, 0, t0, sh);
+      for (int j = 0; j < nkt; j++) {
+        const int st = j % k9Stages;
+        const uint32_t ph = (j / k9Stages) & 1;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_expect_tx(&kv_full[st], kKBytes + kVBytes);
+        tma_load_3d(smem + k9OffK + st * kKBytes, &tmK, &kv_full[st], 0, j * kKT, sh);
+        tma_load_3d(smem + k9OffV + st * kVBytes, &tmV, &kv_full[st], j * kKT, 0, sh);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, kKT, 0);
+      constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0);
+      const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(smem));
+      auto issue_s = [&](int j) {
+        const int st = j % k9Stages;
+        mbar_wait(&kv_full[st], (j / k9Stages) & 1);
+        tc_fence_after();
+        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(smem + k9OffK + st * kKBytes));
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          umma_f16(tmem_base + k9TmemS, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0);
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nkt; j++) {
+        mbar_wait(p_full, j & 1);   // softmax j has replaced S_j by P_j in tensor memory
+        tc_fence_after();
+        const int st = j % k9Stages;
+        const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(smem + k9OffV + st * kVBytes));
+#pragma unroll
+        for (int k = 0; k < kKT / 16; k++)
+          umma_f16_ts(tmem_base + k9TmemO, tmem_base + k9TmemS + k * 8, v_desc + (uint64_t)(k * 2), idesc_o, (j | k) != 0);
+        umma_commit(&kv_empty[st]);
+        if (j + 1 < nkt) issue_s(j + 1);   // in order behind PV(j): S_{j+1} overwrites P_j only after it was consumed
+        else umma_commit(o_done);
+      }
+    }
+  } else {
+    const int r = warp * 32 + lane;
+    const int t = t0 + r;
+    int kv_lim = len;
+    if (p.chunk > 0) kv_lim = min(len, (t / p.chunk + 1) * p.chunk);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const float LOG2E = 1.4426950408889634f;
+    float mref = 0.f, l = 0.f;     // reference max in log2 units
+    for (int j = 0; j < nkt; j++) {
+      mbar_wait(s_full, j & 1);     // also implies PV(j-1) has completed (same in-order pipe, commit covers prior MMAs)
+      tc_fence_after();
+      const int kbase = j * kKT;
+      const bool edge = kbase + kKT > kv_lim;
+      uint32_t sa[32];
+      // pass 1: row maximum
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        tmem_ld32(lane_addr + k9TmemS + c * 32, sa);
+        tmem_ld_wait();
+        if (edge) {
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            if (kbase + c * 32 + i >= kv_lim) sa[i] = 0xff800000u;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sa[i]), __uint_as_float(sa[i + 4])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sa[i + 1]), __uint_as_float(sa[i + 5])));
+          mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sa[i + 2]), __uint_as_float(sa[i + 6])));
+          mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sa[i + 3]), __uint_as_float(sa[i + 7])));
+        }
+      }
+      const float mxl = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * LOG2E;
+      float alpha = 1.f;
+      if (j == 0) {
+        mref = mxl;
+      } else if (mxl > mref + 8.f) {
+        alpha = fast_exp2(mref - mxl);
+        mref = mxl;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          tmem_ld32(lane_addr + k9TmemO + c * 32, sa);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) sa[i] = __float_as_uint(__uint_as_float(sa[i]) * alpha);
+          tmem_st32(lane_addr + k9TmemO + c * 32, sa);
+        }
+        l *= alpha;
+      }
+      // pass 2: probabilities; P chunk c (16 columns) lands on S columns [16c, 16c+16), all consumed by then
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        tmem_ld32(lane_addr + k9TmemS + c * 32, sa);
+        tmem_ld_wait();
+        if (edge) {
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            if (kbase + c * 32 + i >= kv_lim) sa[i] = 0xff800000u;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float e0 = fast_exp2(fmaf(__uint_as_float(sa[i]), LOG2E, -mref));
+          const float e1 = fast_exp2(fmaf(__uint_as_float(sa[i + 1]), LOG2E, -mref));
+          const float e2 = fast_exp2(fmaf(__uint_as_float(sa[i + 2]), LOG2E, -mref));
+          const float e3 = fast_exp2(fmaf(__uint_as_float(sa[i + 3]), LOG2E, -mref));
+          l0 += e0; l1 += e1; l2 += e2; l3 += e3;
+          __half2 h0 = __floats2half2_rn(e0, e1), h1 = __floats2half2_rn(e2, e3);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h0);
+          pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+        }
+        tmem_st16(lane_addr + k9TmemS + c * 16, pk);
+      }
+      l += (l0 + l1) + (l2 + l3);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    mbar_wait(o_done, 0);
+    tc_fence_after();
+    __half* dst = p.out + ((long long)s * p.T_alloc + t) * (p.heads * 64) + h * 64;
+    const bool valid = t < len;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      uint32_t raw[32];
+      tmem_ld32(lane_addr + k9TmemO + c * 32, raw);
+      tmem_ld_wait();
+      uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) f[e] = valid ? __uint_as_float(raw[i * 8 + e]) * inv : 0.f;
+        __half2 h0 = __floats2half2_rn(f[0], f[1]);
+        __half2 h1 = __floats2half2_rn(f[2], f[3]);
+        __half2 h2 = __floats2half2_rn(f[4], f[5]);
+        __half2 h3 = __floats2half2_rn(f[6], f[7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2);
+        u.w = *reinterpret_cast<uint32_t*>(&h3);
+        d4[i] = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<128>(tmem_base);
+}
+
+static void launch_flash_attn_v9(const AttnParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    CV2_CUDA(cudaFuncSetAttribute(flash_attn_v9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k9Smem));
+    configured = true;
+  }
+  const uint64_t SH = (uint64_t)p.S * p.heads;
+  uint64_t dq[3] = {64, (uint64_t)p.T_alloc, SH};
+  uint64_t sq[2] = {128, (uint64_t)p.T_alloc * 128};
+  uint32_t bq[3] = {64, 128, 1};
+  uint32_t bk[3] = {64, (uint32_t)kKT, 1};
+  CUtensorMap tmQ = make_tmap_16b(p.q, 3, dq, sq, bq);
+  CUtensorMap tmK = make_tmap_16b(p.k, 3, dq, sq, bk);
+  uint64_t dv[3] = {(uint64_t)p.T_alloc, 64, SH};
+  uint64_t sv[2] = {(uint64_t)p.T_alloc * 2, (uint64_t)p.T_alloc * 128};
+  uint32_t bv[3] = {(uint32_t)kKT, 64, 1};
+  CUtensorMap tmV = make_tmap_16b(p.vt, 3, dv, sv, bv);
+  dim3 grid(p.T_alloc / 128, p.heads, p.S);
+  flash_attn_v9_kernel<<<grid, k9Threads, k9Smem, stream>>>(tmQ, tmK, tmV, p);
+  CV2_LAUNCH_CHECK();
+}
+
 void launch_flash_attn(const AttnParams& p, cudaStream_t stream) {
   CV2_CHECK(p.T_alloc % 128 == 0, "attention: T_alloc %d not a multiple of 128", p.T_alloc);
+  static const bool use_v6 = getenv("CV2_ATTN_V6") != nullptr;   // two threads per row, P through smem, 2 CTAs/SM
+  static const bool use_v8 = getenv("CV2_ATTN_V8") != nullptr;   // one thread per row, P in TMEM, S double-buffered, 2 CTAs/SM
+  if (use_v8) return launch_flash_attn_v8(p, stream);
+  if (!use_v6) return launch_flash_attn_v9(p, stream);
   static bool configured = false;
   if (!configured) {
     CV2_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));

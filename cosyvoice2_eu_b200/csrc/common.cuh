@@ -53,12 +53,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifndef CV2_MBAR_TIMEOUT
+#define CV2_MBAR_TIMEOUT 20000000000LL   // ~10 s: far beyond any legitimate wait, even under ncu's instrumented replays
+#endif
 // Bounded wait: a protocol bug traps (and fails the launch) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (clock64() - t0 > CV2_MBAR_TIMEOUT) {
       printf("cv2: mbarrier timeout block (%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
              threadIdx.x, smem_u32(bar), parity);
       __trap();
@@ -147,6 +150,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
   asm volatile(
@@ -199,6 +211,20 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 2^x on the FMA / ALU pipes (no MUFU): Cody-Waite split with the round-down magic add, cubic minimax for 2^f on [0,1)
+// (max relative error 1.03e-4, below the 16-bit rounding of the probabilities it feeds), exponent spliced in with one
+// shift-add.  x <= ~120; anything below -126 flushes to (almost) zero.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.f);
+  float t;
+  asm("add.rm.ftz.f32 %0, %1, 0f4B400000;" : "=f"(t) : "f"(x));   // 2^23 + 2^22: floor(x) lands in the low mantissa bits
+  const float fl = t - 12582912.f;
+  const float f = x - fl;
+  float p = fmaf(f, 0.07826797f, 0.22630768f);
+  p = fmaf(p, f, 0.69542435f);
+  p = fmaf(p, f, 1.0f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
 }
 __device__ __forceinline__ float mish_f(float x) {
   // x * tanh(softplus(x)); softplus with PyTorch's threshold 20
