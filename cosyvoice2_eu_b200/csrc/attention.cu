@@ -734,6 +734,218 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 5) tmem_dealloc<128>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// v10: v9 with the logits double-buffered inside the same 128 TMEM columns.
+//   The v9 profile has the softmax warps waiting for S a third of the time (S(j+1) sits behind PV(j) because P_j lives
+//   on top of S_j).  Here the softmax step is 32 keys: S0 [0,32), S1 [32,64), O [64,128); S(jj+2) is issued right behind
+//   PV(jj), so the logits of step jj+1 are ready before softmax(jj) ends.  K / V^T still move as 64-key TMA tiles; a
+//   step uses rows [32h, 32h+32) of the K tile (descriptor + 4 KB) and k-steps {2h, 2h+1} of the V^T tile.  One 32-column
+//   pass per step (32 logits in registers), so the TMEM read traffic is half of v9's two-pass walk.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(k9Threads, 4)
+flash_attn_v10_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  const int t0 = blockIdx.x * 128;
+  const int h = blockIdx.y;
+  const int s = blockIdx.z;
+  const int len = p.lens ? p.lens[s] : p.len_all;
+  if (t0 >= len + p.halo) return;
+  const int sh = s * p.heads + h;
+  int kv_end = len;
+  if (p.chunk > 0) kv_end = min(len, ((t0 + 127) / p.chunk + 1) * p.chunk);
+  const int nh = (kv_end + 31) / 32;            // 32-key softmax steps
+  const int nkt = (nh + 1) / 2;                 // 64-key K / V^T tiles
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k9OffBar);
+  uint64_t* q_full = bars;                      // 1
+  uint64_t* kv_full = bars + 1;                 // [k9Stages]
+  uint64_t* kv_empty = kv_full + k9Stages;      // [k9Stages]
+  uint64_t* s_full = kv_empty + k9Stages;       // [2]
+  uint64_t* p_full = s_full + 2;                // 1 (128 arrivals)
+  uint64_t* pv_done = p_full + 1;               // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < k9Stages; i++) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kQBytes);
+      tma_load_3d(smem, &tmQ, q_full, 0, t0, sh);
+      for (int j = 0; j < nkt; j++) {
+        const int st = j % k9Stages;
+        const uint32_t ph = (j / k9Stages) & 1;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_expect_tx(&kv_full[st], kKBytes + kVBytes);
+        tma_load_3d(smem + k9OffK + st * kKBytes, &tmK, &kv_full[st], 0, j * kKT, sh);
+        tma_load_3d(smem + k9OffV + st * kVBytes, &tmV, &kv_full[st], j * kKT, 0, sh);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, 32, 0);
+      constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0);
+      const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(smem));
+      auto issue_s = [&](int jj) {
+        const int j = jj >> 1, hf = jj & 1;
+        const int st = j % k9Stages;
+        if (hf == 0) {
+          mbar_wait(&kv_full[st], (j / k9Stages) & 1);
+          tc_fence_after();
+        }
+        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(smem + k9OffK + st * kKBytes + hf * 4096));
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          umma_f16(tmem_base + hf * 32, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0);
+        umma_commit(&s_full[hf]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      if (nh > 1) issue_s(1);
+      for (int jj = 0; jj < nh; jj++) {
+        mbar_wait(p_full, jj & 1);   // softmax jj has replaced S_jj by P_jj in tensor memory
+        tc_fence_after();
+        const int j = jj >> 1, hf = jj & 1;
+        const int st = j % k9Stages;
+        const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(smem + k9OffV + st * kVBytes));
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+          umma_f16_ts(tmem_base + k9TmemO, tmem_base + hf * 32 + k * 8, v_desc + (uint64_t)((hf * 2 + k) * 2), idesc_o, (jj | k) != 0);
+        if (hf == 1 || jj == nh - 1) umma_commit(&kv_empty[st]);
+        umma_commit(pv_done);
+        if (jj + 2 < nh) issue_s(jj + 2);   // in order behind PV(jj): overwrites P_jj only after it was consumed
+      }
+    }
+  } else {
+    const int r = warp * 32 + lane;
+    const int t = t0 + r;
+    int kv_lim = len;
+    if (p.chunk > 0) kv_lim = min(len, (t / p.chunk + 1) * p.chunk);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const float LOG2E = 1.4426950408889634f;
+    float mref = 0.f, l = 0.f;     // reference max in log2 units
+    for (int jj = 0; jj < nh; jj++) {
+      const uint32_t s_addr = lane_addr + (jj & 1) * 32;
+      mbar_wait(&s_full[jj & 1], (jj >> 1) & 1);
+      tc_fence_after();
+      const int kbase = jj * 32;
+      uint32_t sa[32];
+      tmem_ld32(s_addr, sa);
+      tmem_ld_wait();
+      if (kbase + 32 > kv_lim) {
+#pragma unroll
+        for (int i = 0; i < 32; i++)
+          if (kbase + i >= kv_lim) sa[i] = 0xff800000u;
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sa[i]), __uint_as_float(sa[i + 4])));
+        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sa[i + 1]), __uint_as_float(sa[i + 5])));
+        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sa[i + 2]), __uint_as_float(sa[i + 6])));
+        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sa[i + 3]), __uint_as_float(sa[i + 7])));
+      }
+      const float mxl = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * LOG2E;
+      float alpha = 1.f;
+      if (jj == 0) {
+        mref = mxl;                        // step 0 always holds a visible key for every row
+      } else if (mxl > mref + 8.f) {
+        alpha = fast_exp2(mref - mxl);
+        mref = mxl;
+      }
+      bool pv_seen = jj == 0;
+      if (jj > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+        mbar_wait(pv_done, (jj - 1) & 1);
+        tc_fence_after();
+        pv_seen = true;
+        uint32_t o[16];
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {     // 16 columns at a time: the 32 logits stay in registers
+          tmem_ld16(lane_addr + k9TmemO + c * 16, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(lane_addr + k9TmemO + c * 16, o);
+        }
+        l *= alpha;
+      }
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float e0 = fast_exp2(fmaf(__uint_as_float(sa[i]), LOG2E, -mref));
+        const float e1 = fast_exp2(fmaf(__uint_as_float(sa[i + 1]), LOG2E, -mref));
+        const float e2 = fast_exp2(fmaf(__uint_as_float(sa[i + 2]), LOG2E, -mref));
+        const float e3 = fast_exp2(fmaf(__uint_as_float(sa[i + 3]), LOG2E, -mref));
+        l0 += e0; l1 += e1; l2 += e2; l3 += e3;
+        __half2 h0 = __floats2half2_rn(e0, e1), h1 = __floats2half2_rn(e2, e3);
+        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h0);
+        pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+      }
+      tmem_st16(s_addr, pk);
+      l += (l0 + l1) + (l2 + l3);
+      if (!pv_seen) mbar_wait(pv_done, (jj - 1) & 1);   // every thread observes every phase of pv_done
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    mbar_wait(pv_done, (nh - 1) & 1);
+    tc_fence_after();
+    __half* dst = p.out + ((long long)s * p.T_alloc + t) * (p.heads * 64) + h * 64;
+    const bool valid = t < len;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      uint32_t raw[32];
+      tmem_ld32(lane_addr + k9TmemO + c * 32, raw);
+      tmem_ld_wait();
+      uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) f[e] = valid ? __uint_as_float(raw[i * 8 + e]) * inv : 0.f;
+        __half2 h0 = __floats2half2_rn(f[0], f[1]);
+        __half2 h1 = __floats2half2_rn(f[2], f[3]);
+        __half2 h2 = __floats2half2_rn(f[4], f[5]);
+        __half2 h3 = __floats2half2_rn(f[6], f[7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2);
+        u.w = *reinterpret_cast<uint32_t*>(&h3);
+        d4[i] = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<128>(tmem_base);
+}
+
 static void launch_flash_attn_v9(const AttnParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
@@ -752,7 +964,17 @@ static void launch_flash_attn_v9(const AttnParams& p, cudaStream_t stream) {
   uint32_t bv[3] = {(uint32_t)kKT, 64, 1};
   CUtensorMap tmV = make_tmap_16b(p.vt, 3, dv, sv, bv);
   dim3 grid(p.T_alloc / 128, p.heads, p.S);
-  flash_attn_v9_kernel<<<grid, k9Threads, k9Smem, stream>>>(tmQ, tmK, tmV, p);
+  static const bool use_v10 = getenv("CV2_ATTN_V10") != nullptr;   // measured 7 % slower than v9: twice the barrier round trips per key
+  if (use_v10) {
+    static bool configured10 = false;
+    if (!configured10) {
+      CV2_CUDA(cudaFuncSetAttribute(flash_attn_v10_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k9Smem));
+      configured10 = true;
+    }
+    flash_attn_v10_kernel<<<grid, k9Threads, k9Smem, stream>>>(tmQ, tmK, tmV, p);
+  } else {
+    flash_attn_v9_kernel<<<grid, k9Threads, k9Smem, stream>>>(tmQ, tmK, tmV, p);
+  }
   CV2_LAUNCH_CHECK();
 }
 

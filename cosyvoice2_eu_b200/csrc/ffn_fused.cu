@@ -4,8 +4,10 @@
 //
 // The 1024-wide GELU activation never leaves the SM: per 128-row tile the hidden dimension is processed in 8 chunks of
 // 128; FF1(c) accumulates into a double-buffered 128-column TMEM tile, the epilogue warps apply bias + GELU and write the
-// 16-bit chunk straight into 128B-swizzled shared memory, where it is the A operand of FF2(c), which accumulates the
-// 256-column output tile in TMEM across the 8 chunks.  Weights stream through a 5-slot TMA ring (16 KB slots).
+// 16-bit chunk back into the first 64 columns of the SAME TMEM buffer, where it is the A operand of FF2(c) (tcgen05.mma with
+// a tensor-memory A operand), which accumulates the 256-column output tile in TMEM across the 8 chunks.  No shared-memory
+// hand-off, no generic->async proxy fence, and the hidden chunk is double-buffered with its accumulator.  Buffer reuse needs
+// no barrier: FF1(c+2) is issued behind FF2(c) on the in-order tensor pipe.  Weights stream through a 7-slot TMA ring.
 //   warp 0: TMA (H tile + weight stream)   warp 1: tcgen05.mma issuer   warps 2-17: epilogue (four per TMEM lane quarter)
 // Saves the [rows,1024] 16-bit round trip through HBM (4 KB/row of the 18 KB/row a transformer block moves) and one launch.
 #include "common.cuh"
@@ -134,8 +136,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
       // ------------------------------- MMA issuer ---------------------------------
       constexpr uint32_t idesc = umma_idesc_f16(128, 128, 0);
       const uint32_t h_addr = smem_u32(smem);
-      const uint32_t f_addr = smem_u32(smem + kOffF);
-      int lt = 0, wit = 0, use1[2] = {0, 0}, fcnt = 0;
+      int lt = 0, wit = 0, fcnt = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int s, t0, len;
         if (!ffn_tile(p, tile, t_tiles, s, t0, len)) continue;
@@ -146,9 +147,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
           int c;
           ffn_op(o, is_ff2, c);
           if (!is_ff2) {
-            const int b = c & 1;
-            mbar_wait(&acc1_empty[b], (use1[b] & 1) ^ 1);       // GELU epilogue has drained this accumulator
-            tc_fence_after();
+            const int b = c & 1;   // buffer b was last read by FF2(c-2), issued earlier on the same in-order pipe
             for (int kb = 0; kb < 4; kb++, wit++) {
               const int st = wit % kSlots;
               mbar_wait(&w_full[st], (wit / kSlots) & 1);
@@ -161,29 +160,27 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
               umma_commit(&w_empty[st]);
             }
             umma_commit(&acc1_full[b]);
-            use1[b]++;
             if (c == 7) umma_commit(h_empty);                  // all FF1 MMAs of this tile issued: H tile may be refilled
           } else {
             if (c == 0) {
               mbar_wait(acc2_empty, (lt & 1) ^ 1);              // previous tile's output epilogue has drained acc2
               tc_fence_after();
             }
-            mbar_wait(f_full, fcnt & 1);                        // GELU chunk c is in shared memory
+            mbar_wait(f_full, fcnt & 1);                        // GELU chunk c (16-bit) is in TMEM, on top of its accumulator
             tc_fence_after();
+            const uint32_t a_tmem = tmem_base + kAcc1 + (c & 1) * 128;
             for (int i = 0; i < 4; i++, wit++) {
               const int st = wit % kSlots;
               const int kb = i >> 1, half = i & 1;
               mbar_wait(&w_full[st], (wit / kSlots) & 1);
               tc_fence_after();
-              const uint64_t a_desc = umma_smem_desc_sw128(f_addr + kb * 16384);
               const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(smem + kOffW + st * kSlotBytes));
 #pragma unroll
               for (int k = 0; k < 4; k++)
-                umma_f16(tmem_base + kAcc2 + half * 128, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                         (c | kb | k) != 0);
+                umma_f16_ts(tmem_base + kAcc2 + half * 128, a_tmem + kb * 32 + k * 8, b_desc + (uint64_t)(k * 2), idesc,
+                            (c | kb | k) != 0);
               umma_commit(&w_empty[st]);
             }
-            umma_commit(f_empty);                               // F chunk consumed
             fcnt++;
             if (c == 7) umma_commit(acc2_full);
           }
@@ -201,8 +198,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
     float* red_c = red;                      // [4][128]
     float* red_d = red + 512;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint8_t* frow = smem + kOffF + (part >> 1) * 16384 + r * 128;   // atom = 64 columns; this thread writes 32 of them
-    int lt = 0, use1[2] = {0, 0}, g = 0;
+    int lt = 0, use1[2] = {0, 0};
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int s, t0, len;
       if (!ffn_tile(p, tile, t_tiles, s, t0, len)) continue;
@@ -211,7 +207,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
       const long long row = (long long)s * p.T_alloc + t;
       const long long row0 = row - lane;
       // ---- 8 hidden chunks: bias + GELU -> 16-bit chunk in shared memory (A operand of FF2) ----
-      for (int c = 0; c < 8; c++, g++) {
+      for (int c = 0; c < 8; c++) {
         const int b = c & 1;
         float bv[32];
         load32(p.b1 + c * 128 + part * 32, bv, true, 32);      // bias first: its latency hides behind the accumulator wait
@@ -221,9 +217,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
         uint32_t raw[32];
         tmem_ld32(lane_addr + kAcc1 + b * 128 + part * 32, raw);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc1_empty[b]);            // accumulator is in registers: release it to the MMA warp
+        // the 16-bit chunk lands on columns [16*part, 16*part+16) of this buffer = fp32 columns of part/2: the four warps
+        // of a lane quarter must all hold their accumulator slice in registers before any of them writes
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
 #pragma unroll
         for (int i = 0; i < 32; i++) bv[i] = fast_gelu_erf(__uint_as_float(raw[i]) + bv[i]);
 #pragma unroll
@@ -231,15 +227,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
           __half2 h2 = __floats2half2_rn(bv[i], bv[i + 1]);
           raw[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
         }
-        if (c == 0) ffn_bar();                                  // every warp has left the previous tile's output staging (= F)
-        mbar_wait(f_empty, (g & 1) ^ 1);                        // FF2 of the previous chunk has finished reading F
-#pragma unroll
-        for (int gq = 0; gq < 4; gq++) {
-          uint4 u;
-          u.x = raw[gq * 4 + 0]; u.y = raw[gq * 4 + 1]; u.z = raw[gq * 4 + 2]; u.w = raw[gq * 4 + 3];
-          *reinterpret_cast<uint4*>(frow + ((((part & 1) * 4 + gq) ^ (r & 7)) << 4)) = u;
-        }
-        fence_proxy_async_smem();
+        tmem_st16(lane_addr + kAcc1 + b * 128 + part * 16, raw);
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(f_full);
       }
