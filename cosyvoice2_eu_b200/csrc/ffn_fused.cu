@@ -68,8 +68,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
   uint64_t* acc1_full = w_empty + kSlots;  // [2]
   uint64_t* acc1_empty = acc1_full + 2;    // [2]
   uint64_t* f_full = acc1_empty + 2;
-  uint64_t* f_empty = f_full + 1;
-  uint64_t* acc2_full = f_empty + 1;
+  uint64_t* f_seen = f_full + 1;           // MMA thread has observed f_full of a chunk (keeps f_full at most one phase ahead)
+  uint64_t* acc2_full = f_seen + 1;
   uint64_t* acc2_empty = acc2_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
 
@@ -93,7 +93,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
       mbar_init(&acc1_empty[i], kEpiW);
     }
     mbar_init(f_full, kEpiW);
-    mbar_init(f_empty, 1);
+    mbar_init(f_seen, 1);
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, kEpiW);
     fence_barrier_init();
@@ -167,6 +167,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
               tc_fence_after();
             }
             mbar_wait(f_full, fcnt & 1);                        // GELU chunk c (16-bit) is in TMEM, on top of its accumulator
+            mbar_arrive(f_seen);                                // back-pressure: chunk c+1 may only be signalled after this observation
             tc_fence_after();
             const uint32_t a_tmem = tmem_base + kAcc1 + (c & 1) * 128;
             for (int i = 0; i < 4; i++, wit++) {
@@ -198,7 +199,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
     float* red_c = red;                      // [4][128]
     float* red_d = red + 512;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    int lt = 0, use1[2] = {0, 0};
+    int lt = 0, use1[2] = {0, 0}, g = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int s, t0, len;
       if (!ffn_tile(p, tile, t_tiles, s, t0, len)) continue;
@@ -207,7 +208,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
       const long long row = (long long)s * p.T_alloc + t;
       const long long row0 = row - lane;
       // ---- 8 hidden chunks: bias + GELU -> 16-bit chunk in shared memory (A operand of FF2) ----
-      for (int c = 0; c < 8; c++) {
+      for (int c = 0; c < 8; c++, g++) {
         const int b = c & 1;
         float bv[32];
         load32(p.b1 + c * 128 + part * 32, bv, true, 32);      // bias first: its latency hides behind the accumulator wait
@@ -230,6 +231,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
         tmem_st16(lane_addr + kAcc1 + b * 128 + part * 16, raw);
         tmem_st_wait();
         tc_fence_before();
+        if (g > 0) mbar_wait(f_seen, (g - 1) & 1);              // never two unobserved phases of f_full (robust to any warp skew)
         __syncwarp();
         if (lane == 0) mbar_arrive(f_full);
       }
