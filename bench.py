@@ -376,6 +376,19 @@ def main():
                     "avg_launch_ms": d["ms_per_step"] / d["launches_per_step"],
                     "algorithmic_gflop_per_launch": 1e3 * d["algorithmic_tflop_per_step"] / d["launches_per_step"],
                     "share_of_step": d["ms_per_step"] / (ms / args.steps)}
+        # bandwidth-bound vocoder kernels: algorithmic bytes (fp32 I/O per output sample) / event-timed launch
+        samples = float(sum(2 * n * 480 for n in n_tokens))
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_bytes = {"source_stft": 22.0, "istft": 22.0, "nsf_source": 4.0 + 4.0 / 480}
+        hbm_kernels = {}
+        for k, bps in hbm_bytes.items():
+            if k in fam and fam[k]["ms_per_step"] > 0:
+                gbs = samples * bps / (fam[k]["ms_per_step"] / fam[k]["launches_per_step"] * 1e-3) / 1e9
+                hbm_kernels[k] = {"algorithmic_bytes_per_sample": bps, "ms_per_launch": fam[k]["ms_per_step"] / fam[k]["launches_per_step"],
+                                  "achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": gbs / hbm_peak}
+        hbm_kernels["note"] = ("peak = measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs); nsf_source in production mode draws its "
+                               "noise in-kernel (9 sines + 9 normals per 4-byte sample), i.e. it is ALU/MUFU bound there and only "
+                               "bandwidth bound in parity mode (36 B/sample noise read)")
         total_flop = sum(flops.values()) * world
         line = {
             "metric": "token2wav_audio_seconds_per_second", "value": total_audio * args.steps / (ms / 1e3), "unit": "audio-s/s",
@@ -392,6 +405,7 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roofline,
             "families": fam,
+            "hbm_kernels": hbm_kernels,
             "gemm256_by_epilogue": g256,
             "whole_step_tflops": total_flop / 1e12 / (ms / args.steps / 1e3) / world,
             "rtf_batch1": {"workload": "BASELINE configs[1]: single 10 s utterance (250 tokens + 75-token prompt), batch 1",

@@ -101,6 +101,16 @@ int cv2_engine_set_seed_ptr(cv2_engine* h, const unsigned long long* seed_dev) {
   CV2_API_END
 }
 
+int cv2_engine_set_option(cv2_engine* h, const char* name, int value) {
+  CV2_API_BEGIN
+  CV2_CHECK(h && name, "null argument");
+  const std::string n(name);
+  if (n == "fuse_euler") h->e.fuse_euler = value != 0;
+  else if (n == "fuse_ffn") h->e.fuse_ffn = value != 0;
+  else fail("unknown engine option '%s'", name);
+  CV2_API_END
+}
+
 int cv2_engine_set_profiling(cv2_engine* h, int on) {
   CV2_API_BEGIN
   CV2_CHECK(h, "null engine");
@@ -216,9 +226,9 @@ size_t cv2_hift_workspace_bytes(cv2_engine* h, int B, int mel_T) {
   }
 }
 
-int cv2_hift_forward(cv2_engine* h, void* stream, const float* mel, int mel_T, const int32_t* lens, const float* cache_source,
-                     int cache_len, const float* noise, unsigned long long seed, float* speech, float* source, float* f0_out,
-                     int B, void* workspace, size_t workspace_bytes) {
+static int hift_forward_impl(cv2_engine* h, void* stream, const float* mel, int mel_T, const int32_t* lens, const float* cache_source,
+                             int cache_len, const float* noise, unsigned long long seed, float* speech, float* source, float* f0_out,
+                             int16_t* pcm16, int B, void* workspace, size_t workspace_bytes) {
   CV2_API_BEGIN
   CV2_CHECK(h && h->e.has_hift, "engine not finalized for hift");
   CV2_CHECK(mel && speech && source && workspace, "null argument");
@@ -229,10 +239,24 @@ int cv2_hift_forward(cv2_engine* h, void* stream, const float* mel, int mel_T, c
   HiftArgs a;
   memset(&a, 0, sizeof(a));
   a.mel = mel; a.mel_T = mel_T; a.lens = lens; a.cache_source = cache_source; a.cache_len = cache_source ? cache_len : 0;
-  a.noise = noise; a.seed = seed; a.speech = speech; a.source = source; a.f0_out = f0_out; a.B = B;
+  a.noise = noise; a.seed = seed; a.speech = speech; a.source = source; a.f0_out = f0_out; a.pcm16 = pcm16; a.B = B;
   h->e.launches = 0;
   hift_forward(h->e, (cudaStream_t)stream, a, ws);
   CV2_API_END
+}
+
+int cv2_hift_forward(cv2_engine* h, void* stream, const float* mel, int mel_T, const int32_t* lens, const float* cache_source,
+                     int cache_len, const float* noise, unsigned long long seed, float* speech, float* source, float* f0_out,
+                     int B, void* workspace, size_t workspace_bytes) {
+  return hift_forward_impl(h, stream, mel, mel_T, lens, cache_source, cache_len, noise, seed, speech, source, f0_out, nullptr, B,
+                           workspace, workspace_bytes);
+}
+
+int cv2_hift_forward_pcm16(cv2_engine* h, void* stream, const float* mel, int mel_T, const int32_t* lens, const float* cache_source,
+                           int cache_len, const float* noise, unsigned long long seed, float* speech, float* source, float* f0_out,
+                           int16_t* pcm16, int B, void* workspace, size_t workspace_bytes) {
+  return hift_forward_impl(h, stream, mel, mel_T, lens, cache_source, cache_len, noise, seed, speech, source, f0_out, pcm16, B,
+                           workspace, workspace_bytes);
 }
 
 int cv2_crossfade(void* stream, float* speech, const float* old_tail, const double* window, int n) {

@@ -68,6 +68,7 @@ struct Engine {
   bool finalized = false;
   bool has_flow = false, has_hift = false;
   bool fuse_ffn = getenv("CV2_NO_FFN_FUSION") == nullptr;   // estimator FF1+GELU+FF2 in one kernel (ffn_fused.cu)
+  bool fuse_euler = getenv("CV2_NO_EULER_FUSION") == nullptr; // CFG combine + Euler update inside final_proj's epilogue
   const unsigned long long* seed_dev = nullptr;   // optional device-resident NSF noise seed (CUDA-graph replays)
   std::unordered_map<std::string, Weight> weights;      // lazily built from tensors
   std::unordered_map<uint64_t, CUtensorMap> amap_cache;  // activation tensor maps
@@ -173,6 +174,7 @@ struct HiftArgs {
   float* speech;               // [B, 480*mel_T]
   float* source;               // [B, 1, 480*mel_T]
   float* f0_out;               // optional [B, mel_T]
+  short* pcm16;                // optional [B, 480*mel_T] int16 PCM of `speech` (servers' wire format), written by the iSTFT kernel
   int B;
 };
 size_t hift_forward(Engine& e, cudaStream_t st, const HiftArgs& a, Arena& ws);

@@ -113,7 +113,7 @@ void Engine::gemm(cudaStream_t st, const __half* A, int S, int T_alloc, int Kc, 
   }
   const int bi = bn == 64 ? 0 : (bn == 128 ? 1 : 2);
   const CUtensorMap& tb = wmap(w, bn);
-  const CUtensorMap& ta = amap(A, S, T_alloc, Kc, ldA);
+  const CUtensorMap& ta = amap(A, p.S_map > 0 ? p.S_map : S, T_alloc, Kc, ldA);
   prof_begin(st, bn == 256 ? F_COUNT + gemm_tap_spec(bn, p) : bi);
   launch_gemm_tap(bn, ta, tb, p, st);
   prof_end(st);

@@ -2,6 +2,8 @@
 // CausalConditionalDecoder estimator (reference: cosyvoice/flow/flow.py:235-283, flow_matching.py:71-123,
 // decoder.py:405-494, transformer/upsample_encoder.py:243-306).  Batched over utterances with per-utterance
 // lengths (B=1 semantics per utterance: every kernel treats a sequence end like a tensor edge).
+#include <math.h>
+
 #include "attention.cuh"
 #include "engine.h"
 #include "flow_kernels.cuh"
@@ -58,8 +60,20 @@ static EstBuffers est_alloc(Arena& ws, int S, int T) {
   return b;
 }
 
+// Classifier-free-guidance combine + Euler update fused into final_proj (flow_matching.py:104-121): the projection is
+// linear, so (1+cfg) W h_cond - cfg W h_uncond is ONE GEMM over the K-concatenated pair of rows (weights [(1+cfg) W | -cfg W],
+// the second "tap" reads sequence s + B), and the epilogue does x += dt * (v + b) * mask in fp32 and re-emits x as the
+// 16-bit input channels of both CFG rows for the next step.
+struct EulerFuse {
+  float* x32;        // [B, T_alloc, 80] Euler state
+  __half* xin16;     // [2B, T_alloc, 320]: channels 0..79 of both rows are rewritten
+  float dt;
+  int B;
+};
+
 static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __half* xin16, const int* lens, int S, int T,
-                     const float* temb_res, int nt, int trow, int trow_ld, int streaming, bool dry) {
+                     const float* temb_res, int nt, int trow, int trow_ld, int streaming, bool dry,
+                     const EulerFuse* ef = nullptr) {
   static const int causal3[3] = {-2, -1, 0};
   static const int tap1[1] = {0};
   const __half* cur = xin16;
@@ -185,6 +199,19 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
     p.act = ACT_MISH;
     p.emit[0] = emit_plain(b.M16, 256);
     e.gemm(st, b.N16, S, T, 256, 256, e.W("est.final.c"), 256, 3, causal3, p, dry);
+  }
+  if (ef) {  // final_proj + CFG combine + Euler update, one launch over the B utterances
+    static const int pair[2] = {0, 0};
+    GemmParams p = base_params(lens);
+    p.tap_seq[1] = ef->B;
+    p.S_map = S;
+    p.mask_pre_res = 1;
+    p.out_scale = ef->dt;
+    p.out32 = ef->x32; p.out32_ld = 80; p.out32_accum = 1;
+    p.emit[0] = emit_plain(ef->xin16, 320, 0);
+    p.emit[1] = emit_plain(ef->xin16 + (size_t)ef->B * T * 320, 320, 0);
+    e.gemm(st, b.M16, ef->B, T, 256, 256, e.W("est.proj_cfg"), 128, 2, pair, p, dry);
+    return;
   }
   {  // final_proj (1x1, 256 -> 80), output * mask
     GemmParams p = base_params(lens);
@@ -446,7 +473,15 @@ size_t flow_forward(Engine& e, cudaStream_t st, const FlowArgs& a, Arena& ws) {
     if (a.mu_out) launch_ntc_to_nct(MU32, Tm, 80, 0, nullptr, a.mu_out, (long long)80 * 2 * a.max_tok_total, 2 * a.max_tok_total, 80,
                                     len_mel, B, st);
   }
+  // the fused weights are packed for the model's inference_cfg_rate (0.7, cosyvoice2.yaml:75); any other rate takes the
+  // separate CFG-combine + Euler kernel
+  const bool fuse_euler = e.fuse_euler && fabsf(a.cfg - 0.7f) < 1e-6f && e.tensors.count("est.proj_cfg.w");
   for (int step = 0; step < a.n_steps; step++) {
+    if (fuse_euler) {
+      EulerFuse ef{Xst, XIN16, a.dt_steps[step], B};
+      est_core(e, st, sb, XIN16, len_mel, 2 * B, Tm, tres, a.n_steps, step, 0, a.streaming, dry, &ef);
+      continue;
+    }
     est_core(e, st, sb, XIN16, len_mel, 2 * B, Tm, tres, a.n_steps, step, 0, a.streaming, dry);
     e.launches++;
     if (!dry) launch_euler_pack(Xst, sb.V32, nullptr, 0, XIN16, len_mel, B, Tm, a.dt_steps[step], a.cfg, 0, st);

@@ -223,7 +223,7 @@ size_t hift_forward(Engine& e, cudaStream_t st, const HiftArgs& a, Arena& ws) {
   e.launches++;
   if (!dry) {
     e.prof_begin(st, Engine::F_ISTFT);
-    launch_istft(CP32, Ta[3], 18, lens[0], 0, a.speech, (long long)480 * a.mel_T, B, a.mel_T, st);
+    launch_istft(CP32, Ta[3], 18, lens[0], 0, a.speech, (long long)480 * a.mel_T, B, a.mel_T, st, a.pcm16);
     e.prof_end(st);
   }
   return ws.peak;

@@ -127,7 +127,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           uint8_t* a_dst = smem + st * SM::kStageBytes;
           uint8_t* b_dst = a_dst + kABytes;
           mbar_expect_tx(&full_bar[st], SM::kStageBytes);
-          tma_load_3d(a_dst, &tmA, &full_bar[st], kb * kKBlock, c.t0 + p.tap_off[tap], c.s);
+          tma_load_3d(a_dst, &tmA, &full_bar[st], kb * kKBlock, c.t0 + p.tap_off[tap], c.s + p.tap_seq[tap]);
           tma_load_2d(b_dst, &tmB, &full_bar[st], it * kKBlock, c.n0);
         }
       }

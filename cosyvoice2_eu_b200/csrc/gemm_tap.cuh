@@ -35,6 +35,8 @@ struct GemmParams {
   int kb_per_tap;      // Kc_pad / 64
   int ntaps;
   int tap_off[16];     // row offset of each tap
+  int tap_seq[16];     // sequence offset of each tap (A row block read from sequence s + tap_seq[j]; CFG pair = two "taps")
+  int S_map;           // sequences covered by the A tensor map when it differs from S (0: S)
   const int* lens;     // [S] valid rows per sequence (nullptr: len_all)
   int len_all;
   int halo;            // a tile is computed iff t0 < len + halo

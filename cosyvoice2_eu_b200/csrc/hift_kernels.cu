@@ -124,15 +124,28 @@ __global__ void nsf_phase_kernel(const float* __restrict__ f0, int f0_stride, co
   }
 }
 
-__device__ __forceinline__ float gauss_hash(unsigned long long seed, unsigned long long idx) {
-  // counter-based N(0,1): two 32-bit hashes -> Box-Muller (production mode only; parity mode injects noise)
+// counter-based N(0,1) pair: one 64-bit mix -> two uniforms -> both Box-Muller outputs (production mode only; parity mode
+// injects the reference's noise tensor)
+__device__ __forceinline__ void gauss_pair(unsigned long long seed, unsigned long long idx, float& n0, float& n1) {
   unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   z = z ^ (z >> 31);
   const float u1 = ((unsigned)(z >> 40) + 1.f) * (1.f / 16777217.f);
   const float u2 = (unsigned)((z >> 8) & 0xFFFFFF) * (1.f / 16777216.f);
-  return sqrtf(-2.f * __logf(u1)) * __cosf(6.283185307f * u2);
+  const float rr = sqrtf(-2.f * __logf(u1));
+  float sn, cs;
+  __sincosf(6.283185307f * u2, &sn, &cs);
+  n0 = rr * cs;
+  n1 = rr * sn;
+}
+// sin of a large fp32 phase (2 pi * 480 * cumulative cycles reaches 1e5..1e6): reduce modulo 2 pi in fp64 (exact to 1e-10),
+// then the fp32 fast path; avoids sinf's Payne-Hanek slow path, which dominated this kernel
+__device__ __forceinline__ float sin_big(float ph) {
+  const double x = (double)ph;
+  const double k = rint(x * 0.15915494309189535);
+  const float r = (float)fma(-k, 6.283185307179586, x);
+  return sinf(r);
 }
 
 __global__ void nsf_source_kernel(const float* __restrict__ f0, int f0_stride, const float* __restrict__ P, int T_alloc,
@@ -165,13 +178,21 @@ __global__ void nsf_source_kernel(const float* __restrict__ f0, int f0_stride, c
   const float* p1 = P + ((long long)b * T_alloc + i1) * 9;
   const float* nz = noise ? noise + (long long)b * noise_bstride + j * 9 : nullptr;
   if (seed_ptr) seed = *seed_ptr;   // device-resident seed: a captured CUDA graph still draws fresh noise per replay
+  float nv[10];
+  if (nz) {
+#pragma unroll
+    for (int h = 0; h < 9; h++) nv[h] = nz[h];
+  } else {
+#pragma unroll
+    for (int h = 0; h < 10; h += 2)
+      gauss_pair(seed + (unsigned long long)b * 0x1000003ull, (unsigned long long)j * 5 + (h >> 1), nv[h], nv[h + 1]);
+  }
   float acc = lb[0];
 #pragma unroll
   for (int h = 0; h < 9; h++) {
     const float ph = __fadd_rn(__fmul_rn(l0, p0[h]), __fmul_rn(l1, p1[h]));
-    const float sine = sinf(ph) * 0.1f;
-    const float n = nz ? nz[h] : gauss_hash(seed + (unsigned long long)b * 0x1000003ull, (unsigned long long)j * 9 + h);
-    acc += lw[h] * (sine * uv + namp * n);
+    const float sine = sin_big(ph) * 0.1f;
+    acc += lw[h] * (sine * uv + namp * nv[h]);
   }
   src[(long long)b * src_bstride + j] = tanhf(acc);
 }
@@ -212,46 +233,69 @@ static void ensure_tables() {
 }
 void hift_init_tables() { ensure_tables(); }
 
-__global__ void source_stft_kernel(const float* __restrict__ src, long long src_bstride, const int* __restrict__ lens, int len_all,
-                                   float* __restrict__ out, int F_alloc) {
+// One block = 256 consecutive frames of one utterance: the 1036 source samples they cover are staged in shared memory
+// with coalesced loads (reflect indexing only matters for the first / last block), every thread computes the 18 outputs of
+// its frame into a shared [256][18] tile, and the tile -- one contiguous 18 KB span of the channels-last output -- is
+// written back with coalesced 16-byte stores.  HBM traffic = the algorithmic 4 B read + 18 B written per sample.
+__global__ void __launch_bounds__(256) source_stft_kernel(const float* __restrict__ src, long long src_bstride,
+                                                          const int* __restrict__ lens, int len_all, float* __restrict__ out,
+                                                          int F_alloc) {
+  __shared__ float xs[4 * 256 + 16];
+  __shared__ __align__(16) float os[256 * 18];
   const int b = blockIdx.y;
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= F_alloc) return;
-  const int len = lens ? lens[b] : len_all;  // mel frames
+  const int f0 = blockIdx.x * 256;
+  const int nf = min(256, F_alloc - f0);        // frames of this block that exist in the output tensor
+  const int len = lens ? lens[b] : len_all;     // mel frames
   const int L = len * 480;
   const int F = L / 4 + 1;
-  float* o = out + ((long long)b * F_alloc + f) * 18;
-  if (f >= F) {
+  float* ob = out + ((long long)b * F_alloc + f0) * 18;
+  if (f0 < F) {
+    const float* sb = src + (long long)b * src_bstride;
+    const int m0 = 4 * f0 - 8;
+    for (int e = threadIdx.x; e < 4 * 256 + 12; e += 256) {
+      int m = m0 + e;
+      if (m < 0) m = -m;
+      if (m >= L) m = 2 * (L - 1) - m;
+      xs[e] = (m >= 0 && m < L) ? sb[m] : 0.f;
+    }
+  }
+  __syncthreads();
+  const int f = f0 + threadIdx.x;
+  float* o = os + threadIdx.x * 18;
+  if (f < F) {
+    float x[16];
+#pragma unroll
+    for (int n = 0; n < 16; n++) x[n] = xs[4 * threadIdx.x + n] * c_hann16[n];
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      float re = 0.f, im = 0.f;
+#pragma unroll
+      for (int n = 0; n < 16; n++) {
+        const int idx = (k * n) & 15;
+        re += x[n] * c_cos16[idx];
+        im -= x[n] * c_sin16[idx];
+      }
+      o[k] = re;
+      o[9 + k] = im;
+    }
+  } else {
 #pragma unroll
     for (int k = 0; k < 18; k++) o[k] = 0.f;
-    return;
   }
-  float x[16];
-  const float* sb = src + (long long)b * src_bstride;
-#pragma unroll
-  for (int n = 0; n < 16; n++) {
-    int m = 4 * f + n - 8;
-    if (m < 0) m = -m;
-    if (m >= L) m = 2 * (L - 1) - m;
-    x[n] = sb[m] * c_hann16[n];
-  }
-#pragma unroll
-  for (int k = 0; k < 9; k++) {
-    float re = 0.f, im = 0.f;
-#pragma unroll
-    for (int n = 0; n < 16; n++) {
-      const int idx = (k * n) & 15;
-      re += x[n] * c_cos16[idx];
-      im -= x[n] * c_sin16[idx];
-    }
-    o[k] = re;
-    o[9 + k] = im;
+  __syncthreads();
+  const int nflt = nf * 18;
+  if ((reinterpret_cast<uintptr_t>(ob) & 15) == 0 && (nflt & 3) == 0) {
+    float4* o4 = reinterpret_cast<float4*>(ob);
+    const float4* s4 = reinterpret_cast<const float4*>(os);
+    for (int e = threadIdx.x; e < nflt / 4; e += 256) o4[e] = s4[e];
+  } else {
+    for (int e = threadIdx.x; e < nflt; e += 256) ob[e] = os[e];
   }
 }
 void launch_source_stft(const float* src, long long src_bstride, const int* lens, int len_all, float* out, int F_alloc, int B,
                         cudaStream_t st) {
   ensure_tables();
-  source_stft_kernel<<<dim3((F_alloc + 127) / 128, B), 128, 0, st>>>(src, src_bstride, lens, len_all, out, F_alloc);
+  source_stft_kernel<<<dim3((F_alloc + 255) / 256, B), 256, 0, st>>>(src, src_bstride, lens, len_all, out, F_alloc);
   CV2_LAUNCH_CHECK();
 }
 
@@ -347,7 +391,8 @@ void launch_reflect_row0(float* x, int B, int T_alloc, int C, cudaStream_t st) {
 // trim 8 samples per side, clamp to +-0.99.  One pass: 18 B read + 4 B written per output sample... per hop.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp, int F_alloc, int ld, const int* __restrict__ lens,
-                                                    int len_all, float* __restrict__ wav, long long wav_bstride) {
+                                                    int len_all, float* __restrict__ wav, long long wav_bstride,
+                                                    short* __restrict__ pcm) {
   __shared__ float Xre[260][9];
   __shared__ float Xim[260][9];
   const int b = blockIdx.y;
@@ -355,17 +400,29 @@ __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp
   const int F = len * 120 + 1;
   const int q0 = blockIdx.x * 256;          // first hop of this block; hop q covers samples n = 4q..4q+3
   if (q0 >= F - 1) return;
-  // frames q0-1 .. q0+257
+  // frames q0-1 .. q0+257; a frame's 18 fp32 values are 72 contiguous bytes (8-byte aligned when ld is even)
   for (int e = threadIdx.x; e < 259; e += 256) {
     const int f = q0 - 1 + e;
     if (f >= 0 && f < F) {
       const float* c = cp + ((long long)b * F_alloc + f) * ld;
+      float cv[18];
+      if ((ld & 1) == 0 && (reinterpret_cast<uintptr_t>(cp) & 7) == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          const float2 t2 = __ldg(reinterpret_cast<const float2*>(c) + k);
+          cv[2 * k] = t2.x;
+          cv[2 * k + 1] = t2.y;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 18; k++) cv[k] = c[k];
+      }
 #pragma unroll
       for (int k = 0; k < 9; k++) {
-        const float mag = fminf(expf(c[k]), 100.f);
-        const float ph = sinf(c[9 + k]);
+        const float mag = fminf(__expf(cv[k]), 100.f);
+        const float ph = sinf(cv[9 + k]);      // |ph| <= 1: the fast sincos below is exact to 2^-21 there
         float sn, cs;
-        sincosf(ph, &sn, &cs);
+        __sincosf(ph, &sn, &cs);
         Xre[e][k] = mag * cs;
         Xim[e][k] = mag * sn;
       }
@@ -407,12 +464,20 @@ __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp
   o.z = fminf(fmaxf(y[2] / env[2], -0.99f), 0.99f);
   o.w = fminf(fmaxf(y[3] / env[3], -0.99f), 0.99f);
   *reinterpret_cast<float4*>(wav + (long long)b * wav_bstride + 4 * (long long)q) = o;
+  if (pcm) {   // the servers' wire format: (speech * 2**15).astype(int16), i.e. truncation toward zero (fastapi/server.py:42)
+    short4 s4;
+    s4.x = (short)__float2int_rz(o.x * 32768.f);
+    s4.y = (short)__float2int_rz(o.y * 32768.f);
+    s4.z = (short)__float2int_rz(o.z * 32768.f);
+    s4.w = (short)__float2int_rz(o.w * 32768.f);
+    *reinterpret_cast<short4*>(pcm + (long long)b * wav_bstride + 4 * (long long)q) = s4;
+  }
 }
 void launch_istft(const float* cp, int F_alloc, int ld, const int* lens, int len_all, float* wav, long long wav_bstride, int B,
-                  int max_len, cudaStream_t st) {
+                  int max_len, cudaStream_t st, short* pcm) {
   ensure_tables();
   const int hops = max_len * 120;
-  istft_kernel<<<dim3((hops + 255) / 256, B), 256, 0, st>>>(cp, F_alloc, ld, lens, len_all, wav, wav_bstride);
+  istft_kernel<<<dim3((hops + 255) / 256, B), 256, 0, st>>>(cp, F_alloc, ld, lens, len_all, wav, wav_bstride, pcm);
   CV2_LAUNCH_CHECK();
 }
 

@@ -12,7 +12,8 @@ void hift_init_tables();
 void launch_source_stft(const float* src, long long src_bstride, const int* lens, int len_all, float* out, int F_alloc, int B, cudaStream_t st);
 void launch_source_down(const float* stft, int F_alloc, const float* w, const float* bias, int k, int stride, int pad, int C, const int* lens, int len_all, int frames_per_len, int frames_add, float* out32, __half* out16, const float* alpha, int B, int T_alloc, cudaStream_t st);
 void launch_reflect_row0(float* x, int B, int T_alloc, int C, cudaStream_t st);
-void launch_istft(const float* cp, int F_alloc, int ld, const int* lens, int len_all, float* wav, long long wav_bstride, int B, int max_len, cudaStream_t st);
+void launch_istft(const float* cp, int F_alloc, int ld, const int* lens, int len_all, float* wav, long long wav_bstride, int B, int max_len, cudaStream_t st,
+                  short* pcm = nullptr);   // optional int16 PCM copy of the waveform (same layout)
 void launch_crossfade(float* speech, const float* old_tail, const double* window, int n, cudaStream_t st);
 
 }  // namespace cv2

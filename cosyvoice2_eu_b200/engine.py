@@ -247,9 +247,10 @@ class B200HiFT:
         self.loaded = True
 
     @torch.inference_mode()
-    def inference(self, speech_feat, cache_source=torch.zeros(1, 1, 0), noise=None, lens=None, return_f0=False):
+    def inference(self, speech_feat, cache_source=torch.zeros(1, 1, 0), noise=None, lens=None, return_f0=False, return_pcm16=False):
         """speech_feat f32 [B,80,T]; cache_source [B,1,n]; noise (parity mode) [B,480T,9] replaces the reference's
-        torch.randn_like draw (generator.py:334).  Returns (speech [B,480T], source [B,1,480T])."""
+        torch.randn_like draw (generator.py:334).  Returns (speech [B,480T], source [B,1,480T]) (+ f0 [B,T]) (+ int16 PCM
+        [B,480T] = the servers' `(speech * 2**15).astype(np.int16)`, written by the iSTFT kernel)."""
         dev = self.device
         mel = speech_feat.to(dev, torch.float32).contiguous()
         B, _, T = mel.shape
@@ -268,12 +269,16 @@ class B200HiFT:
             raise _lib.Cv2Error(self.eng.lib.cv2_last_error().decode())
         ws = self.eng.workspace(("hift", B, T), n)
         self._seed += 1
-        _lib.check(self.eng.lib.cv2_hift_forward(self.eng.h, _stream(), _lib.ptr(mel), T, _lib.ptr(ln), _lib.ptr(cs), cache_len,
-                                                 _lib.ptr(nz), self._seed, _lib.ptr(speech), _lib.ptr(source), _lib.ptr(f0), B,
-                                                 _lib.ptr(ws), ws.numel()))
+        pcm = torch.zeros(B, 480 * T, dtype=torch.int16, device=dev) if return_pcm16 else None
+        _lib.check(self.eng.lib.cv2_hift_forward_pcm16(self.eng.h, _stream(), _lib.ptr(mel), T, _lib.ptr(ln), _lib.ptr(cs), cache_len,
+                                                       _lib.ptr(nz), self._seed, _lib.ptr(speech), _lib.ptr(source), _lib.ptr(f0),
+                                                       _lib.ptr(pcm), B, _lib.ptr(ws), ws.numel()))
+        out = (speech, source)
         if return_f0:
-            return speech, source, f0
-        return speech, source
+            out = out + (f0,)
+        if return_pcm16:
+            out = out + (pcm,)
+        return out
 
 
 class B200Token2Wav:

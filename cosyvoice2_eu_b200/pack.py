@@ -17,6 +17,7 @@ import math
 import torch
 
 OP_DTYPE = torch.float16
+CFG_RATE = 0.7   # inference_cfg_rate (cosyvoice2.yaml:75); the engine falls back to the unfused update for any other rate
 
 
 def _conv_w(w, cin_pad=None):
@@ -129,6 +130,11 @@ def pack_flow(sd):
     o["est.final.ln_b"] = _f32(sd[e + "final_block.block.2.bias"])
     o["est.proj.w"] = _lin_w(sd[e + "final_proj.weight"][:, :, 0])
     o["est.proj.b"] = _f32(sd[e + "final_proj.bias"])
+    # CFG combine folded into the projection (flow_matching.py:116: dphi = (1+r) v_cond - r v_uncond, r = inference_cfg_rate):
+    # K-concatenated [(1+r) W | -r W] over the (cond, uncond) pair of rows; the bias is unchanged ((1+r) b - r b = b)
+    w = sd[e + "final_proj.weight"][:, :, 0].float()
+    o["est.proj_cfg.w"] = _lin_w(torch.cat([(1.0 + CFG_RATE) * w, -CFG_RATE * w], 1))
+    o["est.proj_cfg.b"] = _f32(sd[e + "final_proj.bias"])
     return o
 
 

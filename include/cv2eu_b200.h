@@ -45,6 +45,9 @@ long long cv2_engine_last_launches(cv2_engine* e);
 /* optional device-resident seed of the in-kernel NSF noise generator (read at kernel run time, so a captured CUDA graph
  * draws fresh noise on every replay); NULL restores the by-value `seed` argument of cv2_hift_forward */
 int cv2_engine_set_seed_ptr(cv2_engine* e, const unsigned long long* seed_dev);
+/* engine switches (tests / A-B measurements): "fuse_euler" (CFG combine + Euler update inside final_proj, default 1),
+ * "fuse_ffn" (FF1+GELU+FF2 in one kernel, default 1) */
+int cv2_engine_set_option(cv2_engine* e, const char* name, int value);
 int cv2_engine_set_profiling(cv2_engine* e, int on);
 int cv2_engine_read_profile(cv2_engine* e, double* ms_per_family, long long* launches_per_family, int n_families);
 
@@ -81,6 +84,13 @@ size_t cv2_hift_workspace_bytes(cv2_engine* e, int B, int mel_T);
 int cv2_hift_forward(cv2_engine* e, void* stream, const float* mel, int mel_T, const int32_t* lens, const float* cache_source,
                      int cache_len, const float* noise, unsigned long long seed, float* speech, float* source, float* f0_out,
                      int B, void* workspace, size_t workspace_bytes);
+
+/* Same, plus the servers' wire format fused into the iSTFT epilogue: pcm16 [B,480*mel_T] int16 = (speech * 2**15) truncated
+ * toward zero, bit-exact with `(tts_speech.numpy() * (2 ** 15)).astype(np.int16)` (runtime/python/fastapi/server.py:42,
+ * runtime/python/grpc/server.py:68). */
+int cv2_hift_forward_pcm16(cv2_engine* e, void* stream, const float* mel, int mel_T, const int32_t* lens, const float* cache_source,
+                           int cache_len, const float* noise, unsigned long long seed, float* speech, float* source, float* f0_out,
+                           int16_t* pcm16, int B, void* workspace, size_t workspace_bytes);
 
 /* ---- streaming glue: fade_in_out (cosyvoice/utils/common.py:142-150) on the device.  window: [2n] f64 device. ---- */
 int cv2_crossfade(void* stream, float* speech, const float* old_tail, const double* window, int n);

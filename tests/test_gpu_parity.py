@@ -240,3 +240,38 @@ def test_streaming_batched_sessions_equal_single_sessions(engine, golden):
         for a, b in zip(got[si], solo[si]):
             assert a.shape == b.shape
             assert snr_db(b.numpy(), a.numpy()) > 60
+
+
+def test_pcm16_epilogue_bit_exact(engine, golden):
+    """int16 PCM written by the iSTFT kernel == the servers' `(speech * 2**15).astype(np.int16)`
+    (runtime/python/fastapi/server.py:42) -- integer output, bit-exact."""
+    hift = engine[1]
+    g = golden("tiny")
+    noise = T(weights.make_nsf_noise(g["mel"].shape[2] * 480, int(g["seed"])))
+    speech, _, pcm = hift.inference(T(g["mel"]), noise=noise, return_pcm16=True)
+    want = (speech.cpu().numpy() * (2 ** 15)).astype(np.int16)
+    assert pcm.dtype == torch.int16 and tuple(pcm.shape) == tuple(speech.shape)
+    assert np.array_equal(pcm.cpu().numpy(), want)
+    assert int(np.abs(want).max()) > 30000          # the fixture reaches the +-0.99 clamp
+
+
+def test_fused_euler_matches_separate_kernel(engine, golden, monkeypatch):
+    """CFG combine + Euler update inside final_proj's epilogue (one K-concatenated GEMM over the cond/uncond pair)
+    vs the separate euler_pack kernel: same mel within fp16-operand rounding of the projection."""
+    import ctypes as C
+    flow = engine[0]
+    g = golden("tiny")
+    u = _utt(g)
+    args = ([u["token"][0]], [u["prompt_token"][0]], [u["prompt_feat"][0]], [u["embedding"][0]])
+    mel_fused = flow.inference_batch(*args)[0].cpu().numpy()
+    lib = flow.eng.lib
+    lib.cv2_engine_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    assert lib.cv2_engine_set_option(flow.eng.h, b"fuse_euler", 0) == 0
+    try:
+        mel_sep = flow.inference_batch(*args)[0].cpu().numpy()
+    finally:
+        lib.cv2_engine_set_option(flow.eng.h, b"fuse_euler", 1)
+    d = np.abs(mel_fused - mel_sep).max()
+    print("fused vs separate Euler update: max-abs mel diff", d)
+    assert d < 3e-3
+    assert np.abs(mel_fused - g["mel"]).max() <= MEL_TOL and np.abs(mel_sep - g["mel"]).max() <= MEL_TOL

@@ -50,7 +50,7 @@ def test_pack_names_cover_state_dict(fixture_weights):
     fs, hs = fixture_weights
     pf, ph = pack.pack_flow(fs), pack.pack_hift(hs)
     assert pf["est.res.0.c1.w"].shape == (256, 3 * 320) and pf["est.res.13.c1.w"].shape == (256, 3 * 512)
-    assert pf["est.tfm.5.2.qkv.w"].shape == (1536, 256) and pf["enc.layers.3.qkv.w"].shape == (1536, 512)
+    assert pf["est.tfm.5.2.qkv.w"].shape == (1536, 256) and pf["enc.layers.3.qkv.w"].shape == (2048, 512)   # (q+u) | (q+v) | k | v
     assert ph["hift.ups.0.w"].shape == (8 * 256, 2 * 512) and ph["hift.ups.1.w"].shape == (5 * 128, 3 * 256)
     assert ph["hift.ups.2.w"].shape == (3 * 64, 3 * 128) and ph["hift.conv_pre.w"].shape == (512, 7 * 128)
     assert ph["f0.c0.w"].shape == (3, 80, 512) and ph["hift.sd.0.w"].shape == (30, 18, 256)
