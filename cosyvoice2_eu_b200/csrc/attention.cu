@@ -670,7 +670,7 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         l *= alpha;
       }
       // pass 2: probabilities; P chunk c (16 columns) lands on S columns [16c, 16c+16), all consumed by then
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 2; c++) {
         tmem_ld32(lane_addr + k9TmemS + c * 32, sa);
@@ -681,20 +681,22 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (kbase + c * 32 + i >= kv_lim) sa[i] = 0xff800000u;
         }
         uint32_t pk[16];
+        const float2 sc2 = make_float2(LOG2E, LOG2E), nm2 = make_float2(-mref, -mref);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float e0 = fast_exp2(fmaf(__uint_as_float(sa[i]), LOG2E, -mref));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(sa[i + 1]), LOG2E, -mref));
-          const float e2 = fast_exp2(fmaf(__uint_as_float(sa[i + 2]), LOG2E, -mref));
-          const float e3 = fast_exp2(fmaf(__uint_as_float(sa[i + 3]), LOG2E, -mref));
-          l0 += e0; l1 += e1; l2 += e2; l3 += e3;
-          __half2 h0 = __floats2half2_rn(e0, e1), h1 = __floats2half2_rn(e2, e3);
+        for (int i = 0; i < 32; i += 4) {   // packed fp32 pairs: one FFMA2 / FADD2 per two logits
+          const float2 x01 = ffma2(make_float2(__uint_as_float(sa[i]), __uint_as_float(sa[i + 1])), sc2, nm2);
+          const float2 x23 = ffma2(make_float2(__uint_as_float(sa[i + 2]), __uint_as_float(sa[i + 3])), sc2, nm2);
+          const float2 e01 = make_float2(fast_exp2(x01.x), fast_exp2(x01.y));
+          const float2 e23 = make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
+          la = fadd2(la, e01);
+          lb = fadd2(lb, e23);
+          __half2 h0 = __floats2half2_rn(e01.x, e01.y), h1 = __floats2half2_rn(e23.x, e23.y);
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h0);
           pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
         }
         tmem_st16(lane_addr + k9TmemS + c * 16, pk);
       }
-      l += (l0 + l1) + (l2 + l3);
+      l += (la.x + la.y) + (lb.x + lb.y);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full);

@@ -26,6 +26,16 @@ __device__ __forceinline__ float fast_gelu_erf(float x) {
   const float e = fast_exp2(fmaf(-g, z, -1.f));
   return fmaf(-fabsf(x), e, fmaxf(x, 0.f));
 }
+// the same GELU on a packed pair: polynomial and scaling on FFMA2 / FMUL2 (half the FMA-pipe issue slots)
+__device__ __forceinline__ float2 fast_gelu_erf2(float2 x) {
+  const float2 xc = fmul2(x, make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+  const float2 z = make_float2(fminf(fabsf(xc.x), 4.0f), fminf(fabsf(xc.y), 4.0f));
+  float2 h = ffma2(make_float2(0.0192909595f, 0.0192909595f), z, make_float2(-0.136979282f, -0.136979282f));   // h = -g
+  h = ffma2(h, z, make_float2(-0.923393071f, -0.923393071f));
+  h = ffma2(h, z, make_float2(-1.6273005f, -1.6273005f));
+  const float2 t = ffma2(h, z, make_float2(-1.f, -1.f));
+  return make_float2(fmaf(-fabsf(x.x), fast_exp2(t.x), fmaxf(x.x, 0.f)), fmaf(-fabsf(x.y), fast_exp2(t.y), fmaxf(x.y, 0.f)));
+}
 __device__ __forceinline__ float fast_silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_snake(float x, float a) {
   const float s = __sinf(x * a);

@@ -222,10 +222,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
         // of a lane quarter must all hold their accumulator slice in registers before any of them writes
         asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
 #pragma unroll
-        for (int i = 0; i < 32; i++) bv[i] = fast_gelu_erf(__uint_as_float(raw[i]) + bv[i]);
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          __half2 h2 = __floats2half2_rn(bv[i], bv[i + 1]);
+        for (int i = 0; i < 32; i += 2) {   // bias + GELU on packed fp32 pairs, straight to 16-bit pairs
+          const float2 g2 = fast_gelu_erf2(fadd2(make_float2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1])),
+                                                 make_float2(bv[i], bv[i + 1])));
+          __half2 h2 = __floats2half2_rn(g2.x, g2.y);
           raw[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
         }
         tmem_st16(lane_addr + kAcc1 + b * 128 + part * 16, raw);
