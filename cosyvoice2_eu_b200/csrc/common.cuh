@@ -97,6 +97,11 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// L2 prefetch of a contiguous global span (no data movement into the SM): hides HBM latency of a later epilogue read
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ------------------------------------------------------------------------------------------

@@ -11,12 +11,15 @@
 namespace cv2 {
 
 static const int kHalo = 32;
+// The estimator is causal end to end (CausalConv1d taps -2..0, attention masked by length), so no row >= len is ever read by a
+// valid row: its tiles need no halo.  (The encoder looks 3 tokens ahead and the vocoder's same-pad convs up to 25 frames.)
+static const int kEstHalo = 0;
 
-static GemmParams base_params(const int* lens) {
+static GemmParams base_params(const int* lens, int halo = kHalo) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.lens = lens;
-  p.halo = kHalo;
+  p.halo = halo;
   p.out_scale = 1.f;
   return p;
 }
@@ -86,13 +89,13 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
     }
     // res_conv (1x1) -> R32
     {
-      GemmParams p = base_params(lens);
+      GemmParams p = base_params(lens, kEstHalo);
       p.out32 = b.R32; p.out32_ld = 256;
       e.gemm(st, cur, S, T, cur_c, cur_ld, e.W(rp + ".res"), 256, 1, tap1, p, dry);
     }
     // block1: causal conv k3 -> LN -> Mish -> + time vector -> C16
     {
-      GemmParams p = base_params(lens);
+      GemmParams p = base_params(lens, kEstHalo);
       LN ln = e.ln(rp + ".ln1");
       p.ln = 1; p.ln_g = ln.g; p.ln_b = ln.b; p.ln_eps = 1e-5f;
       p.act = ACT_MISH;
@@ -102,7 +105,7 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
     }
     // block2: conv -> LN -> Mish -> mask -> + R32 -> X32 ; emit LN(norm1 of tfm 0) -> H16
     {
-      GemmParams p = base_params(lens);
+      GemmParams p = base_params(lens, kEstHalo);
       LN ln = e.ln(rp + ".ln2");
       p.ln = 1; p.ln_g = ln.g; p.ln_b = ln.b; p.ln_eps = 1e-5f;
       p.act = ACT_MISH;
@@ -115,7 +118,7 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
     for (int j = 0; j < 4; j++) {
       const std::string tp = "est.tfm." + std::to_string(r) + "." + std::to_string(j);
       {  // q,k,v (no bias); q pre-scaled by 1/sqrt(64)
-        GemmParams p = base_params(lens);
+        GemmParams p = base_params(lens, kEstHalo);
         p.q = b.Q16; p.k = b.K16; p.vt = b.VT16; p.heads = 8; p.q_scale = 0.125f;
         e.gemm(st, b.H16, S, T, 256, 256, e.W(tp + ".qkv"), 256, 1, tap1, p, dry);
       }
@@ -123,7 +126,7 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
         AttnParams ap;
         memset(&ap, 0, sizeof(ap));
         ap.q = b.Q16; ap.k = b.K16; ap.vt = b.VT16; ap.out = b.ATT16;
-        ap.lens = lens; ap.S = S; ap.heads = 8; ap.T_alloc = T; ap.chunk = streaming ? 50 : 0; ap.halo = kHalo;
+        ap.lens = lens; ap.S = S; ap.heads = 8; ap.T_alloc = T; ap.chunk = streaming ? 50 : 0; ap.halo = kEstHalo;
         e.launches++;
         if (!dry) {
           e.prof_begin(st, Engine::F_FLASH_ATTN);
@@ -132,7 +135,7 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
         }
       }
       {  // out-proj + bias + residual ; emit LN(norm3)
-        GemmParams p = base_params(lens);
+        GemmParams p = base_params(lens, kEstHalo);
         p.res = b.X32; p.res_ld = 256;
         p.out32 = b.X32; p.out32_ld = 256;
         p.emit[0] = emit_ln(b.H16, 256, e.ln(tp + ".ln3"), 1e-5f);
@@ -141,7 +144,7 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
       if (e.fuse_ffn) {  // FF1 -> GELU -> FF2 -> + residual -> next pre-norm / masked block output, one kernel
         FfnParams fp;
         memset(&fp, 0, sizeof(fp));
-        fp.lens = lens; fp.halo = kHalo; fp.x32 = b.X32;
+        fp.lens = lens; fp.halo = kEstHalo; fp.x32 = b.X32;
         if (j < 3) {
           fp.emit_ln = emit_ln(b.H16, 256, e.ln("est.tfm." + std::to_string(r) + "." + std::to_string(j + 1) + ".ln1"), 1e-5f);
         } else if (r == 0) {
@@ -156,13 +159,13 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
         continue;
       }
       {  // FF1 + exact GELU
-        GemmParams p = base_params(lens);
+        GemmParams p = base_params(lens, kEstHalo);
         p.act = ACT_GELU;
         p.emit[0] = emit_plain(b.F16, 1024);
         e.gemm(st, b.H16, S, T, 256, 256, e.W(tp + ".ff1"), 256, 1, tap1, p, dry);
       }
       {  // FF2 + bias + residual ; emit next pre-norm or the (masked) block output
-        GemmParams p = base_params(lens);
+        GemmParams p = base_params(lens, kEstHalo);
         p.res = b.X32; p.res_ld = 256;
         p.out32 = b.X32; p.out32_ld = 256;
         if (j < 3) {
@@ -179,7 +182,7 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
       }
     }
     if (r == 0) {  // down_blocks.0.2 : CausalConv1d(256,256,3) on x*mask
-      GemmParams p = base_params(lens);
+      GemmParams p = base_params(lens, kEstHalo);
       p.emit[0] = emit_plain(b.N16, 256);
       e.gemm(st, b.M16, S, T, 256, 256, e.W("est.down_conv"), 256, 3, causal3, p, dry);
       cur = b.N16; cur_c = 256; cur_ld = 256;
@@ -188,12 +191,12 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
     }
   }
   {  // up_blocks.0.2
-    GemmParams p = base_params(lens);
+    GemmParams p = base_params(lens, kEstHalo);
     p.emit[0] = emit_plain(b.N16, 256);
     e.gemm(st, b.M16, S, T, 256, 256, e.W("est.up_conv"), 256, 3, causal3, p, dry);
   }
   {  // final_block
-    GemmParams p = base_params(lens);
+    GemmParams p = base_params(lens, kEstHalo);
     LN ln = e.ln("est.final.ln");
     p.ln = 1; p.ln_g = ln.g; p.ln_b = ln.b; p.ln_eps = 1e-5f;
     p.act = ACT_MISH;
@@ -202,7 +205,7 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
   }
   if (ef) {  // final_proj + CFG combine + Euler update, one launch over the B utterances
     static const int pair[2] = {0, 0};
-    GemmParams p = base_params(lens);
+    GemmParams p = base_params(lens, kEstHalo);
     p.tap_seq[1] = ef->B;
     p.S_map = S;
     p.mask_pre_res = 1;
@@ -214,7 +217,7 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
     return;
   }
   {  // final_proj (1x1, 256 -> 80), output * mask
-    GemmParams p = base_params(lens);
+    GemmParams p = base_params(lens, kEstHalo);
     p.mask_pre_res = 1;
     p.out32 = b.V32; p.out32_ld = 80;
     e.gemm(st, b.M16, S, T, 256, 256, e.W("est.proj"), 128, 1, tap1, p, dry);
@@ -251,7 +254,7 @@ size_t estimator_forward(Engine& e, cudaStream_t st, const EstArgs& a, Arena& ws
   float* tres = est_time(e, st, ws, a.t, S, dry);
   e.launches += 6;
   if (!dry) launch_mask_to_lens(a.mask, a.T, lens, S, st);
-  e.make_tile_list(st, ws, lens, S, T, kHalo, dry);
+  e.make_tile_list(st, ws, lens, S, T, kEstHalo, dry);
   if (!dry) {
     launch_nct_to_ntc(a.x, (long long)80 * a.T, a.T, nullptr, xin, lens, 0, S, T, 80, 320, 0, 0, st);
     launch_nct_to_ntc(a.mu, (long long)80 * a.T, a.T, nullptr, xin, lens, 0, S, T, 80, 320, 80, 0, st);
@@ -348,7 +351,7 @@ size_t flow_forward(Engine& e, cudaStream_t st, const FlowArgs& a, Arena& ws) {
   }
   e.tile_lists.clear();
   e.make_tile_list(st, ws, len_ctx, B, Tt, kHalo, dry, len_enc);        // token-rate encoder GEMMs
-  e.make_tile_list(st, ws, len_mel, 2 * B, Tm, kHalo, dry);             // estimator (both CFG rows)
+  e.make_tile_list(st, ws, len_mel, 2 * B, Tm, kEstHalo, dry);          // estimator (both CFG rows)
   e.make_tile_list(st, ws, len_mel, B, Tm, kHalo, dry);                 // mel-rate encoder GEMMs
 
   // ---- encoder, token rate ----
