@@ -71,7 +71,7 @@ def algorithmic_flops(n_tokens, n_prompt=N_PROMPT):
         f["gemm_tap<128>"] += tg * (8 * 720896.0 + 40 * 336 * 16384.0)
         f["gemm_tap<64>"] += tg * (40 * 114688.0 + 120 * 384 * 4096.0 + 120 * 16128.0)
         f["source_down"] += tg * (8 * 276480.0 + 40 * 27648.0 + 120 * 2304.0)
-        f["f0_conv_f32"] += tg * 6.54e6
+        f["gemm_tap<256>" if os.environ.get("CV2_F0_SPLIT") else "f0_conv_f32"] += tg * 6.54e6   # F0 predictor
     return f
 
 

@@ -66,12 +66,44 @@ size_t hift_forward(Engine& e, cudaStream_t st, const HiftArgs& a, Arena& ws) {
   float* F0 = ws.get<float>((size_t)B * Ta[0]);
   float* PH = ws.get<float>((size_t)B * Ta[0] * 9);
   float* STFT = ws.get<float>((size_t)B * Ta[3] * 18);
+  // F0 predictor (f0_predictor.py:55-58).  Its output drives a phase accumulator (0.1 Hz decorrelates the harmonics within
+  // a second), so plain 16-bit operands are not enough -- but fp32 SIMT was 2 % of the step.  Split precision on the tensor
+  // cores: every activation and weight is carried as hi + lo 16-bit halves and the conv is hi*W_hi + lo*W_hi + hi*W_lo in one
+  // tap GEMM (6 "taps": the 3 conv taps over [hi | lo] against [W_hi | W_hi], then again against [W_lo | 0]); products are
+  // exact to ~2^-21, accumulation is fp32.
+  const bool f0_split = e.f0_split && e.tensors.count("f0.t0.w");
+  __half* MS16 = f0_split ? ws.get<__half>((size_t)B * Ta[0] * 256) : nullptr;
+  __half* FS[2] = {nullptr, nullptr};
+  if (f0_split)
+    for (int i = 0; i < 2; i++) FS[i] = ws.get<__half>((size_t)B * Ta[0] * 1024);
   e.launches += 1 + 5 + 1 + 2 + 1;
-  if (!dry) {
-    launch_nct_to_ntc(a.mel, (long long)80 * a.mel_T, a.mel_T, MEL32, MEL16, lens[0], 0, B, Ta[0], 80, 80, 0, 0, st);
-    const float* cur = MEL32;
-    int cin = 80;
+  if (!dry) launch_nct_to_ntc(a.mel, (long long)80 * a.mel_T, a.mel_T, MEL32, MEL16, lens[0], 0, B, Ta[0], 80, 80, 0, 0, st);
+  if (f0_split) {
+    static const int taps6[6] = {-1, 0, 1, -1, 0, 1};
+    e.launches++;
+    if (!dry) launch_split16(MEL32, 80, MS16, 256, 128, (long long)B * Ta[0], st);
+    const __half* cur = MS16;
+    int kc = 256;
     for (int l = 0; l < 5; l++) {
+      GemmParams p = hp(lens[0]);
+      p.act = ACT_ELU;
+      p.acc_scale = 1.f / 256.f;   // pack.py stores these weights x256 so that W_lo is a normal fp16 number
+      if (l < 4) {
+        p.emit[0] = mk_emit(EMIT_PLAIN, FS[l & 1], 1024);
+        p.emit[1] = mk_emit(EMIT_LO, FS[l & 1], 1024);
+        p.emit[1].col_off = 512;
+      } else {
+        p.out32 = FA; p.out32_ld = 512;
+      }
+      e.gemm(st, cur, B, Ta[0], kc, kc, e.W("f0.t" + std::to_string(l)), 256, 6, taps6, p, dry);
+      cur = FS[l & 1];
+      kc = 1024;
+    }
+  }
+  if (!dry) {
+    const float* cur = f0_split ? FA : MEL32;
+    int cin = 80;
+    for (int l = 0; l < 5 && !f0_split; l++) {
       const std::string n = "f0.c" + std::to_string(l);
       float* out = (l & 1) ? FB : FA;
       e.prof_begin(st, Engine::F_F0_CONV);

@@ -249,6 +249,23 @@ void launch_euler_pack(float* x, const float* v, const float* noise, int noise_s
   CV2_LAUNCH_CHECK();
 }
 
+// fp32 channels-last [rows, C] -> two-term 16-bit split [rows, ld]: hi = fp16(x) at columns [0, C), lo = fp16(x - hi) at
+// [lo_off, lo_off + C); the columns in between stay zero (K padding of the split-precision GEMM)
+__global__ void split16_kernel(const float* __restrict__ x, int C, __half* __restrict__ out, int ld, int lo_off, long long rows) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const long long r = i / C;
+  const int c = (int)(i - r * C);
+  const float v = x[i];
+  const __half h = __float2half_rn(v);
+  out[r * ld + c] = h;
+  out[r * ld + lo_off + c] = __float2half_rn(v - __half2float(h));
+}
+void launch_split16(const float* x, int C, __half* out, int ld, int lo_off, long long rows, cudaStream_t st) {
+  split16_kernel<<<(unsigned)((rows * C + 255) / 256), 256, 0, st>>>(x, C, out, ld, lo_off, rows);
+  CV2_LAUNCH_CHECK();
+}
+
 // ---- generic layout movers ------------------------------------------------------------------------------
 // fp32 NCT [B, C, T] (reference layout) -> fp32 / 16-bit channels-last [B, T_alloc, ldc]
 __global__ void nct_to_ntc_kernel(const float* __restrict__ in, long long in_bstride, int in_T, float* __restrict__ out32,

@@ -22,4 +22,6 @@ void launch_mask_to_lens(const float* mask, int T, int* lens, int S, cudaStream_
 void launch_bcast_rows16(const float* v, int C, __half* out, int ldc, int col_off, const int* lens, int S, int T_alloc, cudaStream_t st);
 void launch_f32_to_f16(const float* in, __half* out, long long n, cudaStream_t st);
 
+void launch_split16(const float* x, int C, __half* out, int ld, int lo_off, long long rows, cudaStream_t st);
+
 }  // namespace cv2

@@ -270,6 +270,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]);
+        if (Cfg::SCALE < 0 && p.acc_scale != 0.f) {   // generic kernel only
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] *= p.acc_scale;
+        }
         if (has_bias) {
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] += tmp[i];
@@ -373,6 +377,9 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           } else if (ek == EMIT_LRELU) {
 #pragma unroll
             for (int i = 0; i < 32; i++) w[i] = v[i] > 0.f ? v[i] : v[i] * em.f;
+          } else if (ek == EMIT_LO) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) w[i] = v[i] - __half2float(__float2half_rn(v[i]));
           } else {
 #pragma unroll
             for (int i = 0; i < 32; i++) w[i] = v[i];
@@ -557,6 +564,10 @@ static bool cfg_matches(const GemmParams& p) {
 
 template <int BN>
 static void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  if (p.acc_scale != 0.f && p.acc_scale != 1.f) {   // only the generic epilogue implements the accumulator pre-scale
+    launch_cfg<BN, EpiGeneric>(tmA, tmB, p, stream);
+    return;
+  }
 #define TRY(CFG)                                  \
   if (cfg_matches<CFG>(p)) {                      \
     launch_cfg<BN, CFG>(tmA, tmB, p, stream);     \
@@ -573,6 +584,7 @@ static void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
 
 // index of the epilogue specialisation launch_gemm_tap would pick (profiling labels only)
 int gemm_tap_spec(int bn, const GemmParams& p) {
+  if (p.acc_scale != 0.f && p.acc_scale != 1.f) return 0;
   int i = 1;
 #define TRYS(CFG)                 \
   if (cfg_matches<CFG>(p)) return i; \
@@ -595,6 +607,7 @@ void launch_gemm_tap(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, con
   for (int e = 0; e < 3; e++) wants_row |= (p.emit[e].kind == EMIT_LN);
   CV2_CHECK(!wants_row || p.N <= bn, "gemm_tap: LayerNorm epilogue needs the full row in one tile (N=%d, BN=%d)", p.N, bn);
   CV2_CHECK(!p.ln || p.bias, "gemm_tap: LayerNorm epilogue expects a bias");
+  CV2_CHECK(!p.ln || p.acc_scale == 0.f || p.acc_scale == 1.f, "gemm_tap: acc_scale is not implemented together with the LayerNorm epilogue");
   CV2_CHECK(!p.q || (p.N == (p.q2 ? 4 : 3) * p.heads * 64), "gemm_tap: qkv split needs N == 3*heads*64 (4*heads*64 with q2)");
   switch (bn) {
     case 64: launch_bn<64>(tmA, tmB, p, stream); break;

@@ -16,7 +16,8 @@
 namespace cv2 {
 
 enum Act { ACT_NONE = 0, ACT_MISH = 1, ACT_GELU = 2, ACT_SILU = 3, ACT_ELU = 4, ACT_LRELU = 5, ACT_SNAKE = 6 };
-enum EmitKind { EMIT_NONE = 0, EMIT_PLAIN = 1, EMIT_SNAKE = 2, EMIT_LN = 3, EMIT_LRELU = 4 };
+enum EmitKind { EMIT_NONE = 0, EMIT_PLAIN = 1, EMIT_SNAKE = 2, EMIT_LN = 3, EMIT_LRELU = 4,
+                EMIT_LO = 5 };   // v - fp16(v): the low half of a two-term 16-bit split (with EMIT_PLAIN as the high half)
 
 struct Emit {
   __half* ptr;         // 16-bit output [S, T_alloc, ld]; rows >= len are written as 0
@@ -42,7 +43,9 @@ struct GemmParams {
   int halo;            // a tile is computed iff t0 < len + halo
   const int* tile_list;   // optional compact list of active (s, t0) pairs (device), balanced round-robin over CTAs
   const int* tile_count;  // number of pairs in tile_list (device)
-  // epilogue program: v = acc + bias -> LN -> act -> + rowvec[s] -> (mask) -> + res + res2 -> *scale (+= out32) -> store / emit
+  // epilogue program: v = acc * acc_scale + bias -> LN -> act -> + rowvec[s] -> (mask) -> + res + res2 -> *scale (+= out32) -> store / emit
+  float acc_scale;     // 0 / 1: none; else the raw accumulator is multiplied by it before the bias (weights stored pre-scaled to
+                       // keep a 16-bit low half out of the subnormal range); generic epilogue only, not with ln
   const float* bias;   // [N] or null
   int ln;
   const float* ln_g;

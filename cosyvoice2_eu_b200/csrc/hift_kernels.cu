@@ -9,70 +9,107 @@ namespace cv2 {
 
 // ---------------------------------------------------------------------------------------------------------
 // fp32 conv1d k=3 pad=1 + ELU, channels-last (ConvRNNF0Predictor.condnet, f0_predictor.py:31-52).
-// Classic 64x64 register-tiled SGEMM over K = 3*Cin; rows beyond len read as 0 (tensor-edge semantics).
-// w: [3][Cin][Cout] (Cout contiguous), weight-norm folded on the host.
+// fp32 on purpose (see engine.h: f0_split): 128 x 128 register-tiled SGEMM over K = 3*Cin, 8 x 8 outputs per thread as
+// packed FFMA2 (one issue slot per two FMAs), BK = 16, global loads of step k+1 in flight while step k is computed
+// (double-buffered shared tiles); rows beyond len read as 0 (tensor-edge semantics).
+// w: [3][Cin][Cout] (Cout contiguous), weight-norm folded on the host.  Cin % 16 == 0, Cout % 128 == 0.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) conv3_elu_f32_kernel(const float* __restrict__ x, int Cin, const float* __restrict__ w,
-                                                            const float* __restrict__ bias, float* __restrict__ y, int Cout,
-                                                            const int* __restrict__ lens, int len_all, int T_alloc) {
-  __shared__ float xs[16][64 + 4];   // [k][t]
-  __shared__ float ws[16][64 + 4];   // [k][co]
-  const int b = blockIdx.z, t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+static constexpr int kF0BM = 128, kF0BN = 128, kF0BK = 16, kF0LD = 132;
+__global__ void __launch_bounds__(256, 1) conv3_elu_f32_kernel(const float* __restrict__ x, int Cin, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, float* __restrict__ y, int Cout,
+                                                               const int* __restrict__ lens, int len_all, int T_alloc) {
+  __shared__ __align__(16) float xs[2][kF0BK][kF0LD];   // [k][t]
+  __shared__ __align__(16) float ws[2][kF0BK][kF0LD];   // [k][co]
+  const int b = blockIdx.z, t0 = blockIdx.x * kF0BM, c0 = blockIdx.y * kF0BN;
   const int len = lens ? lens[b] : len_all;
   if (t0 >= len) return;
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 4x4 outputs each
-  float acc[4][4];
+  const int tx = tid & 15, ty = tid >> 4;   // 16 x 16 threads; rows {4ty..4ty+3, 64+4ty..}, cols {4tx..4tx+3, 64+4tx..}
+  float2 acc[8][4];                          // [row][col pair]
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < 8; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.f, 0.f);
   const float* xb = x + (long long)b * T_alloc * Cin;
-  for (int tap = 0; tap < 3; tap++) {
-    for (int k0 = 0; k0 < Cin; k0 += 16) {
-      // x tile: 64 t x 16 k
-      for (int e = tid; e < 64 * 16; e += 256) {
-        const int tt = e >> 4, kk = e & 15;
-        const int ts = t0 + tt + tap - 1;
-        float v = 0.f;
-        if (ts >= 0 && ts < len && k0 + kk < Cin) v = xb[(long long)ts * Cin + k0 + kk];
-        xs[kk][tt] = v;
-      }
-      for (int e = tid; e < 16 * 64; e += 256) {
-        const int kk = e >> 6, cc = e & 63;
-        float v = 0.f;
-        if (k0 + kk < Cin) v = w[((long long)tap * Cin + k0 + kk) * Cout + c0 + cc];
-        ws[kk][cc] = v;
-      }
-      __syncthreads();
+  const int ksteps = Cin / kF0BK, nsteps = 3 * ksteps;
+  // this thread's slice of a step's global loads: x: rows xr, xr + 64, 4 consecutive k (float4); w: rows wk, wk + 8, float4 of co
+  const int xr = tid >> 2, xk = (tid & 3) * 4;
+  const int wk = tid >> 5, wc = (tid & 31) * 4;
+  float4 gx[2], gw[2];
+  auto gload = [&](int step) {
+    const int tap = step / ksteps, k0 = (step - tap * ksteps) * kF0BK;
 #pragma unroll
-      for (int kk = 0; kk < 16; kk++) {
-        const float4 a = *reinterpret_cast<const float4*>(&xs[kk][ty * 4]);
-        const float4 bb = *reinterpret_cast<const float4*>(&ws[kk][tx * 4]);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+    for (int h = 0; h < 2; h++) {
+      const int ts = t0 + xr + 64 * h + tap - 1;
+      gx[h] = (ts >= 0 && ts < len) ? __ldg(reinterpret_cast<const float4*>(xb + (long long)ts * Cin + k0 + xk)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      gw[h] = __ldg(reinterpret_cast<const float4*>(w + ((long long)tap * Cin + k0 + wk + 8 * h) * Cout + c0 + wc));
+    }
+  };
+  auto sstore = [&](int buf) {
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+    for (int h = 0; h < 2; h++) {
+      xs[buf][xk + 0][xr + 64 * h] = gx[h].x;
+      xs[buf][xk + 1][xr + 64 * h] = gx[h].y;
+      xs[buf][xk + 2][xr + 64 * h] = gx[h].z;
+      xs[buf][xk + 3][xr + 64 * h] = gx[h].w;
+      *reinterpret_cast<float4*>(&ws[buf][wk + 8 * h][wc]) = gw[h];
+    }
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int step = 0; step < nsteps; step++) {
+    const int buf = step & 1;
+    if (step + 1 < nsteps) gload(step + 1);
 #pragma unroll
-          for (int j = 0; j < 4; j++) acc[i][j] += av[i] * bv[j];
+    for (int kk = 0; kk < kF0BK; kk++) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&xs[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&xs[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&ws[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&ws[buf][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float2 bp[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float2 aa = make_float2(av[i], av[i]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = ffma2(aa, bp[j], acc[i][j]);
       }
+    }
+    if (step + 1 < nsteps) {
+      sstore(buf ^ 1);     // the other buffer was last read in step-1, which every thread left at the barrier below
       __syncthreads();
     }
   }
+  float bv[8];
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int t = t0 + ty * 4 + i;
+  for (int j = 0; j < 4; j++) {
+    bv[j] = bias[c0 + tx * 4 + j];
+    bv[4 + j] = bias[c0 + 64 + tx * 4 + j];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int t = t0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (t >= T_alloc) continue;
-    float4 o;
-    float* ov = reinterpret_cast<float*>(&o);
-#pragma unroll
-    for (int j = 0; j < 4; j++) ov[j] = (t < len) ? elu_f(acc[i][j] + bias[c0 + tx * 4 + j]) : 0.f;
-    *reinterpret_cast<float4*>(y + ((long long)b * T_alloc + t) * Cout + c0 + tx * 4) = o;
+    const bool valid = t < len;
+    float4 o0, o1;
+    o0.x = valid ? elu_f(acc[i][0].x + bv[0]) : 0.f;
+    o0.y = valid ? elu_f(acc[i][0].y + bv[1]) : 0.f;
+    o0.z = valid ? elu_f(acc[i][1].x + bv[2]) : 0.f;
+    o0.w = valid ? elu_f(acc[i][1].y + bv[3]) : 0.f;
+    o1.x = valid ? elu_f(acc[i][2].x + bv[4]) : 0.f;
+    o1.y = valid ? elu_f(acc[i][2].y + bv[5]) : 0.f;
+    o1.z = valid ? elu_f(acc[i][3].x + bv[6]) : 0.f;
+    o1.w = valid ? elu_f(acc[i][3].y + bv[7]) : 0.f;
+    float* yr = y + ((long long)b * T_alloc + t) * Cout + c0;
+    *reinterpret_cast<float4*>(yr + tx * 4) = o0;
+    *reinterpret_cast<float4*>(yr + 64 + tx * 4) = o1;
   }
 }
 void launch_conv3_elu_f32(const float* x, int Cin, const float* w, const float* bias, float* y, int Cout, const int* lens,
                           int len_all, int B, int T_alloc, cudaStream_t st) {
-  dim3 grid((T_alloc + 63) / 64, Cout / 64, B);
+  CV2_CHECK(Cin % kF0BK == 0 && Cout % kF0BN == 0, "conv3_elu_f32: Cin %d / Cout %d not tileable", Cin, Cout);
+  dim3 grid((T_alloc + kF0BM - 1) / kF0BM, Cout / kF0BN, B);
   conv3_elu_f32_kernel<<<grid, 256, 0, st>>>(x, Cin, w, bias, y, Cout, lens, len_all, T_alloc);
   CV2_LAUNCH_CHECK();
 }

@@ -17,6 +17,7 @@ import math
 import torch
 
 OP_DTYPE = torch.float16
+F0_WSCALE = 256.0   # F0-predictor split weights are stored x256 (engine: acc_scale = 1/256)
 CFG_RATE = 0.7   # inference_cfg_rate (cosyvoice2.yaml:75); the engine falls back to the unfused update for any other rate
 
 
@@ -162,6 +163,22 @@ def pack_hift(sd):
         w = fold_weight_norm(sd, f"f0_predictor.condnet.{idx}")
         o[f"f0.c{l}.w"] = _f32(w.permute(2, 1, 0))                     # [3][Cin][512]
         o[f"f0.c{l}.b"] = _f32(sd[f"f0_predictor.condnet.{idx}.bias"])
+    # split-precision tensor-core form of the same convs: W = W_hi + W_lo (16-bit halves); per output channel the K axis is
+    # 6 "taps" x [A_hi | A_lo] blocks: taps 0-2 hold [W_hi | W_hi] (conv taps -1, 0, +1), taps 3-5 hold [W_lo | 0]
+    for l, idx in enumerate((0, 2, 4, 6, 8)):
+        w = fold_weight_norm(sd, f"f0_predictor.condnet.{idx}")          # [512, Cin, 3]
+        cout, cin, k = w.shape
+        cp = (cin + 127) // 128 * 128 if cin < 512 else cin
+        w = w * F0_WSCALE                                                 # keeps W_lo (~2^-11 |W|) a normal fp16 number
+        hi = w.to(OP_DTYPE).float()
+        lo = (w - hi).to(OP_DTYPE).float()
+        blk = torch.zeros(cout, 6, 2, cp, dtype=torch.float32)
+        for j in range(3):
+            blk[:, j, 0, :cin] = hi[:, :, j]
+            blk[:, j, 1, :cin] = hi[:, :, j]
+            blk[:, 3 + j, 0, :cin] = lo[:, :, j]
+        o[f"f0.t{l}.w"] = blk.reshape(cout, 6 * 2 * cp).to(OP_DTYPE).contiguous()
+        o[f"f0.t{l}.b"] = _f32(sd[f"f0_predictor.condnet.{idx}.bias"])
     o["f0.cls.w"] = _f32(sd["f0_predictor.classifier.weight"].reshape(-1))
     o["f0.cls.b"] = _f32(sd["f0_predictor.classifier.bias"].reshape(-1))
     o["hift.src.lw"] = _f32(sd["m_source.l_linear.weight"].reshape(-1))
