@@ -227,14 +227,18 @@ def main():
         speech, _ = hift.inference(mel, lens=mel_lens_d)
         return speech, n1 + eng.last_launches()
 
+    gather_buf = {}
+
     def step_e2e():
         speech, lens = t2w.token2wav_batch(tokens, ptoks, pfeats, embs)
-        out = speech.cpu()                                   # D2H of the step's result
-        if world > 1:                                        # final gather of (lengths, padded audio) on rank 0
-            lens_g = [torch.empty_like(lens.to(dev)) for _ in range(world)] if rank == 0 else None
-            dist.gather(lens.to(dev), lens_g, dst=0)
-            aud_g = [torch.empty_like(speech) for _ in range(world)] if rank == 0 else None
-            dist.gather(speech, aud_g, dst=0)
+        if world > 1:                                        # final gather of (lengths, padded audio) on rank 0 (the only collective)
+            lens_d = lens.to(dev, non_blocking=True)
+            if rank == 0 and not gather_buf:                 # receive buffers are allocated once, not per step
+                gather_buf["lens"] = [torch.empty_like(lens_d) for _ in range(world)]
+                gather_buf["aud"] = [torch.empty_like(speech) for _ in range(world)]
+            dist.gather(lens_d, gather_buf.get("lens"), dst=0)
+            dist.gather(speech, gather_buf.get("aud"), dst=0)
+        out = speech.cpu()                                   # D2H of the step's result (also drains the gather on rank 0)
         return out
 
     def barrier():

@@ -533,7 +533,9 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   const int t0 = blockIdx.x * 128;
   const int h = blockIdx.y;
-  const int s = blockIdx.z;
+  // blocks are dispatched in blockIdx.z order: walking the sequences backwards puts the longest ones first when the caller
+  // sorted the batch by ascending length (length bucketing), so the last wave is made of short CTAs
+  const int s = p.reverse_seq ? p.S - 1 - (int)blockIdx.z : (int)blockIdx.z;
   const int len = p.lens ? p.lens[s] : p.len_all;
   if (t0 >= len + p.halo) return;
   const int sh = s * p.heads + h;

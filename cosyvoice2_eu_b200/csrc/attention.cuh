@@ -15,6 +15,7 @@ struct AttnParams {
   int S, heads, T_alloc;
   int chunk;         // 0: every valid key visible; >0: key j visible to query i iff j < (i/chunk+1)*chunk
   int halo;
+  int reverse_seq;   // dispatch sequences S-1 .. 0 (longest first for an ascending length-sorted batch)
 };
 void launch_flash_attn(const AttnParams& p, cudaStream_t stream);
 

@@ -1,4 +1,5 @@
 // extern "C" surface of libcv2eu_b200.so (declared in include/cv2eu_b200.h).
+#include <stdlib.h>
 #include "../../include/cv2eu_b200.h"
 
 #include "attention.cuh"
@@ -310,6 +311,7 @@ int cv2_op_flash_attn(void* stream, const void* q, const void* k, const void* vt
   p.q = static_cast<const __half*>(q); p.k = static_cast<const __half*>(k); p.vt = static_cast<const __half*>(vt);
   p.out = static_cast<__half*>(out); p.lens = lens; p.len_all = len_all; p.S = S; p.heads = heads; p.T_alloc = T_alloc;
   p.chunk = chunk; p.halo = 32;
+  p.reverse_seq = getenv("CV2_ATTN_FWD_ORDER") == nullptr;
   launch_flash_attn(p, (cudaStream_t)stream);
   CV2_API_END
 }

@@ -127,6 +127,7 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
         memset(&ap, 0, sizeof(ap));
         ap.q = b.Q16; ap.k = b.K16; ap.vt = b.VT16; ap.out = b.ATT16;
         ap.lens = lens; ap.S = S; ap.heads = 8; ap.T_alloc = T; ap.chunk = streaming ? 50 : 0; ap.halo = kEstHalo;
+        ap.reverse_seq = 1;
         e.launches++;
         if (!dry) {
           e.prof_begin(st, Engine::F_FLASH_ATTN);
