@@ -275,3 +275,45 @@ def test_fused_euler_matches_separate_kernel(engine, golden, monkeypatch):
     print("fused vs separate Euler update: max-abs mel diff", d)
     assert d < 3e-3
     assert np.abs(mel_fused - g["mel"]).max() <= MEL_TOL and np.abs(mel_sep - g["mel"]).max() <= MEL_TOL
+
+
+def test_cfg3_full_size_properties(engine):
+    """BASELINE.json configs[2] at full size (64 utterances, U[4,20] s, length-sorted ragged batch): size-independent properties.
+    (i) integer bookkeeping is exact (mel frames = 2 * tokens, samples = 480 * frames), (ii) padding of every output is exactly
+    zero, (iii) the batched result of sampled utterances (shortest, median, longest) equals their B=1 result, (iv) the int16 PCM of
+    the batch equals the NumPy conversion, (v) everything is finite and clamped to +-0.99."""
+    flow, hift, t2w = engine
+    rng = np.random.Generator(np.random.Philox(key=1000))
+    n_tokens = sorted(int(round(25 * d)) for d in rng.uniform(4.0, 20.0, size=64))
+    utts = [_utt(dict(n_tok=n, n_prompt=75, seed=100 + i)) for i, n in enumerate(n_tokens)]
+    args = ([u["token"][0] for u in utts], [u["prompt_token"][0] for u in utts], [u["prompt_feat"][0] for u in utts],
+            [u["embedding"][0] for u in utts])
+    mel, mel_lens = flow.inference_batch(*args)
+    assert mel_lens.tolist() == [2 * n for n in n_tokens]
+    assert bool(torch.isfinite(mel).all())
+    Tm = mel.shape[2]
+    pick = [0, 31, 63]
+    noise = torch.zeros(64, 480 * Tm, 9)
+    for i in pick:
+        nz = T(weights.make_nsf_noise(int(mel_lens[i]) * 480, 700 + i))
+        noise[i, :nz.shape[1]] = nz[0]
+    speech, source, pcm = hift.inference(mel, noise=noise, lens=mel_lens, return_pcm16=True)
+    sp = speech.cpu().numpy()
+    assert np.isfinite(sp).all() and np.abs(sp).max() <= 0.99 + 1e-7
+    assert np.array_equal(pcm.cpu().numpy(), (sp * (2 ** 15)).astype(np.int16))
+    for i in range(64):
+        n = int(mel_lens[i])
+        if n < Tm:
+            assert float(mel[i, :, n:].abs().max()) == 0.0
+            assert float(np.abs(sp[i, 480 * n:]).max()) == 0.0
+    for i in pick:
+        u = utts[i]
+        n = int(mel_lens[i])
+        mel_1, _ = flow.inference(u["token"], None, u["prompt_token"], None, u["prompt_feat"], None, u["embedding"], False, True)
+        d = float((mel[i, :, :n] - mel_1[0]).abs().max())
+        wav_1, _ = hift.inference(mel_1, noise=noise[i:i + 1, :480 * n])
+        s = snr_db(wav_1[0].cpu().numpy(), sp[i, :480 * n])
+        print("cfg3 utt", i, "tokens", n_tokens[i], "batch-vs-single mel", d, "wav SNR", s)
+        assert tuple(mel_1.shape) == (1, 80, n)
+        assert d < 1e-4
+        assert s > 60
