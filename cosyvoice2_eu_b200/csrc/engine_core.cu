@@ -112,6 +112,8 @@ void Engine::gemm(cudaStream_t st, const __half* A, int S, int T_alloc, int Kc, 
     }
   }
   const int bi = bn == 64 ? 0 : (bn == 128 ? 1 : 2);
+  // 2-CTA clusters with TMA multicast of the weight operand: big launches only (>= 2 row tiles per SM pair), compact list required
+  if (cluster_mc && bn == 256 && p.tile_list && (long long)S * (T_alloc / 128) >= 148) p.tmB_half = &wmap(w, 128);
   const CUtensorMap& tb = wmap(w, bn);
   const CUtensorMap& ta = amap(A, p.S_map > 0 ? p.S_map : S, T_alloc, Kc, ldA);
   prof_begin(st, bn == 256 ? F_COUNT + gemm_tap_spec(bn, p) : bi);

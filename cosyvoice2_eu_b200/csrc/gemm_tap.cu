@@ -37,19 +37,29 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 struct TileCoord {
   int n0, t0, s, len;
 };
-// tile -> coordinates; returns false when the tile lies entirely in the padding
-__device__ __forceinline__ bool tile_coord(const GemmParams& p, int tile, int n_tiles, int t_tiles, int BN, TileCoord& c) {
-  const int n = tile % n_tiles;
-  const int rest = tile / n_tiles;
+// Work unit u -> coordinates.  A unit is one n tile x CS row tiles (CS = cluster size): CTA `rank` of the cluster takes row tile
+// rg * CS + rank, all CTAs of the cluster share the n tile (= the multicast weight operand).  Returns false when the tile lies
+// entirely in the padding (CS = 1, no compact list); `valid` is false for the filler tile of an odd tail (computed, not stored).
+template <int CS>
+__device__ __forceinline__ bool tile_coord(const GemmParams& p, int u, int n_tiles, int t_tiles, int BN, int rank, int row_count,
+                                           TileCoord& c, bool& valid) {
+  const int n = u % n_tiles;
+  const int rg = u / n_tiles;
+  valid = true;
   if (p.tile_list) {   // compacted list: every entry is active
-    c.s = __ldg(p.tile_list + 2 * rest);
-    c.t0 = __ldg(p.tile_list + 2 * rest + 1);
+    int idx = rg * CS + rank;
+    if (CS > 1 && idx >= row_count) {
+      valid = false;
+      idx = 0;
+    }
+    c.s = __ldg(p.tile_list + 2 * idx);
+    c.t0 = __ldg(p.tile_list + 2 * idx + 1);
     c.n0 = n * BN;
     c.len = p.lens ? __ldg(p.lens + c.s) : p.len_all;
     return true;
   }
-  const int tt = rest % t_tiles;
-  c.s = rest / t_tiles;
+  const int tt = rg % t_tiles;
+  c.s = rg / t_tiles;
   c.n0 = n * BN;
   c.t0 = tt * kTileM;
   c.len = p.lens ? __ldg(p.lens + c.s) : p.len_all;
@@ -69,7 +79,10 @@ struct EpiCfg {
 using EpiGeneric = EpiCfg<-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1>;
 #define CFGB(field, rt) (Cfg::field < 0 ? (rt) : (Cfg::field != 0))
 
-template <int BN, class Cfg>
+// CS > 1: CTAs of a thread-block cluster work on CS row tiles of the same n tile and share the weight operand: each CTA loads
+// BN / CS rows of every B k-block and TMA-multicasts them into all CS shared memories (L2 -> SM traffic of B divided by CS; the
+// K = 256 estimator GEMMs are L2-bandwidth bound).  A stage is recycled when the MMAs of all CS CTAs have read it (multicast commit).
+template <int BN, class Cfg, int CS>
 __global__ void __launch_bounds__(GemmSmem<BN>::kThreads, 1)
 gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using SM = GemmSmem<BN>;
@@ -89,7 +102,11 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_it = p.ntaps * p.kb_per_tap;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int t_tiles = p.T_alloc / kTileM;
-  const int total_tiles = p.tile_list ? n_tiles * __ldg(p.tile_count) : n_tiles * t_tiles * p.S;
+  const int row_count = p.tile_list ? __ldg(p.tile_count) : t_tiles * p.S;
+  const int total_tiles = n_tiles * ((row_count + CS - 1) / CS);    // work units
+  const int rank = CS > 1 ? (int)cluster_ctarank() : 0;
+  const int unit0 = blockIdx.x / CS, unit_step = gridDim.x / CS;
+  constexpr uint16_t kMcMask = (uint16_t)((1u << CS) - 1);
   constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // 128 / 256 / 512
 
   if (warp == 0 && lane == 0) {
@@ -97,7 +114,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < kStages; i++) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CS);
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(&tmem_full[i], 1);
@@ -107,7 +124,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  if (CS > 1) cluster_sync();   // peers multicast into this CTA's stages and arrive on its barriers: all must be initialised
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -115,9 +133,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       // ------------------------------- TMA producer -------------------------------
       int kit = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         TileCoord c;
-        if (!tile_coord(p, tile, n_tiles, t_tiles, BN, c)) continue;
+        bool tvalid;
+        if (!tile_coord<CS>(p, tile, n_tiles, t_tiles, BN, rank, row_count, c, tvalid)) continue;
         for (int it = 0; it < num_it; it++, kit++) {
           const int st = kit % kStages;
           const uint32_t ph = (kit / kStages) & 1;
@@ -128,7 +147,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           uint8_t* b_dst = a_dst + kABytes;
           mbar_expect_tx(&full_bar[st], SM::kStageBytes);
           tma_load_3d(a_dst, &tmA, &full_bar[st], kb * kKBlock, c.t0 + p.tap_off[tap], c.s + p.tap_seq[tap]);
-          tma_load_2d(b_dst, &tmB, &full_bar[st], it * kKBlock, c.n0);
+          if (CS == 1) tma_load_2d(b_dst, &tmB, &full_bar[st], it * kKBlock, c.n0);
+          else tma_load_2d_mc(b_dst + rank * (BN / CS) * 128, &tmB, &full_bar[st], it * kKBlock, c.n0 + rank * (BN / CS), kMcMask);
         }
       }
     }
@@ -137,9 +157,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // ------------------------------- MMA issuer ---------------------------------
       constexpr uint32_t idesc = umma_idesc_f16(kTileM, BN, 0);
       int kit = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         TileCoord c;
-        if (!tile_coord(p, tile, n_tiles, t_tiles, BN, c)) continue;
+        bool tvalid;
+        if (!tile_coord<CS>(p, tile, n_tiles, t_tiles, BN, rank, row_count, c, tvalid)) continue;
         const int acc = lt & 1;
         mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
@@ -155,7 +176,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < kKBlock / 16; k++)
             umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[st]);
+          if (CS == 1) umma_commit(&empty_bar[st]);
+          else umma_commit_mc(&empty_bar[st], kMcMask);
         }
         umma_commit(&tmem_full[acc]);
         lt++;
@@ -198,9 +220,19 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool has_qkv = CFGB(QKV, p.q != nullptr);
 
     int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = unit0; tile < total_tiles; tile += unit_step) {
       TileCoord c;
-      if (!tile_coord(p, tile, n_tiles, t_tiles, BN, c)) continue;
+      bool tvalid;
+      if (!tile_coord<CS>(p, tile, n_tiles, t_tiles, BN, rank, row_count, c, tvalid)) continue;
+      if (CS > 1 && !tvalid) {   // filler tile of an odd tail: drain the accumulator, store nothing
+        mbar_wait(&tmem_full[lt & 1], (lt >> 1) & 1);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[lt & 1]);
+        lt++;
+        continue;
+      }
       const int acc = lt & 1;
       const int t = c.t0 + r;
       const bool valid = t < c.len;
@@ -484,7 +516,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CS > 1) cluster_sync();   // no CTA may exit while a peer can still multicast into it or arrive on its barriers
+  else __syncthreads();
   if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
@@ -518,22 +551,64 @@ void launch_build_tile_list(const int* lens, int S, int T_alloc, int halo, int* 
 
 static int g_num_sms = 0;
 
-template <int BN, class Cfg>
-static void launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+template <int BN, class Cfg, int CS>
+static void launch_cfg_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   static bool configured = false;
-  if (!configured) {
-    CV2_CUDA(cudaFuncSetAttribute(gemm_tap_kernel<BN, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
-    configured = true;
-  }
+  static int max_clusters = 0;
   if (g_num_sms == 0) {
     int dev = 0;
     CV2_CUDA(cudaGetDevice(&dev));
     CV2_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int total = ((p.N + BN - 1) / BN) * (p.T_alloc / kTileM) * p.S;
-  const int grid = total < g_num_sms ? total : g_num_sms;   // persistent: one CTA per SM
-  gemm_tap_kernel<BN, Cfg><<<grid, GemmSmem<BN>::kThreads, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, p);
+  if (!configured) {
+    CV2_CUDA(cudaFuncSetAttribute(gemm_tap_kernel<BN, Cfg, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
+    if (CS > 1) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(g_num_sms / CS * CS);
+      q.blockDim = dim3(GemmSmem<BN>::kThreads);
+      q.dynamicSmemBytes = GemmSmem<BN>::kTotal;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      q.attrs = at;
+      q.numAttrs = 1;
+      CV2_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, gemm_tap_kernel<BN, Cfg, CS>, &q));
+      CV2_CHECK(max_clusters > 0, "gemm_tap: no cluster of %d CTAs fits", CS);
+    }
+    configured = true;
+  }
+  const int rows = (p.T_alloc / kTileM) * p.S;                         // upper bound on row tiles (the list may hold fewer)
+  const int total = ((p.N + BN - 1) / BN) * ((rows + CS - 1) / CS);    // work units
+  if (CS == 1) {
+    const int grid = total < g_num_sms ? total : g_num_sms;   // persistent: one CTA per SM
+    gemm_tap_kernel<BN, Cfg, 1><<<grid, GemmSmem<BN>::kThreads, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, p);
+  } else {
+    const int clusters = total < max_clusters ? total : max_clusters;
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(clusters * CS);
+    q.blockDim = dim3(GemmSmem<BN>::kThreads);
+    q.dynamicSmemBytes = GemmSmem<BN>::kTotal;
+    q.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    q.attrs = at;
+    q.numAttrs = 1;
+    CV2_CUDA(cudaLaunchKernelEx(&q, gemm_tap_kernel<BN, Cfg, CS>, tmA, tmB, p));
+  }
   CV2_LAUNCH_CHECK();
+}
+
+// tmB2: weight map with a {64, BN/2} box for the 2-CTA multicast path (null: single-CTA path)
+template <int BN, class Cfg>
+static void launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  if constexpr (BN == 256) {
+    if (p.tmB_half && p.tile_list) {
+      launch_cfg_cs<BN, Cfg, 2>(tmA, *p.tmB_half, p, stream);
+      return;
+    }
+  }
+  launch_cfg_cs<BN, Cfg, 1>(tmA, tmB, p, stream);
 }
 
 // Specialised epilogues.               ACT       B LN RV MK RS R2 O32 AC FL SC  EMIT0       EMIT1      EMIT2     QKV

@@ -43,6 +43,8 @@ struct GemmParams {
   int halo;            // a tile is computed iff t0 < len + halo
   const int* tile_list;   // optional compact list of active (s, t0) pairs (device), balanced round-robin over CTAs
   const int* tile_count;  // number of pairs in tile_list (device)
+  const CUtensorMap* tmB_half;   // host pointer: weight map with a {64, BN/2} box -> 2-CTA cluster with TMA multicast of the
+                                 // weight operand (BN = 256 and a compact tile list only); null: one CTA per tile
   // epilogue program: v = acc * acc_scale + bias -> LN -> act -> + rowvec[s] -> (mask) -> + res + res2 -> *scale (+= out32) -> store / emit
   float acc_scale;     // 0 / 1: none; else the raw accumulator is multiplied by it before the bias (weights stored pre-scaled to
                        // keep a 16-bit low half out of the subnormal range); generic epilogue only, not with ln
