@@ -87,133 +87,55 @@ __device__ __forceinline__ void store32_f16(__half* __restrict__ p, const float*
   }
 }
 
-// ---- coalesced global I/O for the thread-per-row epilogue ----
-// A warp owns 32 consecutive rows x 32 columns.  Per-thread row segments (16 B pieces 32 rows apart) cost one L1 wavefront
-// per lane; instead the warp moves the 32x32 block with lanes running along the row (4 rows x 128 B per instruction) and
-// transposes it through a private, padded shared-memory staging tile.
-__device__ __forceinline__ void tile_load_f32(const float* __restrict__ g0, long long ld, float* stg, int lane, float* d) {
+// ---- global I/O for the thread-per-row epilogue ----
+// A warp owns 32 consecutive rows x 32 columns and each thread its own row.  Blackwell's 256-bit global accesses
+// (ld/st.global.v8.b32 -> LDG.E.256 / STG.E.256) move one full 32-byte sector per lane per instruction, so the per-thread
+// row segment (128 B of fp32 = 4 instructions, 64 B of 16-bit = 2) is sector-exact without any shared-memory transpose:
+// no staging tile (72 KB in the GEMM kernel, spent on a 4th TMA stage instead), no syncwarp / LDS / STS in the epilogue.
+// (The round-1 kernels used 128-bit pieces 32 rows apart -- half-used sectors -- and then a smem transpose to fix that.)
+// Rows must be 32-byte aligned: ld a multiple of 8 floats / 16 halves, chunk offsets multiples of 32 elements.
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+               "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tile_load_f32(const float* __restrict__ g0, long long ld, float*, int lane, float* d) {
   // g0 -> element (first row of the warp, first column of the chunk)
-  __syncwarp();
+  const float* p = g0 + lane * ld;
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const int rr = 4 * i + (lane >> 3), c4 = (lane & 7) * 4;
-    const float4 f = __ldg(reinterpret_cast<const float4*>(g0 + rr * ld + c4));
-    *reinterpret_cast<float4*>(stg + rr * 36 + c4) = f;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const float4 f = *reinterpret_cast<const float4*>(stg + lane * 36 + i * 4);
-    d[i * 4 + 0] = f.x; d[i * 4 + 1] = f.y; d[i * 4 + 2] = f.z; d[i * 4 + 3] = f.w;
-  }
+  for (int i = 0; i < 4; i++) ldg256(p + i * 8, reinterpret_cast<uint32_t*>(d) + i * 8);
 }
-__device__ __forceinline__ void tile_store_f32(float* __restrict__ g0, long long ld, float* stg, int lane, const float* v) {
-  __syncwarp();
+__device__ __forceinline__ void tile_store_f32(float* __restrict__ g0, long long ld, float*, int lane, const float* v) {
+  float* p = g0 + lane * ld;
 #pragma unroll
-  for (int i = 0; i < 8; i++)
-    *reinterpret_cast<float4*>(stg + lane * 36 + i * 4) = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const int rr = 4 * i + (lane >> 3), c4 = (lane & 7) * 4;
-    *reinterpret_cast<float4*>(g0 + rr * ld + c4) = *reinterpret_cast<const float4*>(stg + rr * 36 + c4);
-  }
+  for (int i = 0; i < 4; i++) stg256(p + i * 8, reinterpret_cast<const uint32_t*>(v) + i * 8);
 }
-__device__ __forceinline__ void tile_store_f16(__half* __restrict__ g0, long long ld, float* stg, int lane, const float* v) {
-  // staging rows of 64 B payload + 16 B pad (20 words)
-  uint32_t* sw = reinterpret_cast<uint32_t*>(stg);
-  __syncwarp();
+__device__ __forceinline__ void tile_store_f16(__half* __restrict__ g0, long long ld, float*, int lane, const float* v) {
+  uint32_t pk[16];
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    __half2 h0 = __floats2half2_rn(v[i * 8 + 0], v[i * 8 + 1]);
-    __half2 h1 = __floats2half2_rn(v[i * 8 + 2], v[i * 8 + 3]);
-    __half2 h2 = __floats2half2_rn(v[i * 8 + 4], v[i * 8 + 5]);
-    __half2 h3 = __floats2half2_rn(v[i * 8 + 6], v[i * 8 + 7]);
-    uint4 u;
-    u.x = *reinterpret_cast<uint32_t*>(&h0);
-    u.y = *reinterpret_cast<uint32_t*>(&h1);
-    u.z = *reinterpret_cast<uint32_t*>(&h2);
-    u.w = *reinterpret_cast<uint32_t*>(&h3);
-    *reinterpret_cast<uint4*>(sw + lane * 20 + i * 4) = u;
+  for (int i = 0; i < 16; i++) {
+    __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    pk[i] = *reinterpret_cast<uint32_t*>(&h);
   }
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int rr = 8 * i + (lane >> 2), pc = lane & 3;
-    *reinterpret_cast<uint4*>(g0 + rr * ld + pc * 8) = *reinterpret_cast<const uint4*>(sw + rr * 20 + pc * 4);
-  }
+  __half* p = g0 + lane * ld;
+  stg256(p, pk);
+  stg256(p + 16, pk + 8);
 }
-
-
-// ---- half-height variants: the same 32-row block moved in two passes of 16 rows through a 16 x 32-float staging tile
-// (2048 B per warp, XOR-swizzled instead of padded: float4 column j of row r lives at column j ^ (r & 7)), for kernels
-// that run 16 epilogue warps and must fit their staging into 32 KB ----
+// (the former half-height staging variants of the FFN kernel are the same direct accesses now)
 __device__ __forceinline__ void tile_load_f32_h16(const float* __restrict__ g0, long long ld, float* stg, int lane, float* d) {
-#pragma unroll
-  for (int h = 0; h < 2; h++) {
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int rr = 4 * i + (lane >> 3), j = lane & 7;
-      const float4 f = __ldg(reinterpret_cast<const float4*>(g0 + (16 * h + rr) * ld + j * 4));
-      *reinterpret_cast<float4*>(stg + rr * 32 + ((j ^ (rr & 7)) << 2)) = f;
-    }
-    __syncwarp();
-    if ((lane >> 4) == h) {
-      const int rr = lane & 15;
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const float4 f = *reinterpret_cast<const float4*>(stg + rr * 32 + ((i ^ (rr & 7)) << 2));
-        d[i * 4 + 0] = f.x; d[i * 4 + 1] = f.y; d[i * 4 + 2] = f.z; d[i * 4 + 3] = f.w;
-      }
-    }
-  }
+  tile_load_f32(g0, ld, stg, lane, d);
 }
 __device__ __forceinline__ void tile_store_f32_h16(float* __restrict__ g0, long long ld, float* stg, int lane, const float* v) {
-#pragma unroll
-  for (int h = 0; h < 2; h++) {
-    __syncwarp();
-    if ((lane >> 4) == h) {
-      const int rr = lane & 15;
-#pragma unroll
-      for (int i = 0; i < 8; i++)
-        *reinterpret_cast<float4*>(stg + rr * 32 + ((i ^ (rr & 7)) << 2)) = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int rr = 4 * i + (lane >> 3), j = lane & 7;
-      *reinterpret_cast<float4*>(g0 + (16 * h + rr) * ld + j * 4) = *reinterpret_cast<const float4*>(stg + rr * 32 + ((j ^ (rr & 7)) << 2));
-    }
-  }
+  tile_store_f32(g0, ld, stg, lane, v);
 }
 __device__ __forceinline__ void tile_store_f16_h16(__half* __restrict__ g0, long long ld, float* stg, int lane, const float* v) {
-  uint32_t* sw = reinterpret_cast<uint32_t*>(stg);   // 16 rows x 20 words (64 B payload + 16 B pad)
-#pragma unroll
-  for (int h = 0; h < 2; h++) {
-    __syncwarp();
-    if ((lane >> 4) == h) {
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        __half2 h0 = __floats2half2_rn(v[i * 8 + 0], v[i * 8 + 1]);
-        __half2 h1 = __floats2half2_rn(v[i * 8 + 2], v[i * 8 + 3]);
-        __half2 h2 = __floats2half2_rn(v[i * 8 + 4], v[i * 8 + 5]);
-        __half2 h3 = __floats2half2_rn(v[i * 8 + 6], v[i * 8 + 7]);
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&h0);
-        u.y = *reinterpret_cast<uint32_t*>(&h1);
-        u.z = *reinterpret_cast<uint32_t*>(&h2);
-        u.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(sw + (lane & 15) * 20 + i * 4) = u;
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-      const int rr = 8 * i + (lane >> 2), pc = lane & 3;
-      *reinterpret_cast<uint4*>(g0 + (16 * h + rr) * ld + pc * 8) = *reinterpret_cast<const uint4*>(sw + rr * 20 + pc * 4);
-    }
-  }
+  tile_store_f16(g0, ld, stg, lane, v);
 }
 
 }  // namespace cv2

@@ -7,7 +7,7 @@
 // 16-bit chunk back into the first 64 columns of the SAME TMEM buffer, where it is the A operand of FF2(c) (tcgen05.mma with
 // a tensor-memory A operand), which accumulates the 256-column output tile in TMEM across the 8 chunks.  No shared-memory
 // hand-off, no generic->async proxy fence, and the hidden chunk is double-buffered with its accumulator.  Buffer reuse needs
-// no barrier: FF1(c+2) is issued behind FF2(c) on the in-order tensor pipe.  Weights stream through a 7-slot TMA ring.
+// no barrier: FF1(c+2) is issued behind FF2(c) on the in-order tensor pipe.  Weights stream through a 9-slot TMA ring.
 //   warp 0: TMA (H tile + weight stream)   warp 1: tcgen05.mma issuer   warps 2-17: epilogue (four per TMEM lane quarter)
 // Saves the [rows,1024] 16-bit round trip through HBM (4 KB/row of the 18 KB/row a transformer block moves) and one launch.
 #include "common.cuh"
@@ -18,14 +18,10 @@
 namespace cv2 {
 
 static constexpr int kHBytes = 4 * 16384;       // [128 x 256] 16-bit, four 64-column swizzle atoms
-static constexpr int kFBytes = 2 * 16384;       // [128 x 128] 16-bit GELU chunk
-static constexpr int kSlots = 7;
-static constexpr int kSlotBytes = 16384;        // one [128 x 64] weight tile
-static constexpr int kOffF = kHBytes;
-static constexpr int kOffW = kOffF + kFBytes;
-static constexpr int kOffStg = kOffF;            // the output epilogue stages through the (then idle) F buffer
+static constexpr int kSlots = 9;                 // the hidden chunk lives in TMEM and the epilogue needs no staging: all the
+static constexpr int kSlotBytes = 16384;        // remaining shared memory is weight ring (one [128 x 64] tile per slot)
+static constexpr int kOffW = kHBytes;
 static constexpr int kEpiW = 16;                 // epilogue warps: four per TMEM lane quarter
-static constexpr int kStgH = 16 * 32;            // swizzled half-height staging tile per warp (floats): 16 x 2 KB = 32 KB
 static constexpr int kOffRed = kOffW + kSlots * kSlotBytes;
 static constexpr int kOffBar = kOffRed + 2 * 4 * 128 * 4;
 static constexpr int kFfnSmem = kOffBar + 256;
@@ -197,7 +193,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
     const int q = warp & 3;
     const int part = ew >> 2;                // 0..3: which quarter of the columns
     const int r = q * 32 + lane;
-    float* stg = reinterpret_cast<float*>(smem + kOffStg) + ew * kStgH;
+    float* stg = nullptr;                    // (epilogue I/O is direct 256-bit global access: no staging tile)
     float* red_c = red;                      // [4][128]
     float* red_d = red + 512;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);

@@ -20,15 +20,16 @@ static constexpr int kABytes = kTileM * kKBlock * 2;     // 16 KB
 template <int BN>
 struct GemmSmem {
   static constexpr int kParts = BN >= 128 ? 4 : 2;        // column parts of a tile = epilogue warps per TMEM lane quarter
-  static constexpr int kEpiWarps = 4 * kParts;            // 16 (8 for BN = 64): enough warps to hide TMEM / smem / MUFU latency
+  static constexpr int kEpiWarps = 4 * kParts;            // 16 (8 for BN = 64): enough warps to hide TMEM / global / MUFU latency
   static constexpr int kThreads = 64 + kEpiWarps * 32;    // + TMA warp + MMA warp
-  static constexpr int kStages = BN == 256 ? 3 : 4;
   static constexpr int kBBytes = BN * kKBlock * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStgOff = kStages * kStageBytes;           // 8 warps x 4608 B
-  static constexpr int kRedOff = kStgOff + kEpiWarps * kStgFloats * 4;   // 4 x [kParts][128] floats for LayerNorm exchanges
+  // the GEMMs of this path are short-K (K = 256..1536) and TMA-latency bound: what matters is bytes in flight.  The epilogue
+  // needs no shared memory (256-bit global accesses), so the ring takes all of it: 192 KB = 4 / 6 / 8 stages.
+  static constexpr int kStages = (192 * 1024) / kStageBytes;
+  static constexpr int kRedOff = kStages * kStageBytes;   // 4 x [kParts][128] floats for LayerNorm exchanges
   static constexpr int kBarOff = kRedOff + 4 * kParts * 128 * 4;
-  static constexpr int kTotal = kBarOff + 256;                    // + barriers
+  static constexpr int kTotal = kBarOff + 512;            // + barriers
 };
 
 template <int NT>
@@ -191,7 +192,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int r = q * 32 + lane;
     constexpr int kHalfCols = BN / kParts;    // 64 / 32 / 32
     constexpr int kChunks = kHalfCols / 32;   // 2 / 1 / 1
-    float* stg = reinterpret_cast<float*>(smem + SM::kStgOff) + ew * kStgFloats;   // this warp's staging tile
+    float* stg = nullptr;                // (epilogue I/O is direct 256-bit global access: no staging tile)
     float* red_a = red;                  // [kParts][128] each
     float* red_b = red + kParts * 128;
     float* red_c = red + 2 * kParts * 128;
