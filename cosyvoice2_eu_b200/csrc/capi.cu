@@ -114,6 +114,12 @@ int cv2_engine_set_option(cv2_engine* h, const char* name, int value) {
   CV2_API_END
 }
 
+int cv2_debug_set_ffn_trace(long long* dev_buf) {
+  CV2_API_BEGIN
+  ffn_set_trace(dev_buf);
+  CV2_API_END
+}
+
 int cv2_engine_set_profiling(cv2_engine* h, int on) {
   CV2_API_BEGIN
   CV2_CHECK(h, "null engine");

@@ -8,7 +8,10 @@
 // a tensor-memory A operand), which accumulates the 256-column output tile in TMEM across the 8 chunks.  No shared-memory
 // hand-off, no generic->async proxy fence, and the hidden chunk is double-buffered with its accumulator.  Buffer reuse needs
 // no barrier: FF1(c+2) is issued behind FF2(c) on the in-order tensor pipe.  Weights stream through a 9-slot TMA ring.
-//   warp 0: TMA (H tile + weight stream)   warp 1: tcgen05.mma issuer   warps 2-17: epilogue (four per TMEM lane quarter)
+//   warps 0-15: epilogue (four per TMEM lane quarter)   warp 16: TMA (H tile + weight stream)   warp 17: tcgen05.mma issuer.
+// The issuing warps carry the HIGHEST warp ids: the scheduler favours high ids, and a single issuing thread that loses
+// arbitration against 16 math-heavy warps paces the tensor pipe (measured with the clock64 trace, profiles/ffn_trace.py:
+// 112-144 cycles per MMA issued instead of 64 when the issuer was warp 1).
 // Saves the [rows,1024] 16-bit round trip through HBM (4 KB/row of the 18 KB/row a transformer block moves) and one launch.
 #include "common.cuh"
 #include "epi_util.cuh"
@@ -18,7 +21,7 @@
 namespace cv2 {
 
 static constexpr int kHBytes = 4 * 16384;       // [128 x 256] 16-bit, four 64-column swizzle atoms
-static constexpr int kSlots = 9;                 // the hidden chunk lives in TMEM and the epilogue needs no staging: all the
+static constexpr int kSlots = 8;                 // the hidden chunk lives in TMEM and the epilogue needs no staging: all the
 static constexpr int kSlotBytes = 16384;        // remaining shared memory is weight ring (one [128 x 64] tile per slot)
 static constexpr int kOffW = kHBytes;
 static constexpr int kEpiW = 16;                 // epilogue warps: four per TMEM lane quarter
@@ -28,6 +31,9 @@ static constexpr int kFfnSmem = kOffBar + 256;
 static constexpr int kFfnThreads = 64 + kEpiW * 32;
 static constexpr uint32_t kAcc1 = 0, kAcc2 = 256;   // TMEM columns: acc1 = 2 x 128, acc2 = 256
 
+__device__ __forceinline__ void ffn_trace(long long* buf, int& idx, int code) {
+  if (buf && idx < 4095) buf[idx++] = (clock64() << 8) | code;
+}
 __device__ __forceinline__ void ffn_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __device__ __forceinline__ bool ffn_tile(const FfnParams& p, int tile, int t_tiles, int& s, int& t0, int& len) {
@@ -74,7 +80,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
   const int t_tiles = p.T_alloc / 128;
   const int total_tiles = p.tile_list ? __ldg(p.tile_count) : t_tiles * p.S;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kEpiW && lane == 0) {
     tma_prefetch_desc(&tmH);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
@@ -94,13 +100,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
     mbar_init(acc2_empty, kEpiW);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == kEpiW + 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kEpiW) {
     if (lane == 0) {
       // ------------------------------- TMA producer -------------------------------
       int lt = 0, wit = 0;
@@ -129,58 +135,92 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
         lt++;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kEpiW + 1) {
     if (lane == 0) {
       // ------------------------------- MMA issuer ---------------------------------
       constexpr uint32_t idesc = umma_idesc_f16(128, 128, 0);
       const uint32_t h_addr = smem_u32(smem);
       int lt = 0, wit = 0, fcnt = 0;
+      long long* tb = blockIdx.x == 0 ? p.trace : nullptr;
+      int ti = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int s, t0, len;
         if (!ffn_tile(p, tile, t_tiles, s, t0, len)) continue;
+        ffn_trace(tb, ti, 1);
         mbar_wait(h_full, lt & 1);
         tc_fence_after();
+        ffn_trace(tb, ti, 2);
         for (int o = 0; o < 16; o++) {
           bool is_ff2;
           int c;
           ffn_op(o, is_ff2, c);
           if (!is_ff2) {
             const int b = c & 1;   // buffer b was last read by FF2(c-2), issued earlier on the same in-order pipe
+            // The tensor-pipe queue is shallow: whatever the issuing thread does between the last MMA of one slot and the first
+            // MMA of the next is a bubble (measured 450 cycles per 4-MMA slot instead of 256, profiles/micro/mma_bubble.cu).  So
+            // the bookkeeping for slot i+1 (full-barrier poll, descriptor arithmetic) is done right after the FIRST MMA of slot
+            // i, while the pipe is busy and the thread would be blocked on issue anyway.
+            int st = wit % kSlots;
+            mbar_wait(&w_full[st], (wit / kSlots) & 1);   // (TMA -> MMA through smem: the mbarrier wait orders it, no tcgen05 fence)
+            uint64_t b_desc = umma_smem_desc_sw128(smem_u32(smem + kOffW + st * kSlotBytes));
             for (int kb = 0; kb < 4; kb++, wit++) {
-              const int st = wit % kSlots;
-              mbar_wait(&w_full[st], (wit / kSlots) & 1);
-              tc_fence_after();
               const uint64_t a_desc = umma_smem_desc_sw128(h_addr + kb * 16384);
-              const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(smem + kOffW + st * kSlotBytes));
+              umma_f16(tmem_base + kAcc1 + b * 128, a_desc, b_desc, idesc, kb != 0);
+              int st_n = st;
+              uint64_t b_next = b_desc;
+              if (kb < 3) {
+                st_n = (wit + 1) % kSlots;
+                mbar_wait(&w_full[st_n], ((wit + 1) / kSlots) & 1);
+                b_next = umma_smem_desc_sw128(smem_u32(smem + kOffW + st_n * kSlotBytes));
+              }
 #pragma unroll
-              for (int k = 0; k < 4; k++)
-                umma_f16(tmem_base + kAcc1 + b * 128, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              for (int k = 1; k < 4; k++)
+                umma_f16(tmem_base + kAcc1 + b * 128, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, 1);
               umma_commit(&w_empty[st]);
+              st = st_n;
+              b_desc = b_next;
             }
             umma_commit(&acc1_full[b]);
+            ffn_trace(tb, ti, 3);
             if (c == 7) umma_commit(h_empty);                  // all FF1 MMAs of this tile issued: H tile may be refilled
           } else {
             if (c == 0) {
               mbar_wait(acc2_empty, (lt & 1) ^ 1);              // previous tile's output epilogue has drained acc2
               tc_fence_after();
             }
+            ffn_trace(tb, ti, 4);
             mbar_wait(f_full, fcnt & 1);                        // GELU chunk c (16-bit) is in TMEM, on top of its accumulator
+            ffn_trace(tb, ti, 5);
             mbar_arrive(f_seen);                                // back-pressure: chunk c+1 may only be signalled after this observation
             tc_fence_after();
             const uint32_t a_tmem = tmem_base + kAcc1 + (c & 1) * 128;
-            for (int i = 0; i < 4; i++, wit++) {
-              const int st = wit % kSlots;
-              const int kb = i >> 1, half = i & 1;
-              mbar_wait(&w_full[st], (wit / kSlots) & 1);
-              tc_fence_after();
-              const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(smem + kOffW + st * kSlotBytes));
+            // W2 tile of a k-block = two adjacent ring slots (output rows 0-127 | 128-255; every op takes 4 slots and kSlots is
+            // even, so the pair never wraps): ONE N = 256 MMA per k-step reads the TMEM A operand once for all 256 outputs
+            constexpr uint32_t idesc256 = umma_idesc_f16(128, 256, 0);
+            int st = wit % kSlots;
+            mbar_wait(&w_full[st], (wit / kSlots) & 1);
+            mbar_wait(&w_full[st + 1], ((wit + 1) / kSlots) & 1);
+            uint64_t b_desc = umma_smem_desc_sw128(smem_u32(smem + kOffW + st * kSlotBytes));
+            for (int kb = 0; kb < 2; kb++, wit += 2) {
+              umma_f16_ts(tmem_base + kAcc2, a_tmem + kb * 32, b_desc, idesc256, (c | kb) != 0);
+              int st_n = st;
+              uint64_t b_next = b_desc;
+              if (kb == 0) {   // next pair's readiness + descriptor while the pipe works on this one
+                st_n = (wit + 2) % kSlots;
+                mbar_wait(&w_full[st_n], ((wit + 2) / kSlots) & 1);
+                mbar_wait(&w_full[st_n + 1], ((wit + 3) / kSlots) & 1);
+                b_next = umma_smem_desc_sw128(smem_u32(smem + kOffW + st_n * kSlotBytes));
+              }
 #pragma unroll
-              for (int k = 0; k < 4; k++)
-                umma_f16_ts(tmem_base + kAcc2 + half * 128, a_tmem + kb * 32 + k * 8, b_desc + (uint64_t)(k * 2), idesc,
-                            (c | kb | k) != 0);
+              for (int k = 1; k < 4; k++)
+                umma_f16_ts(tmem_base + kAcc2, a_tmem + kb * 32 + k * 8, b_desc + (uint64_t)(k * 2), idesc256, 1);
               umma_commit(&w_empty[st]);
+              umma_commit(&w_empty[st + 1]);
+              st = st_n;
+              b_desc = b_next;
             }
             fcnt++;
+            ffn_trace(tb, ti, 6);
             if (c == 7) umma_commit(acc2_full);
           }
         }
@@ -189,7 +229,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
     }
   } else {
     // --------------------------------- epilogue -----------------------------------
-    const int ew = warp - 2;
+    const int ew = warp;
     const int q = warp & 3;
     const int part = ew >> 2;                // 0..3: which quarter of the columns
     const int r = q * 32 + lane;
@@ -198,6 +238,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
     float* red_d = red + 512;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     int lt = 0, use1[2] = {0, 0}, g = 0;
+    long long* tb = (blockIdx.x == 0 && warp == 0 && lane == 0 && p.trace) ? p.trace + 4096 : nullptr;
+    int ti = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int s, t0, len;
       if (!ffn_tile(p, tile, t_tiles, s, t0, len)) continue;
@@ -210,7 +252,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
         const int b = c & 1;
         float bv[32];
         load32(p.b1 + c * 128 + part * 32, bv, true, 32);      // bias first: its latency hides behind the accumulator wait
+        ffn_trace(tb, ti, 10);
         mbar_wait(&acc1_full[b], use1[b] & 1);
+        ffn_trace(tb, ti, 11);
         use1[b]++;
         tc_fence_after();
         uint32_t raw[32];
@@ -219,6 +263,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
         // the 16-bit chunk lands on columns [16*part, 16*part+16) of this buffer = fp32 columns of part/2: the four warps
         // of a lane quarter must all hold their accumulator slice in registers before any of them writes
         asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+        ffn_trace(tb, ti, 12);
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {   // bias + GELU on packed fp32 pairs, straight to 16-bit pairs
           const float2 g2 = fast_gelu_erf2(fadd2(make_float2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1])),
@@ -229,13 +274,17 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
         tmem_st16(lane_addr + kAcc1 + b * 128 + part * 16, raw);
         tmem_st_wait();
         tc_fence_before();
+        ffn_trace(tb, ti, 13);
         if (g > 0) mbar_wait(f_seen, (g - 1) & 1);              // never two unobserved phases of f_full (robust to any warp skew)
         __syncwarp();
         if (lane == 0) mbar_arrive(f_full);
+        ffn_trace(tb, ti, 14);
       }
+      ffn_trace(tb, ti, 20);
       // ---- output tile: + b2 + residual -> X32 ; LayerNorm / plain emits ----
       mbar_wait(acc2_full, lt & 1);
       tc_fence_after();
+      ffn_trace(tb, ti, 21);
       const uint32_t taddr = lane_addr + kAcc2 + part * 64;
       const bool want_ln = p.emit_ln.ptr != nullptr;
       float sum2 = 0.f;
@@ -308,17 +357,23 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc2_empty);
+      ffn_trace(tb, ti, 22);
       lt++;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (warp == kEpiW + 1) tmem_dealloc<512>(tmem_base);
 }
 
-void launch_ffn_fused(const CUtensorMap& tmH, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const FfnParams& p,
+static long long* g_ffn_trace = nullptr;
+void ffn_set_trace(long long* dev_buf) { g_ffn_trace = dev_buf; }
+
+void launch_ffn_fused(const CUtensorMap& tmH, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const FfnParams& p_in,
                       cudaStream_t stream) {
+  FfnParams p = p_in;
+  p.trace = g_ffn_trace;
   static bool configured = false;
   static int num_sms = 0;
   if (!configured) {

@@ -19,7 +19,10 @@ struct FfnParams {
   float* x32;               // [S*T_alloc, 256] residual stream, updated in place
   Emit emit_ln;             // ptr != null: LayerNorm(x; a = gamma, b = beta, f = eps) -> 16-bit
   Emit emit_plain[2];       // ptr != null: masked x -> 16-bit (ld / col_off honoured)
+  long long* trace;         // debug: CTA 0 logs (clock64 << 8 | event code) for its MMA thread [0, 4096) and first epilogue warp
+                            // [4096, 8192) (profiles/ffn_trace.py); null in production
 };
+void ffn_set_trace(long long* dev_buf);   // the next launches log into dev_buf (null: off)
 
 // tmH: 3-D {256, T_alloc, S} box {64,128,1};  tmW1: 2-D {256, 1024} box {64,128};  tmW2: 2-D {1024, 256} box {64,128}
 void launch_ffn_fused(const CUtensorMap& tmH, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const FfnParams& p,

@@ -1,7 +1,10 @@
 // Tap GEMM kernel (see gemm_tap.cuh).  Persistent, warp-specialised:
-//   warp 0      TMA producer: A/B k-blocks into a 4-stage 128B-swizzled smem ring (mbarrier full/empty)
-//   warp 1      tcgen05.mma issuer (kind::f16, fp32 accumulate) into a DOUBLE-BUFFERED TMEM accumulator
-//   warps 2-9   epilogue: 8 warps, two per TMEM lane quarter (each thread owns half a row), so the epilogue of tile i
+//   warps 0..E-1  epilogue (E = 16, 8 for BN = 64): see below
+//   warp E        TMA producer: A/B k-blocks into a 192 KB 128B-swizzled smem ring (mbarrier full/empty)
+//   warp E+1      tcgen05.mma issuer (kind::f16, fp32 accumulate) into a DOUBLE-BUFFERED TMEM accumulator
+//   (the two issuing warps carry the highest warp ids: the scheduler favours high ids, and an issuer that loses arbitration
+//    against the math-heavy epilogue warps paces the tensor pipe)
+//   epilogue: 8 warps, two per TMEM lane quarter (each thread owns half a row), so the epilogue of tile i
 //               overlaps the MMAs of tile i+1; LayerNorm statistics are combined between the two half-row threads
 //               through shared memory.
 // Each CTA walks tiles blockIdx.x, +gridDim.x, ... in (n fastest, then t, then sequence) order and skips tiles that lie
@@ -110,7 +113,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr uint16_t kMcMask = (uint16_t)((1u << CS) - 1);
   constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // 128 / 256 / 512
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kEpiWarps && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < kStages; i++) {
@@ -123,14 +126,14 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == kEpiWarps + 1) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before();
   if (CS > 1) cluster_sync();   // peers multicast into this CTA's stages and arrive on its barriers: all must be initialised
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kEpiWarps) {
     if (lane == 0) {
       // ------------------------------- TMA producer -------------------------------
       int kit = 0;
@@ -153,7 +156,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kEpiWarps + 1) {
     if (lane == 0) {
       // ------------------------------- MMA issuer ---------------------------------
       constexpr uint32_t idesc = umma_idesc_f16(kTileM, BN, 0);
@@ -186,7 +189,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // --------------------------------- epilogue -----------------------------------
-    const int ew = warp - 2;
+    const int ew = warp;
     const int q = warp & 3;              // TMEM lane quarter accessible to this warp
     const int half = ew >> 2;            // which part of the tile's columns this thread owns
     const int r = q * 32 + lane;
@@ -519,7 +522,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_before();
   if (CS > 1) cluster_sync();   // no CTA may exit while a peer can still multicast into it or arrive on its barriers
   else __syncthreads();
-  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+  if (warp == kEpiWarps + 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
 // Compact list of the (sequence, t0) row tiles that contain at least one row < len + halo, in (s, t) order.

@@ -48,6 +48,8 @@ int cv2_engine_set_seed_ptr(cv2_engine* e, const unsigned long long* seed_dev);
 /* engine switches (tests / A-B measurements): "fuse_euler" (CFG combine + Euler update inside final_proj, default 1),
  * "fuse_ffn" (FF1+GELU+FF2 in one kernel, default 1) */
 int cv2_engine_set_option(cv2_engine* e, const char* name, int value);
+/* debug: CTA 0 of the following ffn_fused launches logs (clock64 << 8 | event) records into dev_buf[8192] (profiles/ffn_trace.py) */
+int cv2_debug_set_ffn_trace(long long* dev_buf);
 int cv2_engine_set_profiling(cv2_engine* e, int on);
 int cv2_engine_read_profile(cv2_engine* e, double* ms_per_family, long long* launches_per_family, int n_families);
 
