@@ -238,7 +238,11 @@ def main():
                 gather_buf["aud"] = [torch.empty_like(speech) for _ in range(world)]
             dist.gather(lens_d, gather_buf.get("lens"), dst=0)
             dist.gather(speech, gather_buf.get("aud"), dst=0)
-        out = speech.cpu()                                   # D2H of the step's result (also drains the gather on rank 0)
+        if "host" not in gather_buf or gather_buf["host"].shape != speech.shape:
+            gather_buf["host"] = torch.empty(speech.shape, dtype=speech.dtype).pin_memory()   # pinned once, reused every step
+        out = gather_buf["host"]
+        out.copy_(speech, non_blocking=True)                 # D2H of the step's result into pinned memory
+        torch.cuda.current_stream().synchronize()            # (also drains the gather on rank 0)
         return out
 
     def barrier():
@@ -368,13 +372,23 @@ def main():
                    "algorithmic_tflop_per_step": flops[n] / 1e12,
                    "tflops": (flops[n] / 1e12) / (fam_ms[i] / args.steps / 1e3) if fam_ms[i] > 0 else None}
                for i, n in enumerate(FAMILIES) if fam_n[i] > 0}
-        dom = max(fam, key=lambda n: fam[n]["ms_per_step"])
-        d = fam[dom]
+        # dominant KERNEL by device time: gemm_tap<256> is one template with many epilogue specialisations that serve different
+        # layers; its two big instances (QKV projection, out-proj + residual + LayerNorm) are ranked on their own
+        rows2 = 20.0 * sum(2 * (n + N_PROMPT) for n in n_tokens)          # estimator rows x Euler steps x CFG
+        spec_flops = {"qkv_split": rows2 * 56 * 2 * 256 * 1536.0, "res+ln_emit": rows2 * 56 * 2 * 512 * 256.0}
+        cand = {n: v for n, v in fam.items() if n != "gemm_tap<256>"}
+        for sname, fl in spec_flops.items():
+            if sname in g256:
+                cand["gemm_tap<256>:" + sname] = {"ms_per_step": g256[sname]["ms_per_step"], "launches_per_step": g256[sname]["launches_per_step"],
+                                                  "algorithmic_tflop_per_step": fl / 1e12,
+                                                  "tflops": fl / 1e12 / (g256[sname]["ms_per_step"] / 1e3)}
+        dom = max(cand, key=lambda n: cand[n]["ms_per_step"])
+        d = cand[dom]
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         ach = d["tflops"] or 0.0
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` on this very command
         # (profiles/README.md, round 1): only captured for flash_attn and the QKV GEMM
-        ncu_traffic = {"flash_attn": 414.8e6}
+        ncu_traffic = {"flash_attn": 405.4e6}   # flash_attn_v9_kernel inside `bench.py --steps 1` (profiles/README.md): 315.5 MB read + 89.8 MB written
         roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": ncu_traffic.get(dom), "peak_source": peak_src + " sustained dense bf16 (kernel timed inside a long step)",
                     "avg_launch_ms": d["ms_per_step"] / d["launches_per_step"],
