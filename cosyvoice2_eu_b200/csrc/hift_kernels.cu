@@ -353,10 +353,10 @@ __global__ void __launch_bounds__(256) source_down_kernel(const float* __restric
   const int T_out = len * frames_per_len + frames_add;       // output frames of this stage
   const int F = len * 120 + 1;                               // stft frames
   if (t0 >= T_alloc || c4 >= C) return;
-  float acc[4][4];
+  float2 acc[4][2];   // packed channel pairs: one FFMA2 per two multiply-adds
   const float4 bv = *reinterpret_cast<const float4*>(bias + c4);
 #pragma unroll
-  for (int f = 0; f < 4; f++) { acc[f][0] = bv.x; acc[f][1] = bv.y; acc[f][2] = bv.z; acc[f][3] = bv.w; }
+  for (int f = 0; f < 4; f++) { acc[f][0] = make_float2(bv.x, bv.y); acc[f][1] = make_float2(bv.z, bv.w); }
   if (t0 < T_out) {
     const float* sb = stft + (long long)b * F_alloc * 18;
     for (int j = 0; j < k; j++) {
@@ -374,10 +374,9 @@ __global__ void __launch_bounds__(256) source_down_kernel(const float* __restric
 #pragma unroll
         for (int f = 0; f < 4; f++) {
           const float sv = ok[f] ? __ldg(sb + (long long)fr[f] * 18 + ch) : 0.f;
-          acc[f][0] = fmaf(sv, wv.x, acc[f][0]);
-          acc[f][1] = fmaf(sv, wv.y, acc[f][1]);
-          acc[f][2] = fmaf(sv, wv.z, acc[f][2]);
-          acc[f][3] = fmaf(sv, wv.w, acc[f][3]);
+          const float2 s2 = make_float2(sv, sv);
+          acc[f][0] = ffma2(s2, make_float2(wv.x, wv.y), acc[f][0]);
+          acc[f][1] = ffma2(s2, make_float2(wv.z, wv.w), acc[f][1]);
         }
       }
     }
@@ -389,7 +388,7 @@ __global__ void __launch_bounds__(256) source_down_kernel(const float* __restric
     if (t >= T_alloc) break;
     const bool valid = t < T_out;
     const long long o = ((long long)b * T_alloc + t) * C + c4;
-    float4 v = valid ? make_float4(acc[f][0], acc[f][1], acc[f][2], acc[f][3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = valid ? make_float4(acc[f][0].x, acc[f][0].y, acc[f][1].x, acc[f][1].y) : make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(out32 + o) = v;
     __half2 h0 = __floats2half2_rn(valid ? snake_f(v.x, av.x) : 0.f, valid ? snake_f(v.y, av.y) : 0.f);
     __half2 h1 = __floats2half2_rn(valid ? snake_f(v.z, av.z) : 0.f, valid ? snake_f(v.w, av.w) : 0.f);
