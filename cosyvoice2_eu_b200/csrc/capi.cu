@@ -110,6 +110,7 @@ int cv2_engine_set_option(cv2_engine* h, const char* name, int value) {
   else if (n == "fuse_ffn") h->e.fuse_ffn = value != 0;
   else if (n == "f0_split") h->e.f0_split = value != 0;
   else if (n == "cluster_mc") h->e.cluster_mc = value != 0;
+  else if (n == "ffn_2cta") h->e.ffn_2cta = value != 0;
   else fail("unknown engine option '%s'", name);
   CV2_API_END
 }

@@ -72,6 +72,7 @@ struct Engine {
   // error 4.8e-3 Hz (fp32: 4.5e-4) -- the tensor core adds each K=16 group to the fp32 accumulator with truncation, ~2^-16
   // relative over K = 6144 -- which the phase accumulator turns into 8.7 dB waveform SNR at 8 s.  Off by default.
   bool f0_split = getenv("CV2_F0_SPLIT") != nullptr;
+  bool ffn_2cta = getenv("CV2_NO_FFN_2CTA") == nullptr;      // fused FFN as CTA pairs with tcgen05.mma.cta_group::2 (ffn_fused2.cu)
   bool cluster_mc = getenv("CV2_NO_CLUSTER") == nullptr;      // BN=256 GEMMs as 2-CTA clusters sharing the weight tile by TMA multicast
   bool fuse_euler = getenv("CV2_NO_EULER_FUSION") == nullptr; // CFG combine + Euler update inside final_proj's epilogue
   const unsigned long long* seed_dev = nullptr;   // optional device-resident NSF noise seed (CUDA-graph replays)

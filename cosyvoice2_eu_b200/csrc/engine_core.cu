@@ -80,10 +80,12 @@ void Engine::ffn(cudaStream_t st, const __half* H, int S, int T_alloc, Weight& w
     }
   }
   const CUtensorMap& th = amap(H, S, T_alloc, 256, 256);
-  const CUtensorMap& t1 = wmap(w1, 128);
-  const CUtensorMap& t2 = wmap(w2, 128);
   prof_begin(st, F_FFN_FUSED);
-  launch_ffn_fused(th, t1, t2, p, st);
+  if (ffn_2cta && p.tile_list && (long long)S * (T_alloc / 128) >= 148) {
+    launch_ffn_fused2(th, wmap(w1, 64), wmap(w2, 128), p, st);   // 2-SM MMAs, each CTA stages half of every weight tile
+  } else {
+    launch_ffn_fused(th, wmap(w1, 128), wmap(w2, 128), p, st);
+  }
   prof_end(st);
 }
 

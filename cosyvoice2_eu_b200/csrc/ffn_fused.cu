@@ -369,6 +369,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
 
 static long long* g_ffn_trace = nullptr;
 void ffn_set_trace(long long* dev_buf) { g_ffn_trace = dev_buf; }
+long long* g_ffn_trace_ptr() { return g_ffn_trace; }
 
 void launch_ffn_fused(const CUtensorMap& tmH, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const FfnParams& p_in,
                       cudaStream_t stream) {

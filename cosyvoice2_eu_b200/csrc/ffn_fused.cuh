@@ -28,4 +28,9 @@ void ffn_set_trace(long long* dev_buf);   // the next launches log into dev_buf 
 void launch_ffn_fused(const CUtensorMap& tmH, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const FfnParams& p,
                       cudaStream_t stream);
 
+// 2-SM form (ffn_fused2.cu): cluster of two CTAs, tcgen05.mma.cta_group::2.  tmW1h: {256, 1024} box {64, 64};
+// tmW2h: {1024, 256} box {64, 128}.  Requires the compact tile list.
+void launch_ffn_fused2(const CUtensorMap& tmH, const CUtensorMap& tmW1h, const CUtensorMap& tmW2h, const FfnParams& p,
+                       cudaStream_t stream);
+
 }  // namespace cv2

@@ -1,0 +1,454 @@
+// Two-SM form of the fused estimator feed-forward (see ffn_fused.cu for the algorithm): a cluster of two CTAs works on two
+// 128-row tiles and ONE thread (CTA rank 0) issues every MMA for both SMs with tcgen05.mma.cta_group::2 (M = 256).
+// Why: with one CTA per MMA the tensor pipe ran at ~55 % of its rate in this kernel (112 cycles per 128x128x16 MMA instead of
+// 64; profiles/ffn_trace.py), and the micro-benchmarks in profiles/micro show the cause is the issue path -- descriptors that
+// change every few MMAs cost ~120 cycles per instruction in cta_group::1 form, while the cta_group::2 form sustains the nominal
+// 64 cycles with twice the work per instruction -- and each SM only stages HALF of every weight tile (the pair shares B).
+//   * each CTA: its own H tile, its own 16 epilogue warps, its own TMEM (acc1 2 x 128, acc2 256), its own output epilogue;
+//   * weights: every CTA TMA-loads its half of each tile (W1 chunk: 64 of 128 rows; W2 k-block: 128 of 256 rows) into its own
+//     ring and signals the LEADER's full barrier (cp.async.bulk.tensor ... .cta_group::2, peer bit cleared);
+//   * the leader's commits are multicast to both CTAs' barriers (slot free, acc1_full, acc2_full); the peer's epilogue warps
+//     arrive remotely on the leader's f_full / acc2_empty (count 32); the leader relays f_seen to the peer.
+#include "common.cuh"
+#include "epi_util.cuh"
+#include "ffn_fused.cuh"
+#include "host_util.h"
+
+namespace cv2 {
+
+static constexpr int kHBytes = 4 * 16384;       // [128 x 256] 16-bit, four 64-column swizzle atoms
+static constexpr int kSlots = 8;                 // the hidden chunk lives in TMEM and the epilogue needs no staging: all the
+static constexpr int kSlotBytes = 16384;        // remaining shared memory is weight ring (one [128 x 64] tile per slot)
+static constexpr int kOffW = kHBytes;
+static constexpr int kEpiW = 16;                 // epilogue warps: four per TMEM lane quarter
+static constexpr int kOffRed = kOffW + kSlots * kSlotBytes;
+static constexpr int kOffBar = kOffRed + 2 * 4 * 128 * 4;
+static constexpr int kFfnSmem = kOffBar + 256;
+static constexpr int kFfnThreads = 64 + kEpiW * 32;
+static constexpr uint32_t kAcc1 = 0, kAcc2 = 256;   // TMEM columns: acc1 = 2 x 128, acc2 = 256
+
+static constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even CTA of the pair
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// arrives (once all prior MMAs of this thread are done) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// TMA into this CTA's shared memory, transaction bytes credited to the LEADER's barrier at the same offset
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(m), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(m), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// arrive on the LEADER's barrier at this offset (local for rank 0, remote for rank 1)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+// arrive on the barrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_rank(uint64_t* bar, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void ffn_trace(long long* buf, int& idx, int code) {
+  if (buf && idx < 4095) buf[idx++] = (clock64() << 8) | code;
+}
+__device__ __forceinline__ void ffn_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+__device__ __forceinline__ bool ffn_tile(const FfnParams& p, int tile, int t_tiles, int& s, int& t0, int& len) {
+  if (p.tile_list) {
+    s = __ldg(p.tile_list + 2 * tile);
+    t0 = __ldg(p.tile_list + 2 * tile + 1);
+    len = __ldg(p.lens + s);
+    return true;
+  }
+  s = tile / t_tiles;
+  t0 = (tile % t_tiles) * 128;
+  len = p.lens ? __ldg(p.lens + s) : p.len_all;
+  return t0 < len + p.halo;
+}
+
+// pair unit -> this CTA's row tile; false for the filler tile of an odd tail (computed on a copy of tile 0, nothing stored)
+__device__ __forceinline__ bool ffn2_tile(const FfnParams& p, int unit, uint32_t rank, int row_tiles, int& s, int& t0, int& len) {
+  int idx = 2 * unit + (int)rank;
+  const bool ok = idx < row_tiles;
+  if (!ok) idx = 0;
+  s = __ldg(p.tile_list + 2 * idx);
+  t0 = __ldg(p.tile_list + 2 * idx + 1);
+  len = __ldg(p.lens + s);
+  return ok;
+}
+
+// op o of a tile's schedule: FF1(0), FF1(1), FF2(0), FF1(2), FF2(1), ..., FF1(7), FF2(6), FF2(7)
+__device__ __forceinline__ void ffn_op(int o, bool& is_ff2, int& c) {
+  if (o < 2) { is_ff2 = false; c = o; }
+  else if (o == 15) { is_ff2 = true; c = 7; }
+  else if (o & 1) { is_ff2 = false; c = (o + 1) >> 1; }
+  else { is_ff2 = true; c = (o >> 1) - 1; }
+}
+
+__global__ void __launch_bounds__(kFfnThreads, 1)
+ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const FfnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];   // 1024 B alignment for the 128B-swizzle atoms
+  float* red = reinterpret_cast<float*>(smem + kOffRed);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* h_full = bars + 0;
+  uint64_t* h_empty = bars + 1;
+  uint64_t* w_full = bars + 2;             // [kSlots]
+  uint64_t* w_empty = w_full + kSlots;     // [kSlots]
+  uint64_t* acc1_full = w_empty + kSlots;  // [2]
+  uint64_t* acc1_empty = acc1_full + 2;    // [2]
+  uint64_t* f_full = acc1_empty + 2;
+  uint64_t* f_seen = f_full + 1;           // MMA thread has observed f_full of a chunk (keeps f_full at most one phase ahead)
+  uint64_t* acc2_full = f_seen + 1;
+  uint64_t* acc2_empty = acc2_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int t_tiles = p.T_alloc / 128;
+  const int row_tiles = __ldg(p.tile_count);                 // (the 2-SM path requires the compact tile list)
+  const int total_tiles = (row_tiles + 1) / 2;                // pair units
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
+
+  if (warp == kEpiW && lane == 0) {
+    tma_prefetch_desc(&tmH);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    mbar_init(h_full, 1);          // leader only: its producer's arrive.expect_tx (bytes of BOTH CTAs)
+    mbar_init(h_empty, 1);         // multicast commit
+    for (int i = 0; i < kSlots; i++) {
+      mbar_init(&w_full[i], 1);    // leader only
+      mbar_init(&w_empty[i], 1);   // multicast commit
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&acc1_full[i], 1); // multicast commit
+      mbar_init(&acc1_empty[i], 1);
+    }
+    mbar_init(f_full, 2 * kEpiW);  // leader only: the epilogue warps of both CTAs
+    mbar_init(f_seen, 1);          // leader's MMA thread arrives in both CTAs
+    mbar_init(acc2_full, 1);       // multicast commit
+    mbar_init(acc2_empty, 2 * kEpiW);   // leader only
+    fence_barrier_init();
+  }
+  if (warp == kEpiW + 1) {         // both CTAs, same warp id, same destination
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync();                  // the peer signals this CTA's barriers: everything must be initialised cluster-wide
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kEpiW) {
+    if (lane == 0) {
+      // ------------------------------- TMA producer (both CTAs) --------------------
+      // Each CTA loads ITS H tile and ITS half of every weight tile into its own shared memory; the bytes are credited to the
+      // leader's full barriers, on which only the leader's producer arrives (expecting the bytes of both CTAs).
+      int lt = 0, wit = 0;
+      for (int unit = unit0; unit < total_tiles; unit += unit_step) {
+        int s, t0, len;
+        ffn2_tile(p, unit, rank, row_tiles, s, t0, len);
+        prefetch_l2_bulk(p.x32 + ((long long)s * p.T_alloc + t0) * 256, 128 * 256 * 4);
+        mbar_wait(h_empty, (lt & 1) ^ 1);
+        if (leader) mbar_expect_tx(h_full, 2 * kHBytes);
+#pragma unroll
+        for (int kb = 0; kb < 4; kb++) tma2_load_3d(smem + kb * 16384, &tmH, h_full, kb * 64, t0, s);
+        for (int o = 0; o < 16; o++) {
+          bool is_ff2;
+          int c;
+          ffn_op(o, is_ff2, c);
+          for (int i = 0; i < 2; i++, wit++) {     // two 16 KB slots per op and CTA
+            const int st = wit % kSlots;
+            mbar_wait(&w_empty[st], ((wit / kSlots) & 1) ^ 1);
+            if (leader) mbar_expect_tx(&w_full[st], 2 * kSlotBytes);
+            uint8_t* dst = smem + kOffW + st * kSlotBytes;
+            if (!is_ff2) {   // W1 chunk c, k-blocks 2i and 2i+1: this CTA's 64 of the 128 hidden rows, [64 x 64] each (8 KB)
+              tma2_load_2d(dst, &tmW1, &w_full[st], (2 * i) * 64, c * 128 + (int)rank * 64);
+              tma2_load_2d(dst + 8192, &tmW1, &w_full[st], (2 * i + 1) * 64, c * 128 + (int)rank * 64);
+            } else {         // W2 k-block i of chunk c: this CTA's 128 of the 256 output rows, [128 x 64] (16 KB)
+              tma2_load_2d(dst, &tmW2, &w_full[st], c * 128 + i * 64, (int)rank * 128);
+            }
+          }
+        }
+        lt++;
+      }
+    }
+  } else if (warp == kEpiW + 1) {
+    if (lane == 0 && leader) {
+      // ------------------------------- MMA issuer (leader CTA, for both SMs) -------
+      constexpr uint32_t idesc1 = umma_idesc_f16(256, 128, 0);   // FF1: 256 rows (2 x 128) x 128 hidden columns
+      constexpr uint32_t idesc2 = umma_idesc_f16(256, 256, 0);   // FF2: 256 rows x 256 outputs
+      const uint32_t h_addr = smem_u32(smem);
+      int lt = 0, wit = 0, fcnt = 0;
+      long long* tb = blockIdx.x == 0 ? p.trace : nullptr;
+      int ti = 0;
+      for (int unit = unit0; unit < total_tiles; unit += unit_step) {
+        ffn_trace(tb, ti, 1);
+        mbar_wait(h_full, lt & 1);
+        ffn_trace(tb, ti, 2);
+        for (int o = 0; o < 16; o++) {
+          bool is_ff2;
+          int c;
+          ffn_op(o, is_ff2, c);
+          if (!is_ff2) {
+            const int b = c & 1;   // buffer b was last read by FF2(c-2), issued earlier on the same in-order pipe
+            for (int i = 0; i < 2; i++, wit++) {
+              const int st = wit % kSlots;
+              mbar_wait(&w_full[st], (wit / kSlots) & 1);
+              const uint32_t w_addr = smem_u32(smem + kOffW + st * kSlotBytes);
+#pragma unroll
+              for (int kk = 0; kk < 2; kk++) {
+                const int kb = 2 * i + kk;
+                const uint64_t a_desc = umma_smem_desc_sw128(h_addr + kb * 16384);
+                const uint64_t b_desc = umma_smem_desc_sw128(w_addr + kk * 8192);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                  umma2_f16(tmem_base + kAcc1 + b * 128, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc1, (kb | k) != 0);
+              }
+              umma2_commit(&w_empty[st]);
+            }
+            umma2_commit(&acc1_full[b]);
+            ffn_trace(tb, ti, 3);
+            if (c == 7) umma2_commit(h_empty);                 // all FF1 MMAs of this unit issued: the H tiles may be refilled
+          } else {
+            if (c == 0) {
+              mbar_wait(acc2_empty, (lt & 1) ^ 1);              // both CTAs' output epilogues have drained acc2
+              tc_fence_after();
+            }
+            ffn_trace(tb, ti, 4);
+            mbar_wait(f_full, fcnt & 1);                        // GELU chunk c (16-bit) is in TMEM in both CTAs
+            ffn_trace(tb, ti, 5);
+            mbar_arrive(f_seen);                                // back-pressure (see ffn_fused.cu), relayed to the peer
+            mbar_arrive_rank(f_seen, 1);
+            tc_fence_after();
+            const uint32_t a_tmem = tmem_base + kAcc1 + (c & 1) * 128;
+            for (int kb = 0; kb < 2; kb++, wit++) {
+              const int st = wit % kSlots;
+              mbar_wait(&w_full[st], (wit / kSlots) & 1);
+              const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(smem + kOffW + st * kSlotBytes));
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                umma2_f16_ts(tmem_base + kAcc2, a_tmem + kb * 32 + k * 8, b_desc + (uint64_t)(k * 2), idesc2, (c | kb | k) != 0);
+              umma2_commit(&w_empty[st]);
+            }
+            fcnt++;
+            ffn_trace(tb, ti, 6);
+            if (c == 7) umma2_commit(acc2_full);
+          }
+        }
+        lt++;
+      }
+    }
+  } else {
+    // --------------------------------- epilogue -----------------------------------
+    const int ew = warp;
+    const int q = warp & 3;
+    const int part = ew >> 2;                // 0..3: which quarter of the columns
+    const int r = q * 32 + lane;
+    float* stg = nullptr;                    // (epilogue I/O is direct 256-bit global access: no staging tile)
+    float* red_c = red;                      // [4][128]
+    float* red_d = red + 512;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    int lt = 0, use1[2] = {0, 0}, g = 0;
+    long long* tb = (blockIdx.x == 0 && warp == 0 && lane == 0 && p.trace) ? p.trace + 4096 : nullptr;
+    int ti = 0;
+    for (int unit = unit0; unit < total_tiles; unit += unit_step) {
+      int s, t0, len;
+      const bool tile_ok = ffn2_tile(p, unit, rank, row_tiles, s, t0, len);
+      const int t = t0 + r;
+      const bool valid = t < len;
+      const long long row = (long long)s * p.T_alloc + t;
+      const long long row0 = row - lane;
+      // ---- 8 hidden chunks: bias + GELU -> 16-bit chunk in shared memory (A operand of FF2) ----
+      for (int c = 0; c < 8; c++, g++) {
+        const int b = c & 1;
+        float bv[32];
+        load32(p.b1 + c * 128 + part * 32, bv, true, 32);      // bias first: its latency hides behind the accumulator wait
+        ffn_trace(tb, ti, 10);
+        mbar_wait(&acc1_full[b], use1[b] & 1);
+        ffn_trace(tb, ti, 11);
+        use1[b]++;
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld32(lane_addr + kAcc1 + b * 128 + part * 32, raw);
+        tmem_ld_wait();
+        // the 16-bit chunk lands on columns [16*part, 16*part+16) of this buffer = fp32 columns of part/2: the four warps
+        // of a lane quarter must all hold their accumulator slice in registers before any of them writes
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+        ffn_trace(tb, ti, 12);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {   // bias + GELU on packed fp32 pairs, straight to 16-bit pairs
+          const float2 g2 = fast_gelu_erf2(fadd2(make_float2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1])),
+                                                 make_float2(bv[i], bv[i + 1])));
+          __half2 h2 = __floats2half2_rn(g2.x, g2.y);
+          raw[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        tmem_st16(lane_addr + kAcc1 + b * 128 + part * 16, raw);
+        tmem_st_wait();
+        tc_fence_before();
+        ffn_trace(tb, ti, 13);
+        if (g > 0) mbar_wait(f_seen, (g - 1) & 1);              // never two unobserved phases of f_full (robust to any warp skew)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(f_full);
+        ffn_trace(tb, ti, 14);
+      }
+      ffn_trace(tb, ti, 20);
+      // ---- output tile: + b2 + residual -> X32 ; LayerNorm / plain emits ----
+      mbar_wait(acc2_full, lt & 1);
+      tc_fence_after();
+      ffn_trace(tb, ti, 21);
+      const uint32_t taddr = lane_addr + kAcc2 + part * 64;
+      const bool want_ln = tile_ok && p.emit_ln.ptr != nullptr;
+      if (!tile_ok) {   // filler tile of an odd tail: nothing to store, just hand acc2 back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(acc2_empty);
+        lt++;
+        continue;
+      }
+      float sum2 = 0.f;
+      uint32_t raw[32];
+      float v[32], tmp[32];
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ch++) {
+        const int cbase = part * 64 + ch * 32;
+        tmem_ld32(taddr + ch * 32, raw);
+        load32(p.b2 + cbase, tmp, true, 32);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]) + tmp[i];
+        tile_load_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, tmp);
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] += tmp[i];
+        tile_store_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, v);
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const Emit& em = p.emit_plain[e];
+          if (!em.ptr) continue;
+          float w[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) w[i] = valid ? v[i] : 0.f;
+          tile_store_f16_h16(em.ptr + row0 * em.ld + em.col_off + cbase, em.ld, stg, lane, w);
+        }
+        if (want_ln) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            sum2 += v[i];
+            raw[i] = __float_as_uint(v[i]);
+          }
+          tmem_st32(taddr + ch * 32, raw);
+        }
+      }
+      if (want_ln) {
+        tmem_st_wait();
+        red_c[part * 128 + r] = sum2;
+        ffn_bar();
+        const float mean2 = (red_c[r] + red_c[128 + r] + red_c[256 + r] + red_c[384 + r]) * (1.f / 256.f);
+        float sq2 = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ch++) {
+          tmem_ld32(taddr + ch * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const float d = __uint_as_float(raw[i]) - mean2;
+            sq2 = fmaf(d, d, sq2);
+          }
+        }
+        red_d[part * 128 + r] = sq2;
+        ffn_bar();
+        const float rstd2 = rsqrtf((red_d[r] + red_d[128 + r] + red_d[256 + r] + red_d[384 + r]) * (1.f / 256.f) + p.emit_ln.f);
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ch++) {
+          const int cbase = part * 64 + ch * 32;
+          tmem_ld32(taddr + ch * 32, raw);
+          float gg[32], w[32];
+          load32(p.emit_ln.a + cbase, gg, true, 32);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) w[i] = (__uint_as_float(raw[i]) - mean2) * rstd2 * gg[i];
+          load32(p.emit_ln.b + cbase, gg, true, 32);
+#pragma unroll
+          for (int i = 0; i < 32; i++) w[i] = valid ? (w[i] + gg[i]) : 0.f;
+          tile_store_f16_h16(p.emit_ln.ptr + row0 * p.emit_ln.ld + p.emit_ln.col_off + cbase, p.emit_ln.ld, stg, lane, w);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(acc2_empty);
+      ffn_trace(tb, ti, 22);
+      lt++;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync();   // no CTA may exit (or free TMEM) while the leader can still issue MMAs into it or signal its barriers
+  if (warp == kEpiW + 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+extern long long* g_ffn_trace_ptr();
+
+void launch_ffn_fused2(const CUtensorMap& tmH, const CUtensorMap& tmW1h, const CUtensorMap& tmW2h, const FfnParams& p_in,
+                       cudaStream_t stream) {
+  static bool configured = false;
+  static int max_clusters = 0;
+  FfnParams p = p_in;
+  p.trace = g_ffn_trace_ptr();
+  CV2_CHECK(p.tile_list && p.tile_count && p.lens, "ffn_fused2: the 2-SM path needs the compact tile list");
+  cudaLaunchConfig_t q = {};
+  q.blockDim = dim3(kFfnThreads);
+  q.dynamicSmemBytes = kFfnSmem;
+  q.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  q.attrs = at;
+  q.numAttrs = 1;
+  if (!configured) {
+    CV2_CUDA(cudaFuncSetAttribute(ffn_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem));
+    int dev = 0, sms = 0;
+    CV2_CUDA(cudaGetDevice(&dev));
+    CV2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    q.gridDim = dim3(sms / 2 * 2);
+    CV2_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, ffn_fused2_kernel, &q));
+    CV2_CHECK(max_clusters > 0, "ffn_fused2: no 2-CTA cluster fits");
+    configured = true;
+  }
+  CV2_CHECK(p.T_alloc % 128 == 0, "ffn_fused2: T_alloc %d not a multiple of 128", p.T_alloc);
+  const int units = ((p.T_alloc / 128) * p.S + 1) / 2;
+  const int clusters = units < max_clusters ? units : max_clusters;
+  q.gridDim = dim3(2 * clusters);
+  CV2_CUDA(cudaLaunchKernelEx(&q, ffn_fused2_kernel, tmH, tmW1h, tmW2h, p));
+  CV2_LAUNCH_CHECK();
+}
+
+}  // namespace cv2
