@@ -205,66 +205,98 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
   } else if (warp == kEpiW + 1) {
     if (lane == 0 && leader) {
       // ------------------------------- MMA issuer (leader CTA, for both SMs) -------
+      // The 2-SM pipe retires these MMAs at the nominal rate (8 per 513 cycles in the trace), but its queue is shallow and
+      // the issuing thread blocks on it, so every cycle the thread spends elsewhere between bursts is an idle tensor pipe: a
+      // satisfied mbarrier poll alone costs ~120 cycles.  Hence (i) the op schedule is straight-line code per chunk, and
+      // (ii) the barriers of the NEXT burst (weight slot, GELU chunk) are polled in the MIDDLE of the current burst, where
+      // the thread would be blocked anyway; the blocking wait at the start of a burst is skipped when that poll succeeded.
       constexpr uint32_t idesc1 = umma_idesc_f16(256, 128, 0);   // FF1: 256 rows (2 x 128) x 128 hidden columns
       constexpr uint32_t idesc2 = umma_idesc_f16(256, 256, 0);   // FF2: 256 rows x 256 outputs
       const uint32_t h_addr = smem_u32(smem);
+      const uint32_t w_base = smem_u32(smem + kOffW);
       int lt = 0, wit = 0, fcnt = 0;
+      bool w_ready = false, f_ready = false;
       long long* tb = blockIdx.x == 0 ? p.trace : nullptr;
       int ti = 0;
+      auto poll_next_slot = [&]() {
+        const int n = wit + 1;
+        w_ready = mbar_try_wait(&w_full[n % kSlots], (n / kSlots) & 1);
+      };
+      auto poll_f = [&]() { f_ready = mbar_try_wait(f_full, fcnt & 1); };
+      auto slot_begin = [&]() -> uint32_t {   // returns the smem address of the current slot, data landed
+        const int st = wit % kSlots;
+        if (!w_ready) mbar_wait(&w_full[st], (wit / kSlots) & 1);
+        w_ready = false;
+        return w_base + st * kSlotBytes;
+      };
+      auto ff1 = [&](int c, bool poll_f_after) {
+        const int b = c & 1;   // buffer b was last read by FF2(c-2), issued earlier on the same in-order pipe
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const uint32_t w_addr = slot_begin();
+#pragma unroll
+          for (int kk = 0; kk < 2; kk++) {
+            const int kb = 2 * i + kk;
+            const uint64_t a_desc = umma_smem_desc_sw128(h_addr + kb * 16384);
+            const uint64_t b_desc = umma_smem_desc_sw128(w_addr + kk * 8192);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              umma2_f16(tmem_base + kAcc1 + b * 128, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc1, (kb | k) != 0);
+            if (kk == 0) {               // middle of the burst: look ahead
+              poll_next_slot();
+              if (i == 1 && poll_f_after) poll_f();
+            }
+          }
+          umma2_commit(&w_empty[wit % kSlots]);
+          wit++;
+        }
+        umma2_commit(&acc1_full[b]);
+        ffn_trace(tb, ti, 3);
+      };
+      auto ff2 = [&](int c) {
+        ffn_trace(tb, ti, 4);
+        if (!f_ready) mbar_wait(f_full, fcnt & 1);      // GELU chunk c (16-bit) is in TMEM in both CTAs
+        f_ready = false;
+        fcnt++;
+        ffn_trace(tb, ti, 5);
+        mbar_arrive(f_seen);                            // back-pressure (see ffn_fused.cu), relayed to the peer
+        mbar_arrive_rank(f_seen, 1);
+        tc_fence_after();
+        const uint32_t a_tmem = tmem_base + kAcc1 + (c & 1) * 128;
+#pragma unroll
+        for (int kb = 0; kb < 2; kb++) {
+          const uint64_t b_desc = umma_smem_desc_sw128(slot_begin());
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            umma2_f16_ts(tmem_base + kAcc2, a_tmem + kb * 32 + k * 8, b_desc + (uint64_t)(k * 2), idesc2, (c | kb | k) != 0);
+            if (k == 1) {
+              poll_next_slot();
+              if (kb == 1 && c == 6) poll_f();          // FF2(7) follows FF2(6) directly
+            }
+          }
+          umma2_commit(&w_empty[wit % kSlots]);
+          wit++;
+        }
+        ffn_trace(tb, ti, 6);
+      };
       for (int unit = unit0; unit < total_tiles; unit += unit_step) {
         ffn_trace(tb, ti, 1);
         mbar_wait(h_full, lt & 1);
         ffn_trace(tb, ti, 2);
-        for (int o = 0; o < 16; o++) {
-          bool is_ff2;
-          int c;
-          ffn_op(o, is_ff2, c);
-          if (!is_ff2) {
-            const int b = c & 1;   // buffer b was last read by FF2(c-2), issued earlier on the same in-order pipe
-            for (int i = 0; i < 2; i++, wit++) {
-              const int st = wit % kSlots;
-              mbar_wait(&w_full[st], (wit / kSlots) & 1);
-              const uint32_t w_addr = smem_u32(smem + kOffW + st * kSlotBytes);
-#pragma unroll
-              for (int kk = 0; kk < 2; kk++) {
-                const int kb = 2 * i + kk;
-                const uint64_t a_desc = umma_smem_desc_sw128(h_addr + kb * 16384);
-                const uint64_t b_desc = umma_smem_desc_sw128(w_addr + kk * 8192);
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                  umma2_f16(tmem_base + kAcc1 + b * 128, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc1, (kb | k) != 0);
-              }
-              umma2_commit(&w_empty[st]);
-            }
-            umma2_commit(&acc1_full[b]);
-            ffn_trace(tb, ti, 3);
-            if (c == 7) umma2_commit(h_empty);                 // all FF1 MMAs of this unit issued: the H tiles may be refilled
-          } else {
-            if (c == 0) {
-              mbar_wait(acc2_empty, (lt & 1) ^ 1);              // both CTAs' output epilogues have drained acc2
-              tc_fence_after();
-            }
-            ffn_trace(tb, ti, 4);
-            mbar_wait(f_full, fcnt & 1);                        // GELU chunk c (16-bit) is in TMEM in both CTAs
-            ffn_trace(tb, ti, 5);
-            mbar_arrive(f_seen);                                // back-pressure (see ffn_fused.cu), relayed to the peer
-            mbar_arrive_rank(f_seen, 1);
-            tc_fence_after();
-            const uint32_t a_tmem = tmem_base + kAcc1 + (c & 1) * 128;
-            for (int kb = 0; kb < 2; kb++, wit++) {
-              const int st = wit % kSlots;
-              mbar_wait(&w_full[st], (wit / kSlots) & 1);
-              const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(smem + kOffW + st * kSlotBytes));
-#pragma unroll
-              for (int k = 0; k < 4; k++)
-                umma2_f16_ts(tmem_base + kAcc2, a_tmem + kb * 32 + k * 8, b_desc + (uint64_t)(k * 2), idesc2, (c | kb | k) != 0);
-              umma2_commit(&w_empty[st]);
-            }
-            fcnt++;
-            ffn_trace(tb, ti, 6);
-            if (c == 7) umma2_commit(acc2_full);
-          }
+        // schedule: FF1(0) FF1(1) | FF2(0) FF1(2) | FF2(1) FF1(3) | ... | FF2(5) FF1(7) | FF2(6) FF2(7)
+        ff1(0, false);
+        ff1(1, true);
+        mbar_wait(acc2_empty, (lt & 1) ^ 1);            // both CTAs' output epilogues have drained acc2
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 6; c++) {
+          ff2(c);
+          ff1(c + 2, true);
         }
+        umma2_commit(h_empty);                          // all FF1 MMAs of this unit issued: the H tiles may be refilled
+        ff2(6);
+        ff2(7);
+        umma2_commit(acc2_full);
         lt++;
       }
     }

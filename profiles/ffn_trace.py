@@ -23,7 +23,7 @@ flow.inference_batch(*args)          # every ffn launch overwrites the log: the 
 torch.cuda.synchronize()
 L.cv2_debug_set_ffn_trace(None)
 b = buf.cpu().numpy()
-names = {1: "tile start (mma)", 2: "H tile landed", 3: "FF1 issued", 4: "wait f_full", 5: "f_full seen", 6: "FF2 issued",
+names = {7: "  slot: wait w_full", 8: "  slot: w_full ok", 9: "  slot: 8 MMAs issued", 1: "tile start (mma)", 2: "H tile landed", 3: "FF1 issued", 4: "wait f_full", 5: "f_full seen", 6: "FF2 issued",
          10: "epi: wait acc1", 11: "epi: acc1 ready", 12: "epi: loaded+barrier", 13: "epi: gelu+st done", 14: "epi: arrived",
          20: "epi: chunks done", 21: "epi: acc2 ready", 22: "epi: tile done"}
 for off, who in ((0, "MMA thread"), (4096, "epilogue warp 2")):
@@ -33,6 +33,6 @@ for off, who in ((0, "MMA thread"), (4096, "epilogue warp 2")):
     t0 = ev[0][0]
     print(f"== {who}: {len(ev)} events")
     last = t0
-    for t, c in ev[:120]:
+    for t, c in ev[:200]:
         print(f"  {t - t0:8d}  (+{t - last:6d})  {names.get(c, c)}")
         last = t

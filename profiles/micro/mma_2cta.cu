@@ -19,8 +19,8 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
-template <int N>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k2(long long* out, int groups) {
+template <int N, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(576, 1) k2(long long* out, int groups) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
@@ -30,7 +30,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k2(long long
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  for (int i = threadIdx.x; i < 196608 / 4; i += 576) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   fence_proxy_async_smem();
   tc_fence_before();
   cluster_sync();
@@ -41,10 +41,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k2(long long
     const long long t0 = clock64();
     for (int r = 0; r < groups; r++) {
       const int st = r & 7;
-      const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(smem + (st & 3) * 4096));
-      const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(smem + 16384 + (st & 1) * 16384));
+      // MODE 0: small operand footprint (A 16 KB, B 32 KB), one accumulator
+      // MODE 1: FFN-like footprint: A walks a 64 KB tile (4 x 16 KB), B walks a 128 KB ring (8 x 16 KB)
+      // MODE 2: MODE 1 + the accumulator alternates between two TMEM regions every 4 groups (16 MMAs)
+      // MODE 3: MODE 0 + alternating accumulator
+      const uint32_t a_off = (MODE == 1 || MODE == 2 || MODE == 4) ? (uint32_t)(st & 3) * 16384u : (uint32_t)(st & 3) * 4096u;
+      const uint32_t b_off = (MODE == 1 || MODE == 2 || MODE == 4) ? 65536u + (uint32_t)st * 16384u : 16384u + (uint32_t)(st & 1) * 16384u;
+      const uint32_t d = (MODE == 2 || MODE == 3) ? tm + (((r >> 2) & 1) ? 256u : 0u) : tm;
+      const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(smem + a_off));
+      const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(smem + b_off));
 #pragma unroll
-      for (int kk = 0; kk < 4; kk++) umma2_f16(tm, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, 1);
+      for (int kk = 0; kk < 4; kk++) umma2_f16(d, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, 1);
     }
     umma2_commit_mc(&bar, 3);
     mbar_wait(&bar, 0);
@@ -52,27 +59,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k2(long long
     if (blockIdx.x == 0) out[0] = t1 - t0;
   } else if (rank == 1 && threadIdx.x == 0) {
     mbar_wait(&bar, 0);
+  } else if (MODE >= 4 && threadIdx.x >= 64) {
+    // 16 warps of dependent-free FMA work (the GELU epilogue's pressure on the schedulers) until the MMAs are done
+    float x0 = threadIdx.x, x1 = 1.f, x2 = 2.f, x3 = 3.f;
+    while (!mbar_try_wait(&bar, 0)) {
+#pragma unroll
+      for (int i = 0; i < 64; i++) {
+        x0 = fmaf(x0, 1.0001f, 0.5f); x1 = fmaf(x1, 0.9999f, 0.25f); x2 = fmaf(x2, 1.0002f, 0.125f); x3 = fmaf(x3, 0.9998f, 0.0625f);
+      }
+    }
+    if (x0 + x1 + x2 + x3 == 12345.f) out[1] = 1;
   }
   tc_fence_before();
   cluster_sync();
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
 }
-template <int N>
+template <int N, int MODE>
 void run(long long* d) {
-  cudaFuncSetAttribute(k2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  cudaFuncSetAttribute(k2<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608);
   const int groups = 20000;
-  for (int i = 0; i < 2; i++) k2<N><<<148, 128, 65536>>>(d, groups);
+  for (int i = 0; i < 2; i++) k2<N, MODE><<<148, 576, 196608>>>(d, groups);
   cudaError_t e = cudaDeviceSynchronize();
   long long h = 0;
   cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-  printf("cta_group::2 M=256 N=%3d group=4 (descriptors change per group): %.1f cycles per MMA (nominal %d), %.0f FLOP/clk/SM [%s]\n", N,
+  printf("cta_group::2 M=256 N=%3d mode %d: %.1f cycles per MMA (nominal %d), %.0f FLOP/clk/SM [%s]\n", N, MODE,
          (double)h / (4.0 * groups), N / 2, 2.0 * 128 * N * 16 * 4.0 * groups / (double)h, cudaGetErrorString(e));
 }
 int main() {
   long long* d;
-  cudaMalloc(&d, 8);
-  run<128>(d);
-  run<256>(d);
-  run<64>(d);
+  cudaMalloc(&d, 16);
+  run<128, 0>(d);
+  run<128, 1>(d);
+  run<128, 2>(d);
+  run<128, 3>(d);
+  run<256, 1>(d);
+  run<256, 2>(d);
+  run<128, 4>(d);
+  run<256, 4>(d);
   return 0;
 }
