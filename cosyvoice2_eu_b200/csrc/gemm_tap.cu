@@ -20,12 +20,12 @@ static constexpr int kTileM = 128;
 static constexpr int kKBlock = 64;                       // 64 x 16-bit = one 128B swizzle row
 static constexpr int kABytes = kTileM * kKBlock * 2;     // 16 KB
 
-template <int BN>
+template <int BN, int CS = 1>
 struct GemmSmem {
   static constexpr int kParts = BN >= 128 ? 4 : 2;        // column parts of a tile = epilogue warps per TMEM lane quarter
   static constexpr int kEpiWarps = 4 * kParts;            // 16 (8 for BN = 64): enough warps to hide TMEM / global / MUFU latency
   static constexpr int kThreads = 64 + kEpiWarps * 32;    // + TMA warp + MMA warp
-  static constexpr int kBBytes = BN * kKBlock * 2;
+  static constexpr int kBBytes = (BN / CS) * kKBlock * 2;   // CS = 2 (2-SM MMA): every CTA stages half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   // the GEMMs of this path are short-K (K = 256..1536) and TMA-latency bound: what matters is bytes in flight.  The epilogue
   // needs no shared memory (256-bit global accesses), so the ring takes all of it: 192 KB = 4 / 6 / 8 stages.
@@ -83,13 +83,16 @@ struct EpiCfg {
 using EpiGeneric = EpiCfg<-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1>;
 #define CFGB(field, rt) (Cfg::field < 0 ? (rt) : (Cfg::field != 0))
 
-// CS > 1: CTAs of a thread-block cluster work on CS row tiles of the same n tile and share the weight operand: each CTA loads
-// BN / CS rows of every B k-block and TMA-multicasts them into all CS shared memories (L2 -> SM traffic of B divided by CS; the
-// K = 256 estimator GEMMs are L2-bandwidth bound).  A stage is recycled when the MMAs of all CS CTAs have read it (multicast commit).
+// CS = 2: 2-SM form.  A cluster of two CTAs works on two row tiles of the same n tile; ONE thread (CTA rank 0) issues every MMA
+// for both SMs with tcgen05.mma.cta_group::2 (M = 256), each CTA stages its own A tile and HALF of every weight k-block (the
+// pair shares B), TMA bytes of both CTAs are credited to the leader's full barrier, the leader's commits are multicast to both
+// CTAs (stage free, accumulator full) and the peer's epilogue warps release accumulators on the leader's barrier.
+// Why: in cta_group::1 form these short-K GEMMs run the tensor pipe at ~55 % (issue path: profiles/micro/mma_bubble.cu); the
+// 2-SM form does twice the work per instruction and sustains the nominal rate (profiles/micro/mma_2cta.cu).
 template <int BN, class Cfg, int CS>
-__global__ void __launch_bounds__(GemmSmem<BN>::kThreads, 1)
+__global__ void __launch_bounds__(GemmSmem<BN, CS>::kThreads, 1)
 gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using SM = GemmSmem<BN>;
+  using SM = GemmSmem<BN, CS>;
   constexpr int kStages = SM::kStages;
   constexpr int kEpiWarps = SM::kEpiWarps;
   constexpr int kParts = SM::kParts;
@@ -110,25 +113,28 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int total_tiles = n_tiles * ((row_count + CS - 1) / CS);    // work units
   const int rank = CS > 1 ? (int)cluster_ctarank() : 0;
   const int unit0 = blockIdx.x / CS, unit_step = gridDim.x / CS;
-  constexpr uint16_t kMcMask = (uint16_t)((1u << CS) - 1);
+  const bool leader = rank == 0;
   constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // 128 / 256 / 512
 
   if (warp == kEpiWarps && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < kStages; i++) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CS);
+      mbar_init(&full_bar[i], 1);    // CS = 2: only the leader's is used (its producer expects the bytes of both CTAs)
+      mbar_init(&empty_bar[i], 1);   // CS = 2: multicast commit
     }
     for (int i = 0; i < 2; i++) {
-      mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kEpiWarps);
+      mbar_init(&tmem_full[i], 1);               // CS = 2: multicast commit
+      mbar_init(&tmem_empty[i], CS * kEpiWarps); // CS = 2: leader's, released by the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
-  if (warp == kEpiWarps + 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == kEpiWarps + 1) {
+    if (CS == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    else tmem_alloc2<kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  if (CS > 1) cluster_sync();   // peers multicast into this CTA's stages and arrive on its barriers: all must be initialised
+  if (CS > 1) cluster_sync();   // the peer signals this CTA's barriers: all must be initialised cluster-wide
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -149,17 +155,22 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int kb = it - tap * p.kb_per_tap;
           uint8_t* a_dst = smem + st * SM::kStageBytes;
           uint8_t* b_dst = a_dst + kABytes;
-          mbar_expect_tx(&full_bar[st], SM::kStageBytes);
-          tma_load_3d(a_dst, &tmA, &full_bar[st], kb * kKBlock, c.t0 + p.tap_off[tap], c.s + p.tap_seq[tap]);
-          if (CS == 1) tma_load_2d(b_dst, &tmB, &full_bar[st], it * kKBlock, c.n0);
-          else tma_load_2d_mc(b_dst + rank * (BN / CS) * 128, &tmB, &full_bar[st], it * kKBlock, c.n0 + rank * (BN / CS), kMcMask);
+          if (CS == 1) {
+            mbar_expect_tx(&full_bar[st], SM::kStageBytes);
+            tma_load_3d(a_dst, &tmA, &full_bar[st], kb * kKBlock, c.t0 + p.tap_off[tap], c.s + p.tap_seq[tap]);
+            tma_load_2d(b_dst, &tmB, &full_bar[st], it * kKBlock, c.n0);
+          } else {   // own A tile + own half of the weight k-block, bytes credited to the leader's barrier
+            if (leader) mbar_expect_tx(&full_bar[st], 2 * SM::kStageBytes);
+            tma2_load_3d(a_dst, &tmA, &full_bar[st], kb * kKBlock, c.t0 + p.tap_off[tap], c.s + p.tap_seq[tap]);
+            tma2_load_2d(b_dst, &tmB, &full_bar[st], it * kKBlock, c.n0 + rank * (BN / CS));
+          }
         }
       }
     }
   } else if (warp == kEpiWarps + 1) {
-    if (lane == 0) {
-      // ------------------------------- MMA issuer ---------------------------------
-      constexpr uint32_t idesc = umma_idesc_f16(kTileM, BN, 0);
+    if (lane == 0 && leader) {
+      // ------------------------------- MMA issuer (CS = 2: for both SMs) ----------
+      constexpr uint32_t idesc = umma_idesc_f16(CS * kTileM, BN, 0);
       int kit = 0, lt = 0;
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         TileCoord c;
@@ -178,12 +189,15 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
           const uint64_t b_desc = umma_smem_desc_sw128(a_addr + kABytes);
 #pragma unroll
-          for (int k = 0; k < kKBlock / 16; k++)
-            umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kKBlock / 16; k++) {
+            if (CS == 1) umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+            else umma2_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+          }
           if (CS == 1) umma_commit(&empty_bar[st]);
-          else umma_commit_mc(&empty_bar[st], kMcMask);
+          else umma2_commit(&empty_bar[st]);
         }
-        umma_commit(&tmem_full[acc]);
+        if (CS == 1) umma_commit(&tmem_full[acc]);
+        else umma2_commit(&tmem_full[acc]);
         lt++;
       }
     }
@@ -233,7 +247,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[lt & 1]);
+        if (lane == 0) mbar_arrive_leader(&tmem_empty[lt & 1]);
         lt++;
         continue;
       }
@@ -514,7 +528,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // release this accumulator buffer to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (CS == 1) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_leader(&tmem_empty[acc]);
+      }
       lt++;
     }
   }
@@ -522,7 +539,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_before();
   if (CS > 1) cluster_sync();   // no CTA may exit while a peer can still multicast into it or arrive on its barriers
   else __syncthreads();
-  if (warp == kEpiWarps + 1) tmem_dealloc<kTmemCols>(tmem_base);
+  if (warp == kEpiWarps + 1) {
+    if (CS == 1) tmem_dealloc<kTmemCols>(tmem_base);
+    else tmem_dealloc2<kTmemCols>(tmem_base);
+  }
 }
 
 // Compact list of the (sequence, t0) row tiles that contain at least one row < len + halo, in (s, t) order.
@@ -565,12 +585,12 @@ static void launch_cfg_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     CV2_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   if (!configured) {
-    CV2_CUDA(cudaFuncSetAttribute(gemm_tap_kernel<BN, Cfg, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
+    CV2_CUDA(cudaFuncSetAttribute(gemm_tap_kernel<BN, Cfg, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, CS>::kTotal));
     if (CS > 1) {
       cudaLaunchConfig_t q = {};
       q.gridDim = dim3(g_num_sms / CS * CS);
-      q.blockDim = dim3(GemmSmem<BN>::kThreads);
-      q.dynamicSmemBytes = GemmSmem<BN>::kTotal;
+      q.blockDim = dim3(GemmSmem<BN, CS>::kThreads);
+      q.dynamicSmemBytes = GemmSmem<BN, CS>::kTotal;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -590,8 +610,8 @@ static void launch_cfg_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     const int clusters = total < max_clusters ? total : max_clusters;
     cudaLaunchConfig_t q = {};
     q.gridDim = dim3(clusters * CS);
-    q.blockDim = dim3(GemmSmem<BN>::kThreads);
-    q.dynamicSmemBytes = GemmSmem<BN>::kTotal;
+    q.blockDim = dim3(GemmSmem<BN, CS>::kThreads);
+    q.dynamicSmemBytes = GemmSmem<BN, CS>::kTotal;
     q.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
