@@ -739,6 +739,238 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// v11: v9 as CTA pairs with 2-SM MMAs (tcgen05.mma.cta_group::2, M = 256).
+//   In cta_group::1 form the issue path costs ~115 cycles per MMA whatever its N (profiles/micro/mma_bubble.cu), so v9's eight
+//   N = 64 MMAs per 64-key tile and four CTAs per SM keep the SM's one tensor-issue path ~75 % busy: it, not the MUFU, was the
+//   limiter (s_full wait = a third of the softmax warps' time).  Here two CTAs of a cluster take two adjacent query tiles of
+//   the same (sequence, head); ONE thread issues S and PV for both (half the instructions per row), each CTA loads its own Q
+//   and HALF of every K / V^T tile (the pair shares the B operand), TMA bytes are credited to the leader's barriers, commits
+//   are multicast, and the softmax threads of both CTAs arrive on the leader's p_full.
+//   MEASURED: correct, but 364 us vs v9's 315 us at the bench shape -- the pair-wide p_full (256 threads on two SMs), the
+//   cross-SM barrier latencies and the filler tiles of odd tile counts cost more than the halved MMA count saves.  Kept as an
+//   experiment (CV2_ATTN_V11); v9 stays the default.
+// ---------------------------------------------------------------------------------------------------------
+static constexpr int k11Stages = 4;
+static constexpr int k11StageBytes = 8192;              // 32 keys x 64 d (K half) + 32 d x 64 keys (V^T half)
+static constexpr int k11OffKV = kQBytes;
+static constexpr int k11OffBar = k11OffKV + k11Stages * k11StageBytes;
+static constexpr int k11Smem = k11OffBar + 128;
+
+__global__ void __launch_bounds__(k9Threads, 4)
+flash_attn_v11_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  const uint32_t rank = cluster_ctarank();          // == blockIdx.x & 1
+  const bool leader = rank == 0;
+  const int t0_pair = (blockIdx.x >> 1) * 256;
+  const int t0 = t0_pair + (int)rank * 128;
+  const int h = blockIdx.y;
+  // blocks are dispatched in blockIdx.z order: walking the sequences backwards puts the longest ones first when the caller
+  // sorted the batch by ascending length (length bucketing), so the last wave is made of short CTAs
+  const int s = p.reverse_seq ? p.S - 1 - (int)blockIdx.z : (int)blockIdx.z;
+  const int len = p.lens ? p.lens[s] : p.len_all;
+  if (t0_pair >= len + p.halo) return;               // pair-uniform: both CTAs leave together
+  const int sh = s * p.heads + h;
+  int kv_end = len;
+  if (p.chunk > 0) kv_end = min(len, ((t0_pair + 255) / p.chunk + 1) * p.chunk);   // both CTAs walk the same key tiles
+  const int nkt = (kv_end + kKT - 1) / kKT;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k11OffBar);
+  uint64_t* q_full = bars;                      // 1
+  uint64_t* kv_full = bars + 1;                 // [k11Stages]
+  uint64_t* kv_empty = kv_full + k11Stages;      // [k11Stages]
+  uint64_t* s_full = kv_empty + k11Stages;       // 1
+  uint64_t* p_full = s_full + 1;                // 1 (128 arrivals)
+  uint64_t* o_done = p_full + 1;                // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < k11Stages; i++) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);      // multicast commit
+    mbar_init(p_full, 256);    // leader's: the softmax threads of both CTAs
+    mbar_init(o_done, 1);      // multicast commit
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc2<128>(tmem_slot);
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // both CTAs: own Q tile, own half of every K / V^T tile; bytes credited to the leader's barriers
+      if (leader) mbar_expect_tx(q_full, 2 * kQBytes);
+      tma2_load_3d(smem, &tmQ, q_full, 0, t0, sh);
+      for (int j = 0; j < nkt; j++) {
+        const int st = j % k11Stages;
+        const uint32_t ph = (j / k11Stages) & 1;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        if (leader) mbar_expect_tx(&kv_full[st], 2 * k11StageBytes);
+        tma2_load_3d(smem + k11OffKV + st * k11StageBytes, &tmK, &kv_full[st], 0, j * kKT + (int)rank * 32, sh);        // 32 keys x 64 d
+        tma2_load_3d(smem + k11OffKV + st * k11StageBytes + 4096, &tmV, &kv_full[st], j * kKT, (int)rank * 32, sh);     // 32 d x 64 keys
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(256, kKT, 0);   // both q tiles x 64 keys
+      constexpr uint32_t idesc_o = umma_idesc_f16(256, 64, 0);
+      const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(smem));
+      auto issue_s = [&](int j) {
+        const int st = j % k11Stages;
+        mbar_wait(&kv_full[st], (j / k11Stages) & 1);
+        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(smem + k11OffKV + st * k11StageBytes));
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          umma2_f16(tmem_base + k9TmemS, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0);
+        umma2_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nkt; j++) {
+        mbar_wait(p_full, j & 1);   // the softmax threads of both CTAs have replaced S_j by P_j in tensor memory
+        tc_fence_after();
+        const int st = j % k11Stages;
+        const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(smem + k11OffKV + st * k11StageBytes + 4096));
+#pragma unroll
+        for (int k = 0; k < kKT / 16; k++)
+          umma2_f16_ts(tmem_base + k9TmemO, tmem_base + k9TmemS + k * 8, v_desc + (uint64_t)(k * 2), idesc_o, (j | k) != 0);
+        umma2_commit(&kv_empty[st]);
+        if (j + 1 < nkt) issue_s(j + 1);   // in order behind PV(j): S_{j+1} overwrites P_j only after it was consumed
+        else umma2_commit(o_done);
+      }
+    }
+  } else {
+    const int r = warp * 32 + lane;
+    const int t = t0 + r;
+    int kv_lim = len;
+    if (p.chunk > 0) kv_lim = min(len, (t / p.chunk + 1) * p.chunk);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const float LOG2E = 1.4426950408889634f;
+    float mref = 0.f, l = 0.f;     // reference max in log2 units
+    for (int j = 0; j < nkt; j++) {
+      mbar_wait(s_full, j & 1);     // also implies PV(j-1) has completed (same in-order pipe, commit covers prior MMAs)
+      tc_fence_after();
+      const int kbase = j * kKT;
+      const bool edge = kbase + kKT > kv_lim;
+      uint32_t sa[32];
+      // pass 1: row maximum
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        tmem_ld32(lane_addr + k9TmemS + c * 32, sa);
+        tmem_ld_wait();
+        if (edge) {
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            if (kbase + c * 32 + i >= kv_lim) sa[i] = 0xff800000u;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sa[i]), __uint_as_float(sa[i + 4])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sa[i + 1]), __uint_as_float(sa[i + 5])));
+          mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sa[i + 2]), __uint_as_float(sa[i + 6])));
+          mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sa[i + 3]), __uint_as_float(sa[i + 7])));
+        }
+      }
+      const float mxl = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * LOG2E;
+      float alpha = 1.f;
+      if (j == 0) {
+        mref = mxl;
+      } else if (mxl > mref + 8.f) {
+        alpha = fast_exp2(mref - mxl);
+        mref = mxl;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          tmem_ld32(lane_addr + k9TmemO + c * 32, sa);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) sa[i] = __float_as_uint(__uint_as_float(sa[i]) * alpha);
+          tmem_st32(lane_addr + k9TmemO + c * 32, sa);
+        }
+        l *= alpha;
+      }
+      // pass 2: probabilities; P chunk c (16 columns) lands on S columns [16c, 16c+16), all consumed by then
+      float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        tmem_ld32(lane_addr + k9TmemS + c * 32, sa);
+        tmem_ld_wait();
+        if (edge) {
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            if (kbase + c * 32 + i >= kv_lim) sa[i] = 0xff800000u;
+        }
+        uint32_t pk[16];
+        const float2 sc2 = make_float2(LOG2E, LOG2E), nm2 = make_float2(-mref, -mref);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {   // packed fp32 pairs: one FFMA2 / FADD2 per two logits
+          const float2 x01 = ffma2(make_float2(__uint_as_float(sa[i]), __uint_as_float(sa[i + 1])), sc2, nm2);
+          const float2 x23 = ffma2(make_float2(__uint_as_float(sa[i + 2]), __uint_as_float(sa[i + 3])), sc2, nm2);
+          const float2 e01 = make_float2(fast_exp2(x01.x), fast_exp2(x01.y));
+          const float2 e23 = make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
+          la = fadd2(la, e01);
+          lb = fadd2(lb, e23);
+          __half2 h0 = __floats2half2_rn(e01.x, e01.y), h1 = __floats2half2_rn(e23.x, e23.y);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h0);
+          pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+        }
+        tmem_st16(lane_addr + k9TmemS + c * 16, pk);
+      }
+      l += (la.x + la.y) + (lb.x + lb.y);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_leader(p_full);
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    mbar_wait(o_done, 0);
+    tc_fence_after();
+    __half* dst = p.out + ((long long)s * p.T_alloc + t) * (p.heads * 64) + h * 64;
+    const bool valid = t < len;
+    const bool in_tensor = t < p.T_alloc;   // (an odd tile count is padded with a filler CTA)
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      uint32_t raw[32];
+      tmem_ld32(lane_addr + k9TmemO + c * 32, raw);
+      tmem_ld_wait();
+      uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) f[e] = valid ? __uint_as_float(raw[i * 8 + e]) * inv : 0.f;
+        __half2 h0 = __floats2half2_rn(f[0], f[1]);
+        __half2 h1 = __floats2half2_rn(f[2], f[3]);
+        __half2 h2 = __floats2half2_rn(f[4], f[5]);
+        __half2 h3 = __floats2half2_rn(f[6], f[7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2);
+        u.w = *reinterpret_cast<uint32_t*>(&h3);
+        if (in_tensor) d4[i] = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 5) tmem_dealloc2<128>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // v10: v9 with the logits double-buffered inside the same 128 TMEM columns.
 //   The v9 profile has the softmax warps waiting for S a third of the time (S(j+1) sits behind PV(j) because P_j lives
 //   on top of S_j).  Here the softmax step is 32 keys: S0 [0,32), S1 [32,64), O [64,128); S(jj+2) is issued right behind
@@ -950,6 +1182,38 @@ flash_attn_v10_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (warp == 5) tmem_dealloc<128>(tmem_base);
 }
 
+static void launch_flash_attn_v11(const AttnParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    CV2_CUDA(cudaFuncSetAttribute(flash_attn_v11_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k11Smem));
+    configured = true;
+  }
+  const uint64_t SH = (uint64_t)p.S * p.heads;
+  uint64_t dq[3] = {64, (uint64_t)p.T_alloc, SH};
+  uint64_t sq[2] = {128, (uint64_t)p.T_alloc * 128};
+  uint32_t bq[3] = {64, 128, 1};
+  uint32_t bk[3] = {64, 32, 1};                          // this CTA's 32 of the tile's 64 keys
+  CUtensorMap tmQ = make_tmap_16b(p.q, 3, dq, sq, bq);
+  CUtensorMap tmK = make_tmap_16b(p.k, 3, dq, sq, bk);
+  uint64_t dv[3] = {(uint64_t)p.T_alloc, 64, SH};
+  uint64_t sv[2] = {(uint64_t)p.T_alloc * 2, (uint64_t)p.T_alloc * 128};
+  uint32_t bv[3] = {(uint32_t)kKT, 32, 1};               // this CTA's 32 of the 64 head-dim rows of V^T
+  CUtensorMap tmV = make_tmap_16b(p.vt, 3, dv, sv, bv);
+  const int qt = p.T_alloc / 128;
+  cudaLaunchConfig_t q = {};
+  q.gridDim = dim3((qt + 1) / 2 * 2, p.heads, p.S);
+  q.blockDim = dim3(k9Threads);
+  q.dynamicSmemBytes = k11Smem;
+  q.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  q.attrs = at;
+  q.numAttrs = 1;
+  CV2_CUDA(cudaLaunchKernelEx(&q, flash_attn_v11_kernel, tmQ, tmK, tmV, p));
+  CV2_LAUNCH_CHECK();
+}
+
 static void launch_flash_attn_v9(const AttnParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
@@ -986,7 +1250,9 @@ void launch_flash_attn(const AttnParams& p, cudaStream_t stream) {
   CV2_CHECK(p.T_alloc % 128 == 0, "attention: T_alloc %d not a multiple of 128", p.T_alloc);
   static const bool use_v6 = getenv("CV2_ATTN_V6") != nullptr;   // two threads per row, P through smem, 2 CTAs/SM
   static const bool use_v8 = getenv("CV2_ATTN_V8") != nullptr;   // one thread per row, P in TMEM, S double-buffered, 2 CTAs/SM
+  static const bool use_v11 = getenv("CV2_ATTN_V11") != nullptr;   // 2-SM pairing of v9: measured 16 % slower (364 vs 315 us)
   if (use_v8) return launch_flash_attn_v8(p, stream);
+  if (use_v11) return launch_flash_attn_v11(p, stream);
   if (!use_v6) return launch_flash_attn_v9(p, stream);
   static bool configured = false;
   if (!configured) {
