@@ -413,6 +413,23 @@ def main():
                 gbs = samples * bps / (fam[k]["ms_per_step"] / fam[k]["launches_per_step"] * 1e-3) / 1e9
                 hbm_kernels[k] = {"algorithmic_bytes_per_sample": bps, "ms_per_launch": fam[k]["ms_per_step"] / fam[k]["launches_per_step"],
                                   "achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": gbs / hbm_peak}
+        # the copy figure is a read+write mix; the STFT is 82 % writes and the iSTFT 82 % reads, so also measure one-directional
+        # streams on this box (1 GiB fill / 1 GiB sum reduction, best of 5, CUDA events)
+        try:
+            buf = torch.empty(1 << 28, dtype=torch.float32, device=dev)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            wr, rd = [], []
+            for _ in range(5):
+                ev0.record(); buf.fill_(1.0); ev1.record(); torch.cuda.synchronize(); wr.append(buf.numel() * 4 / ev0.elapsed_time(ev1) / 1e6)
+                ev0.record(); buf.sum(); ev1.record(); torch.cuda.synchronize(); rd.append(buf.numel() * 4 / ev0.elapsed_time(ev1) / 1e6)
+            del buf
+            hbm_kernels["one_directional_peaks_gbs_measured_here"] = {"write_only_fill": max(wr), "read_only_sum": max(rd)}
+            if "source_stft" in hbm_kernels:
+                hbm_kernels["source_stft"]["frac_of_write_only"] = hbm_kernels["source_stft"]["achieved_gbs"] / max(wr)
+            if "istft" in hbm_kernels:
+                hbm_kernels["istft"]["frac_of_read_only"] = hbm_kernels["istft"]["achieved_gbs"] / max(rd)
+        except Exception as exc:   # never let the side measurement break the bench line
+            hbm_kernels["one_directional_peaks_gbs_measured_here"] = {"error": str(exc)}
         hbm_kernels["note"] = ("peak = measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs); nsf_source in production mode draws its "
                                "noise in-kernel (9 sines + 9 normals per 4-byte sample), i.e. it is ALU/MUFU bound there and only "
                                "bandwidth bound in parity mode (36 B/sample noise read)")

@@ -277,7 +277,7 @@ void hift_init_tables() { ensure_tables(); }
 __global__ void __launch_bounds__(256) source_stft_kernel(const float* __restrict__ src, long long src_bstride,
                                                           const int* __restrict__ lens, int len_all, float* __restrict__ out,
                                                           int F_alloc) {
-  __shared__ float xs[4 * 256 + 16];
+  __shared__ __align__(16) float xs[4 * 256 + 16];
   __shared__ __align__(16) float os[256 * 18];
   const int b = blockIdx.y;
   const int f0 = blockIdx.x * 256;
@@ -302,15 +302,31 @@ __global__ void __launch_bounds__(256) source_stft_kernel(const float* __restric
   if (f < F) {
     float x[16];
 #pragma unroll
-    for (int n = 0; n < 16; n++) x[n] = xs[4 * threadIdx.x + n] * c_hann16[n];
+    for (int q4 = 0; q4 < 4; q4++) {   // 16-byte aligned, conflict-free shared loads
+      const float4 v4 = *reinterpret_cast<const float4*>(xs + 4 * threadIdx.x + 4 * q4);
+      x[4 * q4 + 0] = v4.x * c_hann16[4 * q4 + 0];
+      x[4 * q4 + 1] = v4.y * c_hann16[4 * q4 + 1];
+      x[4 * q4 + 2] = v4.z * c_hann16[4 * q4 + 2];
+      x[4 * q4 + 3] = v4.w * c_hann16[4 * q4 + 3];
+    }
+    // real-input symmetry: with a[n] = x[n] + x[16-n], b[n] = x[n] - x[16-n] (n = 1..7),
+    //   Re X[k] = x[0] + (-1)^k x[8] + sum_n a[n] cos(2 pi k n / 16),   Im X[k] = - sum_n b[n] sin(2 pi k n / 16)
+    // 112 multiply-adds per frame instead of the direct form's 288
+    float a[8], bb[8];
+#pragma unroll
+    for (int n = 1; n < 8; n++) {
+      a[n] = x[n] + x[16 - n];
+      bb[n] = x[n] - x[16 - n];
+    }
 #pragma unroll
     for (int k = 0; k < 9; k++) {
-      float re = 0.f, im = 0.f;
+      float re = x[0] + ((k & 1) ? -x[8] : x[8]);
+      float im = 0.f;
 #pragma unroll
-      for (int n = 0; n < 16; n++) {
+      for (int n = 1; n < 8; n++) {
         const int idx = (k * n) & 15;
-        re += x[n] * c_cos16[idx];
-        im -= x[n] * c_sin16[idx];
+        re = fmaf(a[n], c_cos16[idx], re);
+        if (k > 0 && k < 8) im = fmaf(-bb[n], c_sin16[idx], im);
       }
       o[k] = re;
       o[9 + k] = im;
@@ -456,7 +472,8 @@ __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp
 #pragma unroll
       for (int k = 0; k < 9; k++) {
         const float mag = fminf(__expf(cv[k]), 100.f);
-        const float ph = sinf(cv[9 + k]);      // |ph| <= 1: the fast sincos below is exact to 2^-21 there
+        const float ph = __sinf(cv[9 + k]);    // MUFU sine: abs error ~1e-6 on the conv_post phase logits (|x| of a few units),
+                                               // six orders below the 35 dB parity budget; |ph| <= 1 for the sincos below
         float sn, cs;
         __sincosf(ph, &sn, &cs);
         Xre[e][k] = mag * cs;

@@ -317,3 +317,26 @@ def test_cfg3_full_size_properties(engine):
         assert tuple(mel_1.shape) == (1, 80, n)
         assert d < 1e-4
         assert s > 60
+
+
+def test_2sm_kernels_match_1sm_kernels(engine, golden):
+    """The 2-SM forms (tcgen05.mma.cta_group::2: fused FFN as CTA pairs, BN=256 GEMMs as CTA pairs) against the 1-SM kernels they
+    replace on big launches: same contraction order per output, so the mel must agree to rounding noise; both within tolerance of
+    the golden mel.  (Small launches always take the 1-SM kernels, so this runs a batch large enough to switch paths.)"""
+    flow = engine[0]
+    lib = flow.eng.lib
+    utts = [_utt(dict(n_tok=240 + 3 * i, n_prompt=60, seed=40 + i)) for i in range(16)]    # 32 sequences x 5 tiles = 160 >= 148
+    args = ([u["token"][0] for u in utts], [u["prompt_token"][0] for u in utts], [u["prompt_feat"][0] for u in utts],
+            [u["embedding"][0] for u in utts])
+    mel_2sm = flow.inference_batch(*args)[0].cpu().numpy()
+    for name in (b"ffn_2cta", b"cluster_mc"):
+        assert lib.cv2_engine_set_option(flow.eng.h, name, 0) == 0
+    try:
+        mel_1sm = flow.inference_batch(*args)[0].cpu().numpy()
+    finally:
+        for name in (b"ffn_2cta", b"cluster_mc"):
+            lib.cv2_engine_set_option(flow.eng.h, name, 1)
+    d = np.abs(mel_2sm - mel_1sm).max()
+    print("2-SM vs 1-SM kernels: max-abs mel diff", d, "mel std", mel_1sm.std())
+    assert np.isfinite(mel_2sm).all()
+    assert d < 2e-3
