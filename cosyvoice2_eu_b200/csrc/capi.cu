@@ -6,6 +6,7 @@
 #include "engine.h"
 #include "flow_kernels.cuh"
 #include "hift_kernels.cuh"
+#include "prompt_mel.cuh"
 
 using namespace cv2;
 
@@ -272,6 +273,18 @@ int cv2_hift_forward_pcm16(cv2_engine* h, void* stream, const float* mel, int me
 int cv2_crossfade(void* stream, float* speech, const float* old_tail, const double* window, int n) {
   CV2_API_BEGIN
   launch_crossfade(speech, old_tail, window, n, (cudaStream_t)stream);
+  CV2_API_END
+}
+
+int cv2_prompt_mel_frames(int n_samples) { return prompt_mel_frames(n_samples); }
+
+size_t cv2_prompt_mel_workspace_bytes(int B, int max_samples) { return prompt_mel_workspace_bytes(B, max_samples); }
+
+int cv2_prompt_mel(void* stream, const float* wav, long long wav_stride, const int32_t* n_samples, int B, int max_samples,
+                   float* mel, int32_t* mel_len, void* workspace, size_t workspace_bytes) {
+  CV2_API_BEGIN
+  CV2_CHECK(wav && n_samples && mel && workspace, "cv2_prompt_mel: null pointer");
+  launch_prompt_mel(wav, wav_stride, n_samples, B, max_samples, mel, mel_len, workspace, workspace_bytes, (cudaStream_t)stream);
   CV2_API_END
 }
 

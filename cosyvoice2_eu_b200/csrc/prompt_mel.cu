@@ -1,0 +1,289 @@
+// Prompt log-mel front end: the reference's `mel_spectrogram`
+// (third_party/Matcha-TTS/matcha/utils/audio.py:45-82) at the cosyvoice2.yaml:152-160 settings -- n_fft = win = 1920, hop 480,
+// 80 Slaney mels over [0, 8000] Hz at 24 kHz, reflect pad 720, centre = False, log(clamp(., 1e-5)) -- for a batch of prompts.
+//
+// fp32 throughout (the result is a log spectrum; 16-bit operands are not an option).  The 1920-point real DFT of a frame is
+// evaluated as a dense fp32 contraction with K halved by the symmetry of the (periodic Hann) window, w[n] = w[N - n]:
+//     Re X[k] = sum_{n=0}^{960} e[n] cos(2 pi k n / N),   Im X[k] = -sum_{n=1}^{959} o[n] sin(2 pi k n / N),
+//     e[n] = w[n] (x[n] + x[N - n]),  o[n] = w[n] (x[n] - x[N - n])   (n = 1..959),   e[0] = w[0] x[0],  e[960] = w[960] x[960],
+// so one frame costs 2 x 961 x 961 FMAs instead of 2 x 1920 x 961.  `pm_dft_mag_kernel` is a 64 frames x 64 bins register-tiled
+// SGEMM whose A tile is folded on the fly from the waveform (reflect indexing + window), whose B tile is an exact (cos, sin)
+// table (argument reduced in integers, evaluated in fp64 once per device) and whose inner product is packed
+// `fma.rn.f32x2` on (re, im) pairs; its epilogue writes |X| = sqrt(re^2 + im^2 + 1e-9).  `pm_mel_log_kernel` applies the 80
+// triangular filters (compact per-band weights) and the clamped log, writing [B, T, 80] -- the layout `flow.inference` takes.
+#include <math.h>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "host_util.h"
+#include "prompt_mel.cuh"
+
+namespace cv2 {
+
+namespace {
+
+constexpr int kNfft = 1920, kHop = 480, kPad = 720, kBins = 961, kMels = 80;
+constexpr int kKfold = 961;        // folded contraction length (n = 0..960)
+constexpr int kKpad = 976;         // padded to a multiple of the k step
+constexpr int kBinsPad = 1024;     // table / spectrum row length
+constexpr int kBandMax = 64;       // widest mel band in bins (top band: 49)
+constexpr int kTM = 64, kTN = 64, kTK = 16;
+
+struct Tables {
+  float2* cs = nullptr;     // [kKpad][kBinsPad] (cos, sin)(2 pi n k / N); zero outside n < 961, k < 961
+  float* win = nullptr;     // [kKpad] periodic Hann, zero for n > 960
+  float* mel_w = nullptr;   // [kBandMax][kMels] band weights, j-th bin of band m at [j][m]
+  int* mel_lo = nullptr;    // [kMels] first bin of the band
+  int* mel_cnt = nullptr;   // [kMels] bins in the band
+};
+
+__global__ void pm_table_kernel(float2* cs, float* win) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (k >= kBinsPad) return;
+  float2 v = make_float2(0.f, 0.f);
+  if (n < kKfold && k < kBins) {
+    const int m = (int)(((long long)n * k) % kNfft);           // exact argument reduction
+    double s, c;
+    sincospi(2.0 * (double)m / (double)kNfft, &s, &c);
+    v = make_float2((float)c, (float)s);
+  }
+  cs[(size_t)n * kBinsPad + k] = v;
+  if (k == 0) win[n] = n < kKfold ? (float)(0.5 - 0.5 * cospi(2.0 * (double)n / (double)kNfft)) : 0.f;
+}
+
+// reflect padding needs more than kPad samples (the reference raises below that): such a row yields no frames
+__device__ __forceinline__ int frames_of(int n_samples) { return n_samples <= kPad ? 0 : (n_samples - kHop) / kHop + 1; }
+
+__device__ __forceinline__ float wave_reflect(const float* __restrict__ w, int i, int L) {
+  i = i < 0 ? -i : i;                  // left reflect pad (no edge repeat)
+  i = i >= L ? 2 * (L - 1) - i : i;    // right reflect pad
+  return __ldg(w + i);
+}
+
+// grid (frame tiles, bin tiles, B), 256 threads; thread (ty, tx) owns frames ty*4..+3 and bins tx*4..+3 of the tile.
+__global__ void __launch_bounds__(256) pm_dft_mag_kernel(const float* __restrict__ wav, long long wav_stride,
+                                                         const int* __restrict__ n_samples, const float2* __restrict__ cs,
+                                                         const float* __restrict__ win, float* __restrict__ spec, int T_alloc) {
+  __shared__ __align__(16) float2 As[2][kTK][kTM];    // (e, o)
+  __shared__ __align__(16) float2 Bs[2][kTK][kTN];    // (cos, sin)
+  const int b = blockIdx.z;
+  const int L = __ldg(n_samples + b);
+  const int T = frames_of(L);
+  const int t0 = blockIdx.x * kTM;
+  if (t0 >= T) return;
+  const int k0 = blockIdx.y * kTN;
+  const float* w = wav + (long long)b * wav_stride;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int lf = tid & 63, lk = tid >> 6;     // A loader: frame fastest (conflict-free smem stores), 4 k rows per pass
+  const int bk = tid >> 4, bn = (tid & 15) * 4;  // B loader: one k row, 4 bins
+
+  float2 acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.f, 0.f);
+
+  float2 ra[4];
+  float4 rb[2];
+  auto fetch = [&](int kb) {
+    const int base = (t0 + lf) * kHop - kPad;      // first sample of the frame in the unpadded signal
+    const bool live = t0 + lf < T;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int n = kb + lk + 4 * i;
+      float e = 0.f, o = 0.f;
+      if (live && n < kKfold) {
+        const float wn = __ldg(win + n);
+        const float a = wave_reflect(w, base + n, L) * wn;
+        if (n == 0 || n == kNfft / 2) {
+          e = a;
+        } else {
+          const float c = wave_reflect(w, base + kNfft - n, L) * wn;
+          e = a + c;
+          o = a - c;
+        }
+      }
+      ra[i] = make_float2(e, o);
+    }
+    const float4* src = reinterpret_cast<const float4*>(cs + (size_t)(kb + bk) * kBinsPad + k0 + bn);
+    rb[0] = __ldg(src);
+    rb[1] = __ldg(src + 1);
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) As[buf][lk + 4 * i][lf] = ra[i];
+    float4* dst = reinterpret_cast<float4*>(&Bs[buf][bk][bn]);
+    dst[0] = rb[0];
+    dst[1] = rb[1];
+  };
+
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  constexpr int kSteps = kKpad / kTK;
+  for (int s = 0; s < kSteps; s++) {
+    const int buf = s & 1;
+    if (s + 1 < kSteps) fetch((s + 1) * kTK);
+#pragma unroll
+    for (int kk = 0; kk < kTK; kk++) {
+      const float4 a01 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a23 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4 + 2]);
+      const float4 b01 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b23 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4 + 2]);
+      const float2 a[4] = {make_float2(a01.x, a01.y), make_float2(a01.z, a01.w), make_float2(a23.x, a23.y), make_float2(a23.z, a23.w)};
+      const float2 bb[4] = {make_float2(b01.x, b01.y), make_float2(b01.z, b01.w), make_float2(b23.x, b23.y), make_float2(b23.z, b23.w)};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = ffma2(a[i], bb[j], acc[i][j]);
+    }
+    if (s + 1 < kSteps) {
+      stash(buf ^ 1);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int t = t0 + ty * 4 + i;
+    if (t >= T) continue;
+    float4 m;
+    m.x = sqrtf(acc[i][0].x * acc[i][0].x + acc[i][0].y * acc[i][0].y + 1e-9f);
+    m.y = sqrtf(acc[i][1].x * acc[i][1].x + acc[i][1].y * acc[i][1].y + 1e-9f);
+    m.z = sqrtf(acc[i][2].x * acc[i][2].x + acc[i][2].y * acc[i][2].y + 1e-9f);
+    m.w = sqrtf(acc[i][3].x * acc[i][3].x + acc[i][3].y * acc[i][3].y + 1e-9f);
+    *reinterpret_cast<float4*>(spec + ((size_t)b * T_alloc + t) * kBinsPad + k0 + tx * 4) = m;
+  }
+}
+
+// one block of 128 threads per 4 frames: the spectrum rows go through shared memory, thread m < 80 owns one band per frame
+__global__ void __launch_bounds__(128) pm_mel_log_kernel(const float* __restrict__ spec, int T_alloc, const int* __restrict__ n_samples,
+                                                         const float* __restrict__ mel_w, const int* __restrict__ mel_lo,
+                                                         const int* __restrict__ mel_cnt, float* __restrict__ mel, int T_out,
+                                                         int* __restrict__ mel_len) {
+  __shared__ float row[4][kBinsPad];
+  const int b = blockIdx.y;
+  const int T = frames_of(__ldg(n_samples + b));
+  const int t0 = blockIdx.x * 4;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && mel_len) mel_len[b] = T;
+  if (t0 >= T_out) return;
+  for (int f = 0; f < 4; f++) {
+    const int t = t0 + f;
+    if (t < T)
+      for (int k = threadIdx.x; k < kBinsPad; k += 128) row[f][k] = spec[((size_t)b * T_alloc + t) * kBinsPad + k];
+  }
+  __syncthreads();
+  const int m = threadIdx.x;
+  if (m >= kMels) return;
+  const int lo = __ldg(mel_lo + m), cnt = __ldg(mel_cnt + m);
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < cnt; j++) {
+    const float wj = __ldg(mel_w + j * kMels + m);
+#pragma unroll
+    for (int f = 0; f < 4; f++) s[f] = fmaf(wj, row[f][lo + j], s[f]);
+  }
+#pragma unroll
+  for (int f = 0; f < 4; f++) {
+    const int t = t0 + f;
+    if (t >= T_out) break;
+    mel[((size_t)b * T_out + t) * kMels + m] = t < T ? logf(fmaxf(s[f], 1e-5f)) : 0.f;   // audio.py:22-23; padding rows are zero
+  }
+}
+
+// librosa.filters.mel(sr=24000, n_fft=1920, n_mels=80, fmin=0, fmax=8000), Slaney scale + Slaney norm, float32 (audio.py:52)
+double hz_to_mel(double f) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+  return f >= min_log_hz ? min_log_mel + log(f / min_log_hz) / logstep : f / f_sp;
+}
+double mel_to_hz(double m) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+  return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+void build_mel(std::vector<float>& w, std::vector<int>& lo, std::vector<int>& cnt) {
+  const double sr = 24000.0, f_lo = 0.0, f_hi = 8000.0;
+  std::vector<double> mel_f(kMels + 2);
+  const double m0 = hz_to_mel(f_lo), m1 = hz_to_mel(f_hi);
+  for (int i = 0; i < kMels + 2; i++) mel_f[i] = mel_to_hz(m0 + (m1 - m0) * (double)i / (double)(kMels + 1));
+  w.assign((size_t)kBandMax * kMels, 0.f);
+  lo.assign(kMels, 0);
+  cnt.assign(kMels, 0);
+  for (int m = 0; m < kMels; m++) {
+    const double enorm = 2.0 / (mel_f[m + 2] - mel_f[m]);
+    int first = -1, last = -1;
+    std::vector<float> full(kBins);
+    for (int k = 0; k < kBins; k++) {
+      const double f = (sr / 2.0) * (double)k / (double)(kBins - 1);
+      const double lower = (f - mel_f[m]) / (mel_f[m + 1] - mel_f[m]);
+      const double upper = (mel_f[m + 2] - f) / (mel_f[m + 2] - mel_f[m + 1]);
+      const double lu = lower < upper ? lower : upper;
+      const float tri = (float)(lu > 0.0 ? lu : 0.0);   // float32 array, then *= enorm in place
+      full[k] = (float)((double)tri * enorm);
+      if (full[k] != 0.f) {
+        if (first < 0) first = k;
+        last = k;
+      }
+    }
+    if (first < 0) continue;
+    CV2_CHECK(last - first + 1 <= kBandMax, "mel band %d spans %d bins", m, last - first + 1);
+    lo[m] = first;
+    cnt[m] = last - first + 1;
+    for (int j = 0; j < cnt[m]; j++) w[(size_t)j * kMels + m] = full[first + j];
+  }
+}
+
+Tables& tables_for_device() {
+  static std::mutex mu;
+  static Tables tab[64];
+  int dev = 0;
+  CV2_CUDA(cudaGetDevice(&dev));
+  CV2_CHECK(dev >= 0 && dev < 64, "device index %d", dev);
+  std::lock_guard<std::mutex> g(mu);
+  Tables& t = tab[dev];
+  if (t.cs) return t;
+  std::vector<float> w;
+  std::vector<int> lo, cnt;
+  build_mel(w, lo, cnt);
+  CV2_CUDA(cudaMalloc(&t.win, kKpad * sizeof(float)));
+  CV2_CUDA(cudaMalloc(&t.mel_w, w.size() * sizeof(float)));
+  CV2_CUDA(cudaMalloc(&t.mel_lo, kMels * sizeof(int)));
+  CV2_CUDA(cudaMalloc(&t.mel_cnt, kMels * sizeof(int)));
+  CV2_CUDA(cudaMemcpy(t.mel_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CV2_CUDA(cudaMemcpy(t.mel_lo, lo.data(), kMels * sizeof(int), cudaMemcpyHostToDevice));
+  CV2_CUDA(cudaMemcpy(t.mel_cnt, cnt.data(), kMels * sizeof(int), cudaMemcpyHostToDevice));
+  float2* cs = nullptr;
+  CV2_CUDA(cudaMalloc(&cs, (size_t)kKpad * kBinsPad * sizeof(float2)));
+  pm_table_kernel<<<dim3(kBinsPad / 256, kKpad), 256>>>(cs, t.win);
+  CV2_CUDA(cudaGetLastError());
+  CV2_CUDA(cudaDeviceSynchronize());
+  t.cs = cs;
+  return t;
+}
+
+}  // namespace
+
+int prompt_mel_frames(int n_samples) { return n_samples <= kPad ? 0 : (n_samples - kHop) / kHop + 1; }
+
+static int t_alloc_of(int max_samples) { return (prompt_mel_frames(max_samples) + kTM - 1) / kTM * kTM; }
+
+size_t prompt_mel_workspace_bytes(int B, int max_samples) {
+  return (size_t)B * t_alloc_of(max_samples) * kBinsPad * sizeof(float);
+}
+
+void launch_prompt_mel(const float* wav, long long wav_stride, const int* n_samples, int B, int max_samples, float* mel,
+                       int* mel_len, void* ws, size_t ws_bytes, cudaStream_t st) {
+  CV2_CHECK(B > 0 && max_samples > kPad, "prompt_mel: reflect padding needs more than %d samples (got %d)", kPad, max_samples);
+  CV2_CHECK(ws_bytes >= prompt_mel_workspace_bytes(B, max_samples), "prompt_mel: workspace too small");
+  Tables& t = tables_for_device();
+  const int T_out = prompt_mel_frames(max_samples);
+  const int T_alloc = t_alloc_of(max_samples);
+  float* spec = static_cast<float*>(ws);
+  pm_dft_mag_kernel<<<dim3(T_alloc / kTM, kBinsPad / kTN, B), 256, 0, st>>>(wav, wav_stride, n_samples, t.cs, t.win, spec, T_alloc);
+  CV2_CUDA(cudaGetLastError());
+  pm_mel_log_kernel<<<dim3((T_out + 3) / 4, B), 128, 0, st>>>(spec, T_alloc, n_samples, t.mel_w, t.mel_lo, t.mel_cnt, mel, T_out, mel_len);
+  CV2_CUDA(cudaGetLastError());
+}
+
+}  // namespace cv2

@@ -97,6 +97,18 @@ int cv2_hift_forward_pcm16(cv2_engine* e, void* stream, const float* mel, int me
 /* ---- streaming glue: fade_in_out (cosyvoice/utils/common.py:142-150) on the device.  window: [2n] f64 device. ---- */
 int cv2_crossfade(void* stream, float* speech, const float* old_tail, const double* window, int n);
 
+/* ---- prompt features: the 24 kHz log-mel of the prompt waveform, replacing
+ * matcha.utils.audio.mel_spectrogram (third_party/Matcha-TTS/matcha/utils/audio.py:45-82) at the cosyvoice2.yaml:152-160
+ * settings as called by CosyVoiceFrontEnd._extract_speech_feat (cosyvoice/cli/frontend.py:285-289), for a batch of prompts.
+ * wav: [B, wav_stride] fp32 device, n_samples: [B] int32 device, max_samples: the largest of them (host).
+ * mel: [B, cv2_prompt_mel_frames(max_samples), 80] fp32 device (the [1, T, 80] layout flow.inference takes; rows past a
+ * prompt's own frames are zero), mel_len: [B] int32 device or NULL.  A prompt of <= 720 samples cannot be reflect-padded
+ * (the reference raises): cv2_prompt_mel rejects max_samples <= 720, shorter rows of a batch yield mel_len 0. ---- */
+int cv2_prompt_mel_frames(int n_samples);
+size_t cv2_prompt_mel_workspace_bytes(int B, int max_samples);
+int cv2_prompt_mel(void* stream, const float* wav, long long wav_stride, const int32_t* n_samples, int B, int max_samples,
+                   float* mel, int32_t* mel_len, void* workspace, size_t workspace_bytes);
+
 /* ---- single-kernel entry points (parity tests of the individual kernels) ---- */
 /* out = epilogue(sum_taps A[s, t+off, :] W^T): A 16-bit [S,T_alloc,ldA], W 16-bit [N, ntaps*ceil64(Kc)], see gemm_tap.cuh.
  * act: 0 none 1 mish 2 gelu 3 silu 4 elu 5 lrelu(act_f) 6 snake(act_a).  Optional outputs: out32 [S*T_alloc,N] fp32,
