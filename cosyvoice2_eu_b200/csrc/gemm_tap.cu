@@ -265,6 +265,16 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const long long row0 = row - lane;                              // first row of this warp's 32-row block
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after();
+      if (p.dbg_skip_epi) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CS > 1) mbar_arrive_leader(&tmem_empty[acc]);
+          else mbar_arrive(&tmem_empty[acc]);
+        }
+        lt++;
+        continue;
+      }
 
       float mean = 0.f, rstd = 1.f;
       uint32_t raw[32];
