@@ -105,16 +105,44 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
                "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-__device__ __forceinline__ void tile_load_f32(const float* __restrict__ g0, long long ld, float*, int lane, float* d) {
-  // g0 -> element (first row of the warp, first column of the chunk)
-  const float* p = g0 + lane * ld;
+// Epilogue tiles: the accumulator comes out of TMEM one row per lane (tcgen05.ld 32x32b), so a direct global access has every
+// lane in a different 128-byte line (32 tag look-ups per instruction; the clock64 trace of the out-proj epilogue showed the
+// LSU queue, not HBM, pacing it).  A 4x4 (2x2 for 16-bit) register transpose inside each group of 4 (2) lanes makes every
+// instruction touch 8 (16) full rows of 128 (64) contiguous bytes instead.
+template <int U, int M>   // U registers per unit, groups of M + 1 lanes... M = 3: 4x4 units, M = 1: 2x2 units
+__device__ __forceinline__ void lane_group_transpose(uint32_t* a, int lane) {
 #pragma unroll
-  for (int i = 0; i < 4; i++) ldg256(p + i * 8, reinterpret_cast<uint32_t*>(d) + i * 8);
+  for (int m = 1; m <= (M + 1) / 2; m <<= 1) {
+    const bool up = (lane & m) != 0;
+#pragma unroll
+    for (int u = 0; u <= M; u++) {
+      if (u & m) continue;
+#pragma unroll
+      for (int j = 0; j < U; j++) {
+        const uint32_t send = up ? a[u * U + j] : a[(u | m) * U + j];
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, m);
+        if (up) a[u * U + j] = recv;
+        else a[(u | m) * U + j] = recv;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tile_load_f32(const float* __restrict__ g0, long long ld, float*, int lane, float* d) {
+  // g0 -> element (first row of the warp, first column of the chunk); lane 4g+s fetches columns 8s..8s+7 of rows 4g..4g+3
+  const float* p = g0 + (lane & ~3) * ld + (lane & 3) * 8;
+  uint32_t* r = reinterpret_cast<uint32_t*>(d);
+#pragma unroll
+  for (int k = 0; k < 4; k++) ldg256(p + k * ld, r + k * 8);
+  lane_group_transpose<8, 3>(r, lane);
 }
 __device__ __forceinline__ void tile_store_f32(float* __restrict__ g0, long long ld, float*, int lane, const float* v) {
-  float* p = g0 + lane * ld;
+  uint32_t r[32];
 #pragma unroll
-  for (int i = 0; i < 4; i++) stg256(p + i * 8, reinterpret_cast<const uint32_t*>(v) + i * 8);
+  for (int i = 0; i < 32; i++) r[i] = __float_as_uint(v[i]);
+  lane_group_transpose<8, 3>(r, lane);
+  float* p = g0 + (lane & ~3) * ld + (lane & 3) * 8;
+#pragma unroll
+  for (int k = 0; k < 4; k++) stg256(p + k * ld, r + k * 8);
 }
 __device__ __forceinline__ void tile_store_f16(__half* __restrict__ g0, long long ld, float*, int lane, const float* v) {
   uint32_t pk[16];
@@ -123,9 +151,10 @@ __device__ __forceinline__ void tile_store_f16(__half* __restrict__ g0, long lon
     __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
     pk[i] = *reinterpret_cast<uint32_t*>(&h);
   }
-  __half* p = g0 + lane * ld;
+  lane_group_transpose<8, 1>(pk, lane);      // lane 2g+s: columns 16s..16s+15 of rows 2g, 2g+1
+  __half* p = g0 + (lane & ~1) * ld + (lane & 1) * 16;
   stg256(p, pk);
-  stg256(p + 16, pk + 8);
+  stg256(p + ld, pk + 8);
 }
 // (the former half-height staging variants of the FFN kernel are the same direct accesses now)
 __device__ __forceinline__ void tile_load_f32_h16(const float* __restrict__ g0, long long ld, float* stg, int lane, float* d) {

@@ -70,6 +70,14 @@ __device__ __forceinline__ bool tile_coord(const GemmParams& p, int u, int n_til
   return c.t0 < c.len + p.halo;
 }
 
+__device__ __forceinline__ void gtrace(long long* tb, int& ti, int code, float dep = 0.f) {
+  if (tb && ti < 4000) {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "f"(dep) : "memory");
+    tb[ti++] = (t << 8) | code;
+  }
+}
+
 // Compile-time epilogue configuration.  Every field is -1 (decided at run time from GemmParams: the generic kernel) or a
 // fixed value; fixing them removes the untaken branches from the instruction stream (the generic epilogue is ~160 KB of
 // SASS and was instruction-cache bound).  Hot estimator / HiFT epilogues get their own instantiation (see kSpecs).
@@ -176,19 +184,24 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // ------------------------------- MMA issuer (CS = 2: for both SMs) ----------
       constexpr uint32_t idesc = umma_idesc_f16(CS * kTileM, BN, 0);
       int kit = 0, lt = 0;
+      long long* tb = (p.trace && blockIdx.x == 0) ? p.trace + 4096 : nullptr;
+      int ti = 0;
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         TileCoord c;
         bool tvalid;
         if (!tile_coord<CS>(p, tile, n_tiles, t_tiles, BN, rank, row_count, c, tvalid)) continue;
         const int acc = lt & 1;
+        gtrace(tb, ti, 1);
         mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
+        gtrace(tb, ti, 2);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int it = 0; it < num_it; it++, kit++) {
           const int st = kit % kStages;
           const uint32_t ph = (kit / kStages) & 1;
           mbar_wait(&full_bar[st], ph);
           tc_fence_after();
+          gtrace(tb, ti, 3);
           const uint32_t a_addr = smem_u32(smem + st * SM::kStageBytes);
           const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
           const uint64_t b_desc = umma_smem_desc_sw128(a_addr + kABytes);
@@ -202,6 +215,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if (CS == 1) umma_commit(&tmem_full[acc]);
         else umma2_commit(&tmem_full[acc]);
+        gtrace(tb, ti, 4);
         lt++;
       }
     }
@@ -242,6 +256,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool has_qkv = CFGB(QKV, p.q != nullptr);
 
     int lt = 0;
+    long long* tb = (p.trace && blockIdx.x == 0 && (warp == 0 || warp == 13) && lane == 0) ? p.trace + (warp == 0 ? 0 : 2048) : nullptr;
+    int ti = 0;
     for (int tile = unit0; tile < total_tiles; tile += unit_step) {
       TileCoord c;
       bool tvalid;
@@ -263,8 +279,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + my_c0;
       const long long row = (long long)c.s * p.T_alloc + t;
       const long long row0 = row - lane;                              // first row of this warp's 32-row block
+      gtrace(tb, ti, 10);
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after();
+      gtrace(tb, ti, 11);
       if (p.dbg_skip_epi) {
         tc_fence_before();
         __syncwarp();
@@ -334,6 +352,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]);
+        gtrace(tb, ti, 12, v[0] + tmp[0]);
         if (Cfg::SCALE < 0 && p.acc_scale != 0.f) {   // generic kernel only
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] *= p.acc_scale;
@@ -392,6 +411,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           else load32(p.res + row * p.res_ld + cbase, tmp, full, nv);
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] += tmp[i];
+          gtrace(tb, ti, 13, v[0] + v[31]);
         }
         if (has_res2) {
           if (full) tile_load_f32(p.res2 + row0 * p.res2_ld + cbase, p.res2_ld, stg, lane, tmp);
@@ -427,6 +447,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             else store32_f32(op, v, full, nv);
           }
         }
+        gtrace(tb, ti, 14);
         // 16-bit emits (the next contraction's A operand); padded rows are written as zeros
 #pragma unroll
         for (int e = 0; e < 3; e++) {
@@ -490,10 +511,13 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tmem_st32(taddr + ch * 32, raw);
         }
       }
+      gtrace(tb, ti, 15);
       if (stat2) {  // LayerNorm of the final row value (pre-norm of the next sub-block), emitted as 16-bit
         tmem_st_wait();
         red_c[half * 128 + r] = sum2;
+        gtrace(tb, ti, 16);
         epi_bar<kEpiWarps * 32>();
+        gtrace(tb, ti, 17);
         const float mean2 = red_sum(red_c) / (float)ncols;
         float sq2 = 0.f;
 #pragma unroll 1
@@ -510,7 +534,9 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
         red_d[half * 128 + r] = sq2;
+        gtrace(tb, ti, 18);
         epi_bar<kEpiWarps * 32>();
+        gtrace(tb, ti, 19);
         const float var2 = red_sum(red_d) / (float)ncols;
 #pragma unroll 1
         for (int ch = 0; ch < kChunks; ch++) {
@@ -539,6 +565,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       }
+      gtrace(tb, ti, 20);
       // release this accumulator buffer to the MMA warp
       tc_fence_before();
       __syncwarp();

@@ -43,6 +43,7 @@ struct GemmParams {
   int halo;            // a tile is computed iff t0 < len + halo
   const int* tile_list;   // optional compact list of active (s, t0) pairs (device), balanced round-robin over CTAs
   const int* tile_count;  // number of pairs in tile_list (device)
+  long long* trace;              // clock64 timeline of CTA 0 (measurement aid)
   int dbg_skip_epi;              // measurement aid: epilogue drains the accumulator without computing or storing
   const CUtensorMap* tmB_half;   // host pointer: weight map with a {64, BN/2} box -> 2-CTA cluster with TMA multicast of the
                                  // weight operand (BN = 256 and a compact tile list only); null: one CTA per tile
