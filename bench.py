@@ -433,6 +433,14 @@ def main():
         hbm_kernels["note"] = ("peak = measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs); nsf_source in production mode draws its "
                                "noise in-kernel (9 sines + 9 normals per 4-byte sample), i.e. it is ALU/MUFU bound there and only "
                                "bandwidth bound in parity mode (36 B/sample noise read)")
+        # SURVEY.md 8f row F2 (the step before the path): prompt log-mel of 64 prompts of U[3, 30] s, device-resident input, and
+        # the same call with host buffers; the oracle (numpy float64 rFFT, one thread) on one 30 s prompt beside it
+        prompt_mel = None
+        if rank == 0:
+            try:
+                prompt_mel = bench_prompt_mel(dev, peaks, clk, with_cpu=not args.no_cpu_baseline)
+            except Exception as exc:   # side measurement: never break the bench line
+                prompt_mel = {"error": str(exc)}
         total_flop = sum(flops.values()) * world
         line = {
             "metric": "token2wav_audio_seconds_per_second", "value": total_audio * args.steps / (ms / 1e3), "unit": "audio-s/s",
@@ -456,6 +464,7 @@ def main():
                            "latency_s": lat1, "rtf": lat1 / 10.0, "audio_s_per_s": 10.0 / lat1, "how": "CUDA-graph replay, host in / host out",
                            "latency_s_eager_launches": float(np.median(lat_eager))},
             "stream32": stream32,
+            "prompt_mel": prompt_mel,
             "clocks": clocks_summary(clk),
         }
         if not args.no_cpu_baseline:
@@ -469,6 +478,55 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_prompt_mel(dev, peaks, clk, with_cpu=True, reps=10):
+    import torch
+    from cosyvoice2_eu_b200 import extract_speech_feat_batch, frontend
+    rng = np.random.Generator(np.random.Philox(key=4242))
+    lens = [int(24000 * d) for d in rng.uniform(3.0, 30.0, size=63)] + [24000 * 30]
+    g = torch.Generator().manual_seed(5)
+    waves = [(torch.rand(n, generator=g) * 2 - 1) * 0.5 for n in lens]
+    max_len = max(lens)
+    wav = torch.zeros(len(lens), max_len, dtype=torch.float32, device=dev)
+    for i, w in enumerate(waves):
+        wav[i, :lens[i]] = w.to(dev)
+    n = torch.tensor(lens, dtype=torch.int32, device=dev)
+    for _ in range(3):
+        mel, mel_len = frontend._run(wav, n, max_len)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        mel, mel_len = frontend._run(wav, n, max_len)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    frames = int(mel_len.sum())
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        m2, l2 = extract_speech_feat_batch(waves, device=dev)
+        l2.cpu()
+    ms_host = (time.perf_counter() - t0) / reps * 1e3
+    audio = sum(lens) / 24000.0
+    flop = frames * 2.0 * 2 * 961 * 961                 # folded real DFT: 2 x 961 x 961 FMAs per frame
+    sm_mhz = clocks_summary(clk).get("sm_mhz") or 1850.0
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12     # 128 FP32 lanes per SM, FMA = 2 flop, at the clock sampled under load
+    out = {"workload": "64 prompts, U[3,30] s at 24 kHz, one launch pair (pm_dft_mag + pm_mel_log)", "frames": frames,
+           "ms_per_call": ms, "audio_s_per_s": audio / (ms / 1e3), "fp32_tflops_algorithmic": flop / 1e12 / (ms / 1e3),
+           "fp32_peak_tflops": fp32_peak, "frac": flop / 1e12 / (ms / 1e3) / fp32_peak, "bound": "fp32 FMA",
+           "e2e_host_buffers": {"ms_per_call": ms_host, "audio_s_per_s": audio / (ms_host / 1e3), "h2d_bytes": int(len(lens) * max_len * 4),
+                                "d2h_bytes": 4 * len(lens)}}
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import prompt_mel_oracle as PO     # checker timed as the CPU baseline (bench.py's cpu_baseline leg)
+        w0 = waves[-1].numpy()
+        t0 = time.perf_counter()
+        ref = PO.mel_spectrogram(w0)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 30.0 / dt, "unit": "audio-s/s", "cores": 1, "kind": "port", "sample": "one 30 s prompt",
+                               "max_abs_logmel_diff_vs_gpu": float(np.abs(mel[-1, :ref.shape[2]].cpu().numpy() - ref[0].T).max())}
+    return out
 
 
 if __name__ == "__main__":

@@ -155,10 +155,6 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         TileCoord c;
         bool tvalid;
         if (!tile_coord<CS>(p, tile, n_tiles, t_tiles, BN, rank, row_count, c, tvalid)) continue;
-        // the epilogue's fp32 residual rows of this tile: pull them into L2 while the ring fills (one contiguous span when
-        // the row is exactly one tile wide), so that the read after the last MMA is an L2 hit, not an HBM round trip
-        if (p.res != nullptr && tvalid && p.res_ld == BN && p.N == BN)
-          prefetch_l2_bulk(p.res + ((long long)c.s * p.T_alloc + c.t0) * BN, kTileM * BN * 4);
         for (int it = 0; it < num_it; it++, kit++) {
           const int st = kit % kStages;
           const uint32_t ph = (kit / kStages) & 1;
