@@ -32,7 +32,11 @@ struct GemmSmem {
   static constexpr int kStages = (192 * 1024) / kStageBytes;
   static constexpr int kRedOff = kStages * kStageBytes;   // 4 x [kParts][128] floats for LayerNorm exchanges
   static constexpr int kBarOff = kRedOff + 4 * kParts * 128 * 4;
-  static constexpr int kTotal = kBarOff + 512;            // + barriers
+  // per-column parameter vectors of the epilogue, staged once per CTA (the streaming residual / output traffic keeps evicting
+  // them from the small L1 that is left next to a 192 KB ring: in the clock64 trace every re-read cost an L2 round trip)
+  static constexpr int kVecBias = 2048, kVecLn = 256;     // bias [N <= 2048]; LayerNorm gamma/beta + emitted-LN gamma/beta [N <= 256]
+  static constexpr int kVecOff = kBarOff + 512;           // + barriers
+  static constexpr int kTotal = kVecOff + (kVecBias + 4 * kVecLn) * 4;
 };
 
 template <int NT>
@@ -124,6 +128,31 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const bool leader = rank == 0;
   constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // 128 / 256 / 512
 
+  float* vec_bias = reinterpret_cast<float*>(smem + SM::kVecOff);
+  float* vec_lng = vec_bias + SM::kVecBias;
+  float* vec_lnb = vec_lng + SM::kVecLn;
+  float* vec_eg = vec_lnb + SM::kVecLn;
+  float* vec_eb = vec_eg + SM::kVecLn;
+  const bool c_bias = p.bias != nullptr && p.N <= SM::kVecBias;
+  const bool c_ln = p.ln != 0 && p.N <= SM::kVecLn;
+  int e_ln = -1;
+#pragma unroll
+  for (int e = 2; e >= 0; e--)
+    if ((e == 0 ? (Cfg::EMIT0 < 0 ? p.emit[0].kind : Cfg::EMIT0) : e == 1 ? (Cfg::EMIT1 < 0 ? p.emit[1].kind : Cfg::EMIT1)
+                                                                           : (Cfg::EMIT2 < 0 ? p.emit[2].kind : Cfg::EMIT2)) == EMIT_LN)
+      e_ln = e;
+  const bool c_eln = e_ln >= 0 && p.N <= SM::kVecLn;
+  for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+    if (c_bias) vec_bias[i] = __ldg(p.bias + i);
+    if (c_ln) {
+      vec_lng[i] = __ldg(p.ln_g + i);
+      vec_lnb[i] = __ldg(p.ln_b + i);
+    }
+    if (c_eln) {
+      vec_eg[i] = __ldg(p.emit[e_ln].a + i);
+      vec_eb[i] = __ldg(p.emit[e_ln].b + i);
+    }
+  }
   if (warp == kEpiWarps && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -250,6 +279,18 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool is_flat = CFGB(FLAT, p.flat != 0);
     const bool has_scale = CFGB(SCALE, p.out_scale != 1.f);
     const bool has_qkv = CFGB(QKV, p.q != nullptr);
+    // 32 consecutive per-column parameters: from the staged copy (broadcast LDS.128) when there is one
+    auto vload = [&](const float* sv, bool cached, const float* gv, int col, float* d, bool full, int nv) {
+      if (cached && full) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const float4 f = *reinterpret_cast<const float4*>(sv + col + i * 4);
+          d[i * 4 + 0] = f.x; d[i * 4 + 1] = f.y; d[i * 4 + 2] = f.z; d[i * 4 + 3] = f.w;
+        }
+      } else {
+        load32(gv + col, d, full, nv);
+      }
+    };
 
     int lt = 0;
     long long* tb = (p.trace && blockIdx.x == 0 && (warp == 0 || warp == 13) && lane == 0) ? p.trace + (warp == 0 ? 0 : 2048) : nullptr;
@@ -302,7 +343,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (nv <= 0) break;
           tmem_ld32(taddr + ch * 32, raw);
           float bch[32];
-          load32(p.bias + c.n0 + cl, bch, nv == 32, nv);
+          vload(vec_bias, c_bias, p.bias, c.n0 + cl, bch, nv == 32, nv);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; i++)
@@ -319,7 +360,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (nv <= 0) break;
           tmem_ld32(taddr + ch * 32, raw);
           float bch[32];
-          load32(p.bias + c.n0 + cl, bch, nv == 32, nv);
+          vload(vec_bias, c_bias, p.bias, c.n0 + cl, bch, nv == 32, nv);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; i++)
@@ -344,7 +385,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int cbase = c.n0 + cl;              // global column
         tmem_ld32(taddr + ch * 32, raw);
         float tmp[32];
-        if (has_bias) load32(p.bias + cbase, tmp, full, nv);
+        if (has_bias) vload(vec_bias, c_bias, p.bias, cbase, tmp, full, nv);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]);
@@ -358,10 +399,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int i = 0; i < 32; i++) v[i] += tmp[i];
         }
         if (has_ln) {
-          load32(p.ln_g + cbase, tmp, full, nv);
+          vload(vec_lng, c_ln, p.ln_g, cbase, tmp, full, nv);
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] = (v[i] - mean) * rstd * tmp[i];
-          load32(p.ln_b + cbase, tmp, full, nv);
+          vload(vec_lnb, c_ln, p.ln_b, cbase, tmp, full, nv);
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] += tmp[i];
         }
@@ -549,10 +590,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (ek != EMIT_LN) continue;
             const float rstd2 = rsqrtf(var2 + em.f);
             float g[32], w[32];
-            load32(em.a + cbase, g, nv == 32, nv);
+            vload(vec_eg, c_eln && e == e_ln, em.a, cbase, g, nv == 32, nv);
 #pragma unroll
             for (int i = 0; i < 32; i++) w[i] = (__uint_as_float(raw[i]) - mean2) * rstd2 * g[i];
-            load32(em.b + cbase, g, nv == 32, nv);
+            vload(vec_eb, c_eln && e == e_ln, em.b, cbase, g, nv == 32, nv);
             const float sc = valid ? em.scale : 0.f;
 #pragma unroll
             for (int i = 0; i < 32; i++) w[i] = (w[i] + g[i]) * sc;
