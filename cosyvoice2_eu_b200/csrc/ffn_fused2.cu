@@ -23,7 +23,8 @@ static constexpr int kOffW = kHBytes;
 static constexpr int kEpiW = 16;                 // epilogue warps: four per TMEM lane quarter
 static constexpr int kOffRed = kOffW + kSlots * kSlotBytes;
 static constexpr int kOffBar = kOffRed + 2 * 4 * 128 * 4;
-static constexpr int kFfnSmem = kOffBar + 256;
+static constexpr int kOffVec = kOffBar + 256;       // b1 [1024] | b2 [256] | next pre-norm gamma [256] | beta [256], staged once per CTA
+static constexpr int kFfnSmem = kOffVec + (1024 + 3 * 256) * 4;
 static constexpr int kFfnThreads = 64 + kEpiW * 32;
 static constexpr uint32_t kAcc1 = 0, kAcc2 = 256;   // TMEM columns: acc1 = 2 x 128, acc2 = 256
 
@@ -64,6 +65,15 @@ __device__ __forceinline__ void ffn_op(int o, bool& is_ff2, int& c) {
   else { is_ff2 = true; c = (o >> 1) - 1; }
 }
 
+// 32 consecutive staged parameters (every lane reads the same address: broadcast LDS.128)
+__device__ __forceinline__ void lds32(const float* sv, float* d) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float4 f = *reinterpret_cast<const float4*>(sv + i * 4);
+    d[i * 4 + 0] = f.x; d[i * 4 + 1] = f.y; d[i * 4 + 2] = f.z; d[i * 4 + 3] = f.w;
+  }
+}
+
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const FfnParams p) {
@@ -91,6 +101,20 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
   const bool leader = rank == 0;
   const int unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
 
+  float* vec_b1 = reinterpret_cast<float*>(smem + kOffVec);
+  float* vec_b2 = vec_b1 + 1024;
+  float* vec_g = vec_b2 + 256;
+  float* vec_b = vec_g + 256;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+    vec_b1[i] = __ldg(p.b1 + i);
+    if (i < 256) {
+      vec_b2[i] = __ldg(p.b2 + i);
+      if (p.emit_ln.ptr) {
+        vec_g[i] = __ldg(p.emit_ln.a + i);
+        vec_b[i] = __ldg(p.emit_ln.b + i);
+      }
+    }
+  }
   if (warp == kEpiW && lane == 0) {
     tma_prefetch_desc(&tmH);
     tma_prefetch_desc(&tmW1);
@@ -276,7 +300,7 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       for (int c = 0; c < 8; c++, g++) {
         const int b = c & 1;
         float bv[32];
-        load32(p.b1 + c * 128 + part * 32, bv, true, 32);      // bias first: its latency hides behind the accumulator wait
+        lds32(vec_b1 + c * 128 + part * 32, bv);
         ffn_trace(tb, ti, 10);
         mbar_wait(&acc1_full[b], use1[b] & 1);
         ffn_trace(tb, ti, 11);
@@ -326,7 +350,7 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       for (int ch = 0; ch < 2; ch++) {
         const int cbase = part * 64 + ch * 32;
         tmem_ld32(taddr + ch * 32, raw);
-        load32(p.b2 + cbase, tmp, true, 32);
+        lds32(vec_b2 + cbase, tmp);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]) + tmp[i];
@@ -376,11 +400,11 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           const int cbase = part * 64 + ch * 32;
           tmem_ld32(taddr + ch * 32, raw);
           float gg[32], w[32];
-          load32(p.emit_ln.a + cbase, gg, true, 32);
+          lds32(vec_g + cbase, gg);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; i++) w[i] = (__uint_as_float(raw[i]) - mean2) * rstd2 * gg[i];
-          load32(p.emit_ln.b + cbase, gg, true, 32);
+          lds32(vec_b + cbase, gg);
 #pragma unroll
           for (int i = 0; i < 32; i++) w[i] = valid ? (w[i] + gg[i]) : 0.f;
           tile_store_f16_h16(p.emit_ln.ptr + row0 * p.emit_ln.ld + p.emit_ln.col_off + cbase, p.emit_ln.ld, stg, lane, w);

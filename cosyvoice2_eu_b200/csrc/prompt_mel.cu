@@ -6,7 +6,7 @@
 // evaluated as a dense fp32 contraction with K halved by the symmetry of the (periodic Hann) window, w[n] = w[N - n]:
 //     Re X[k] = sum_{n=0}^{960} e[n] cos(2 pi k n / N),   Im X[k] = -sum_{n=1}^{959} o[n] sin(2 pi k n / N),
 //     e[n] = w[n] (x[n] + x[N - n]),  o[n] = w[n] (x[n] - x[N - n])   (n = 1..959),   e[0] = w[0] x[0],  e[960] = w[960] x[960],
-// so one frame costs 2 x 961 x 961 FMAs instead of 2 x 1920 x 961.  `pm_dft_mag_kernel` is a 64 frames x 64 bins register-tiled
+// so one frame costs 2 x 961 x 961 FMAs instead of 2 x 1920 x 961.  `pm_dft_mag_kernel` is a 128 frames x 64 bins register-tiled
 // SGEMM whose A tile is folded on the fly from the waveform (reflect indexing + window), whose B tile is an exact (cos, sin)
 // table (argument reduced in integers, evaluated in fp64 once per device) and whose inner product is packed
 // `fma.rn.f32x2` on (re, im) pairs; its epilogue writes |X| = sqrt(re^2 + im^2 + 1e-9).  `pm_mel_log_kernel` applies the 80
@@ -28,7 +28,7 @@ constexpr int kKfold = 961;        // folded contraction length (n = 0..960)
 constexpr int kKpad = 976;         // padded to a multiple of the k step
 constexpr int kBinsPad = 1024;     // table / spectrum row length
 constexpr int kBandMax = 64;       // widest mel band in bins (top band: 49)
-constexpr int kTM = 64, kTN = 64, kTK = 16;
+constexpr int kTM = 128, kTN = 64, kTK = 16;
 
 struct Tables {
   float2* cs = nullptr;     // [kKpad][kBinsPad] (cos, sin)(2 pi n k / N); zero outside n < 961, k < 961
@@ -62,8 +62,9 @@ __device__ __forceinline__ float wave_reflect(const float* __restrict__ w, int i
   return __ldg(w + i);
 }
 
-// grid (frame tiles, bin tiles, B), 256 threads; thread (ty, tx) owns frames ty*4..+3 and bins tx*4..+3 of the tile.
-__global__ void __launch_bounds__(256) pm_dft_mag_kernel(const float* __restrict__ wav, long long wav_stride,
+// grid (frame tiles, bin tiles, B), 256 threads; thread (ty, tx) owns frames ty*8..+7 and bins tx*4..+3 of the 128 x 64 tile
+// (32 packed accumulators; per k: 6 LDS.128 feed 32 FFMA2).
+__global__ void __launch_bounds__(256, 2) pm_dft_mag_kernel(const float* __restrict__ wav, long long wav_stride,
                                                          const int* __restrict__ n_samples, const float2* __restrict__ cs,
                                                          const float* __restrict__ win, float* __restrict__ spec, int T_alloc) {
   __shared__ __align__(16) float2 As[2][kTK][kTM];    // (e, o)
@@ -77,23 +78,23 @@ __global__ void __launch_bounds__(256) pm_dft_mag_kernel(const float* __restrict
   const float* w = wav + (long long)b * wav_stride;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int lf = tid & 63, lk = tid >> 6;     // A loader: frame fastest (conflict-free smem stores), 4 k rows per pass
+  const int lf = tid & 127, lk = tid >> 7;    // A loader: frame fastest (conflict-free smem stores), 2 k rows per pass
   const int bk = tid >> 4, bn = (tid & 15) * 4;  // B loader: one k row, 4 bins
 
-  float2 acc[4][4];
+  float2 acc[8][4];
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < 8; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.f, 0.f);
 
-  float2 ra[4];
+  float2 ra[8];
   float4 rb[2];
   auto fetch = [&](int kb) {
     const int base = (t0 + lf) * kHop - kPad;      // first sample of the frame in the unpadded signal
     const bool live = t0 + lf < T;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int n = kb + lk + 4 * i;
+    for (int i = 0; i < 8; i++) {
+      const int n = kb + lk + 2 * i;
       float e = 0.f, o = 0.f;
       if (live && n < kKfold) {
         const float wn = __ldg(win + n);
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) pm_dft_mag_kernel(const float* __restrict
   };
   auto stash = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) As[buf][lk + 4 * i][lf] = ra[i];
+    for (int i = 0; i < 8; i++) As[buf][lk + 2 * i][lf] = ra[i];
     float4* dst = reinterpret_cast<float4*>(&Bs[buf][bk][bn]);
     dst[0] = rb[0];
     dst[1] = rb[1];
@@ -129,14 +130,21 @@ __global__ void __launch_bounds__(256) pm_dft_mag_kernel(const float* __restrict
     if (s + 1 < kSteps) fetch((s + 1) * kTK);
 #pragma unroll
     for (int kk = 0; kk < kTK; kk++) {
-      const float4 a01 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
-      const float4 a23 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4 + 2]);
-      const float4 b01 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
-      const float4 b23 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4 + 2]);
-      const float2 a[4] = {make_float2(a01.x, a01.y), make_float2(a01.z, a01.w), make_float2(a23.x, a23.y), make_float2(a23.z, a23.w)};
-      const float2 bb[4] = {make_float2(b01.x, b01.y), make_float2(b01.z, b01.w), make_float2(b23.x, b23.y), make_float2(b23.z, b23.w)};
+      float2 a[8], bb[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+      for (int i = 0; i < 4; i++) {
+        const float4 f = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 2 * i]);
+        a[2 * i] = make_float2(f.x, f.y);
+        a[2 * i + 1] = make_float2(f.z, f.w);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const float4 f = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4 + 2 * j]);
+        bb[2 * j] = make_float2(f.x, f.y);
+        bb[2 * j + 1] = make_float2(f.z, f.w);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j] = ffma2(a[i], bb[j], acc[i][j]);
     }
@@ -146,8 +154,8 @@ __global__ void __launch_bounds__(256) pm_dft_mag_kernel(const float* __restrict
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int t = t0 + ty * 4 + i;
+  for (int i = 0; i < 8; i++) {
+    const int t = t0 + ty * 8 + i;
     if (t >= T) continue;
     float4 m;
     m.x = sqrtf(acc[i][0].x * acc[i][0].x + acc[i][0].y * acc[i][0].y + 1e-9f);
