@@ -517,6 +517,25 @@ def bench_prompt_mel(dev, peaks, clk, with_cpu=True, reps=10):
            "fp32_peak_tflops": fp32_peak, "frac": flop / 1e12 / (ms / 1e3) / fp32_peak, "bound": "fp32 FMA",
            "e2e_host_buffers": {"ms_per_call": ms_host, "audio_s_per_s": audio / (ms_host / 1e3), "h2d_bytes": int(len(lens) * max_len * 4),
                                 "d2h_bytes": 4 * len(lens)}}
+    # the 16 -> 24 kHz resampler in front of it (HBM bound: 4 B read per input sample + 4 B written per output sample)
+    from cosyvoice2_eu_b200 import resample_16k_to_24k
+    lens16 = [n * 2 // 3 for n in lens]
+    x16 = torch.rand(len(lens16), max(lens16), device=dev) - 0.5
+    n16 = torch.tensor(lens16, dtype=torch.int32, device=dev)
+    for _ in range(3):
+        resample_16k_to_24k(x16, device=dev, lengths=n16)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        resample_16k_to_24k(x16, device=dev, lengths=n16)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_rs = e0.elapsed_time(e1) / reps
+    rs_bytes = 4.0 * x16.numel() * 2.5          # padded rows are read and written in full
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    out["resample_16k_24k"] = {"ms_per_call": ms_rs, "achieved_gbs": rs_bytes / (ms_rs * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                               "frac": rs_bytes / (ms_rs * 1e-3) / 1e9 / hbm_peak, "bound": "hbm",
+                               "note": "includes the torch.empty of the output; 10 B per input sample"}
     if with_cpu:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import prompt_mel_oracle as PO     # checker timed as the CPU baseline (bench.py's cpu_baseline leg)

@@ -288,6 +288,16 @@ int cv2_prompt_mel(void* stream, const float* wav, long long wav_stride, const i
   CV2_API_END
 }
 
+int cv2_resample_16k_24k_len(int n_in) { return resample_16k_24k_len(n_in); }
+
+int cv2_resample_16k_24k(void* stream, const float* wav16, long long in_stride, const int32_t* n_in, int B, int max_in, float* wav24,
+                         long long out_stride, int32_t* n_out) {
+  CV2_API_BEGIN
+  CV2_CHECK(wav16 && n_in && wav24, "cv2_resample_16k_24k: null pointer");
+  launch_resample_16k_24k(wav16, in_stride, n_in, B, max_in, wav24, out_stride, n_out, (cudaStream_t)stream);
+  CV2_API_END
+}
+
 int cv2_op_gemm_tap(void* stream, const void* A, int S, int T_alloc, int Kc, long long ldA, const void* W, int N, int Ktot,
                     const float* bias, int bn, int ntaps, const int* tap_off_host, const int32_t* lens, int len_all,
                     const float* ln_g, const float* ln_b, float ln_eps, int act, float act_f, const float* act_a,

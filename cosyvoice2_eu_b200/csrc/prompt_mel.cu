@@ -200,6 +200,54 @@ __global__ void __launch_bounds__(128) pm_mel_log_kernel(const float* __restrict
   }
 }
 
+// 16 kHz -> 24 kHz: torchaudio.transforms.Resample(16000, 24000) (cosyvoice/cli/frontend.py:495,541): polyphase FIR, 3 phases x 16
+// taps of a Hann-windowed sinc (lowpass_filter_width 6, rolloff 0.99): y[3 i + p] = sum_k x[2 i + k - 7] h[p][k], zero outside.
+// HBM bound: 8 B read + 12 B written per input pair.
+__constant__ float c_rs[3][16];
+
+__global__ void __launch_bounds__(256) pm_resample_kernel(const float* __restrict__ x, long long x_stride, const int* __restrict__ n_in,
+                                                          float* __restrict__ y, long long y_stride, int* __restrict__ n_out,
+                                                          int max_out) {
+  const int b = blockIdx.y;
+  const int L = __ldg(n_in + b);
+  const int Lo = (3 * L + 1) / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && n_out) n_out[b] = Lo;
+  if (3 * i >= max_out) return;
+  const float* xr = x + (long long)b * x_stride;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  if (3 * i < Lo) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const int j = 2 * i + k - 7;
+      const float v = (j >= 0 && j < L) ? __ldg(xr + j) : 0.f;
+      a0 = fmaf(v, c_rs[0][k], a0);
+      a1 = fmaf(v, c_rs[1][k], a1);
+      a2 = fmaf(v, c_rs[2][k], a2);
+    }
+  }
+  float* yr = y + (long long)b * y_stride + 3 * i;
+  const float o[3] = {a0, a1, a2};
+#pragma unroll
+  for (int p_ = 0; p_ < 3; p_++)
+    if (3 * i + p_ < max_out) yr[p_] = 3 * i + p_ < Lo ? o[p_] : 0.f;    // rows are zero-padded to max_out
+}
+
+void build_resample(float h[3][16]) {
+  const double base = 2.0 * 0.99, lpw = 6.0, pi = 3.14159265358979323846;
+  for (int p_ = 0; p_ < 3; p_++) {
+    const double ph = (double)((float)(-p_) / 3.0f);     // torch forms the phase offset in float32, the rest in float64
+    for (int k = 0; k < 16; k++) {
+      double t = (ph + (double)(k - 7) / 2.0) * base;
+      t = t < -lpw ? -lpw : (t > lpw ? lpw : t);
+      const double c = cos(t * pi / lpw / 2.0);
+      const double tp = t * pi;
+      const double sinc = tp == 0.0 ? 1.0 : sin(tp) / tp;
+      h[p_][k] = (float)(sinc * (c * c) * (base / 2.0));
+    }
+  }
+}
+
 // librosa.filters.mel(sr=24000, n_fft=1920, n_mels=80, fmin=0, fmax=8000), Slaney scale + Slaney norm, float32 (audio.py:52)
 double hz_to_mel(double f) {
   const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
@@ -261,6 +309,9 @@ Tables& tables_for_device() {
   CV2_CUDA(cudaMemcpy(t.mel_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
   CV2_CUDA(cudaMemcpy(t.mel_lo, lo.data(), kMels * sizeof(int), cudaMemcpyHostToDevice));
   CV2_CUDA(cudaMemcpy(t.mel_cnt, cnt.data(), kMels * sizeof(int), cudaMemcpyHostToDevice));
+  float h[3][16];
+  build_resample(h);
+  CV2_CUDA(cudaMemcpyToSymbol(c_rs, h, sizeof(h)));
   float2* cs = nullptr;
   CV2_CUDA(cudaMalloc(&cs, (size_t)kKpad * kBinsPad * sizeof(float2)));
   pm_table_kernel<<<dim3(kBinsPad / 256, kKpad), 256>>>(cs, t.win);
@@ -291,6 +342,19 @@ void launch_prompt_mel(const float* wav, long long wav_stride, const int* n_samp
   pm_dft_mag_kernel<<<dim3(T_alloc / kTM, kBinsPad / kTN, B), 256, 0, st>>>(wav, wav_stride, n_samples, t.cs, t.win, spec, T_alloc);
   CV2_CUDA(cudaGetLastError());
   pm_mel_log_kernel<<<dim3((T_out + 3) / 4, B), 128, 0, st>>>(spec, T_alloc, n_samples, t.mel_w, t.mel_lo, t.mel_cnt, mel, T_out, mel_len);
+  CV2_CUDA(cudaGetLastError());
+}
+
+int resample_16k_24k_len(int n_in) { return (3 * n_in + 1) / 2; }
+
+void launch_resample_16k_24k(const float* wav16, long long in_stride, const int* n_in, int B, int max_in, float* wav24,
+                             long long out_stride, int* n_out, cudaStream_t st) {
+  CV2_CHECK(B > 0 && max_in > 0, "resample: empty input");
+  const int max_out = resample_16k_24k_len(max_in);
+  CV2_CHECK(out_stride >= max_out, "resample: output rows of %lld samples cannot hold %d", out_stride, max_out);
+  tables_for_device();
+  const int n_i = (max_out + 2) / 3;
+  pm_resample_kernel<<<dim3((n_i + 255) / 256, B), 256, 0, st>>>(wav16, in_stride, n_in, wav24, out_stride, n_out, max_out);
   CV2_CUDA(cudaGetLastError());
 }
 

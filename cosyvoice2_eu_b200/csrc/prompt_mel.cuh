@@ -12,4 +12,9 @@ size_t prompt_mel_workspace_bytes(int B, int max_samples);    // magnitude spect
 void launch_prompt_mel(const float* wav, long long wav_stride, const int* n_samples, int B, int max_samples, float* mel,
                        int* mel_len, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// torchaudio Resample(16000, 24000): wav16 [B, in_stride] -> wav24 [B, out_stride] (rows zero-padded to ceil(3 max_in / 2)), n_out [B]
+int resample_16k_24k_len(int n_in);
+void launch_resample_16k_24k(const float* wav16, long long in_stride, const int* n_in, int B, int max_in, float* wav24,
+                             long long out_stride, int* n_out, cudaStream_t st);
+
 }  // namespace cv2

@@ -5,6 +5,8 @@ Mirrors (names, argument meaning, return layout):
     (at the cosyvoice2.yaml:152-160 settings, the only ones the reference's `feat_extractor` is built with)
   * CosyVoiceFrontEnd._extract_speech_feat  cosyvoice/cli/frontend.py:285-289                   -> extract_speech_feat
   * the "force speech_feat % speech_token = 2" truncation  cosyvoice/cli/frontend.py:498-502    -> align_prompt
+  * torchaudio.transforms.Resample(orig_freq=16000, new_freq=24000)(prompt_speech_16k)  cosyvoice/cli/frontend.py:495,541
+                                                                                               -> resample_16k_to_24k
 plus `extract_speech_feat_batch` for many prompts at once (the reference handles one request at a time).
 
 torch is used for device memory and streams only; the arithmetic runs in libcv2eu_b200.so (no CPU path: without the CUDA
@@ -76,6 +78,30 @@ def extract_speech_feat_batch(speeches, device="cuda:0"):
     wav = host.to(device, non_blocking=True)
     n = torch.tensor(lens, dtype=torch.int32).to(device, non_blocking=True)
     return _run(wav, n, max_len)
+
+
+def resample_16k_to_24k(speech_16k, device="cuda:0", lengths=None):
+    """frontend.py:495: speech_16k [B, L] (or [L]) at 16 kHz -> [B, ceil(3 L / 2)] at 24 kHz on `device` (sinc_interp_hann,
+    lowpass_filter_width 6, rolloff 0.99: torchaudio's defaults).  `lengths` ([B] int32, optional) gives ragged rows; rows are
+    zero-padded and (wav24, n_out) is returned in that case."""
+    L = _lib.load()
+    x = speech_16k.to(device=device, dtype=torch.float32)
+    if x.dim() == 1:
+        x = x[None]
+    x = x.contiguous()
+    if not x.is_cuda:
+        raise _lib.Cv2Error("resampling runs on the GPU only (there is no CPU fallback)")
+    B, max_in = x.shape
+    n_in = (torch.full((B,), max_in, dtype=torch.int32, device=x.device) if lengths is None
+            else lengths.to(device=x.device, dtype=torch.int32))
+    max_out = int(L.cv2_resample_16k_24k_len(int(max_in)))
+    y = torch.empty(B, max_out, dtype=torch.float32, device=x.device)
+    n_out = torch.empty(B, dtype=torch.int32, device=x.device)
+    st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    with torch.cuda.device(x.device):
+        _lib.check(L.cv2_resample_16k_24k(st, _lib.ptr(x), x.stride(0), _lib.ptr(n_in), B, int(max_in), _lib.ptr(y), y.stride(0),
+                                          _lib.ptr(n_out)))
+    return y if lengths is None else (y, n_out)
 
 
 def align_prompt(speech_feat, speech_feat_len, speech_token, speech_token_len):

@@ -109,6 +109,14 @@ size_t cv2_prompt_mel_workspace_bytes(int B, int max_samples);
 int cv2_prompt_mel(void* stream, const float* wav, long long wav_stride, const int32_t* n_samples, int B, int max_samples,
                    float* mel, int32_t* mel_len, void* workspace, size_t workspace_bytes);
 
+/* 16 kHz -> 24 kHz resampling of the prompt, replacing torchaudio.transforms.Resample(orig_freq=16000, new_freq=24000)
+ * (cosyvoice/cli/frontend.py:495,541; sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99).  wav16: [B, in_stride] fp32 device,
+ * n_in: [B] int32 device, max_in: the largest (host); wav24: [B, out_stride] fp32 device with out_stride >=
+ * cv2_resample_16k_24k_len(max_in) = ceil(3 max_in / 2) (rows zero-padded up to that), n_out: [B] int32 device or NULL. */
+int cv2_resample_16k_24k_len(int n_in);
+int cv2_resample_16k_24k(void* stream, const float* wav16, long long in_stride, const int32_t* n_in, int B, int max_in, float* wav24,
+                         long long out_stride, int32_t* n_out);
+
 /* ---- single-kernel entry points (parity tests of the individual kernels) ---- */
 /* out = epilogue(sum_taps A[s, t+off, :] W^T): A 16-bit [S,T_alloc,ldA], W 16-bit [N, ntaps*ceil64(Kc)], see gemm_tap.cuh.
  * act: 0 none 1 mish 2 gelu 3 silu 4 elu 5 lrelu(act_f) 6 snake(act_a).  Optional outputs: out32 [S*T_alloc,N] fp32,

@@ -76,6 +76,24 @@ def main():
         out[f"{name}.wav"] = w
         out[f"{name}.mel"] = mel[0].numpy().astype(np.float32)          # [80, T]
         print(name, w.shape, tuple(mel.shape), float(mel.min()), float(mel.max()))
+    # 16 kHz -> 24 kHz exactly as CV/cli/frontend.py:495 does it, then the reference mel of the result (the chain a request runs)
+    import torchaudio
+    rs = torchaudio.transforms.Resample(orig_freq=16000, new_freq=24000)
+    out["resample.kernel"] = rs.kernel[:, 0, :].numpy().astype(np.float32)          # [3, 16]
+    rng = np.random.Generator(np.random.Philox(key=16000))
+    for name, L in (("rs_a", 16000), ("rs_odd", 7777), ("rs_tiny", 5)):
+        t = np.arange(L) / 16000.0
+        x = (0.5 * np.sin(2 * np.pi * 220.0 * t) + 0.2 * np.sin(2 * np.pi * 3100.0 * t + 1.0) + 0.05 * rng.standard_normal(L)).astype(np.float32)
+        with torch.no_grad():
+            y = rs(torch.from_numpy(x)[None])
+        out[f"{name}.in"] = x
+        out[f"{name}.out"] = y[0].numpy().astype(np.float32)
+        print(name, x.shape, tuple(y.shape))
+        if L >= 16000:
+            with torch.no_grad():
+                mel = audio.mel_spectrogram(y, n_fft=1920, num_mels=80, sampling_rate=24000, hop_size=480, win_size=1920, fmin=0,
+                                            fmax=8000, center=False)
+            out[f"{name}.mel"] = mel[0].numpy().astype(np.float32)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

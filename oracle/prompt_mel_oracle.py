@@ -17,6 +17,11 @@ mel_scale="slaney")`, which the golden generator also hands to the reference in 
 holds no test of its own for this function, so the mel basis is "pinned against a third-party restatement", the STFT / log
 part against the reference itself.
 
+`resample_16k_to_24k` restates `torchaudio.transforms.Resample(orig_freq=16000, new_freq=24000)` (the call at
+CV/cli/frontend.py:495,541; torchaudio is a requirements.txt dependency outside /root/reference, version 2.11 in this image:
+sinc interpolation with a Hann window, lowpass_filter_width 6, rolloff 0.99) and is pinned against torchaudio itself
+(`resample.*` entries of the golden file, written by the same generator).
+
 Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module.
 """
 import numpy as np
@@ -106,3 +111,43 @@ def align_prompt(feat_len, token_len):
     """CV/cli/frontend.py:498-502 (integer, bit-exact): token_len' = min(feat_len // 2, token_len), feat_len' = 2 token_len'."""
     t = min(int(feat_len) // 2, int(token_len))
     return 2 * t, t
+
+
+# ------------------------------------------------------------------------------------------ 16 kHz -> 24 kHz
+RS_ORIG, RS_NEW, RS_LPW, RS_ROLLOFF = 2, 3, 6, 0.99      # 16000 / 24000 reduced by their gcd; torchaudio defaults
+RS_WIDTH = int(np.ceil(RS_LPW * RS_ORIG / (min(RS_ORIG, RS_NEW) * RS_ROLLOFF)))          # 7
+RS_TAPS = 2 * RS_WIDTH + RS_ORIG                                                           # 16
+
+
+def resample_kernel():
+    """torchaudio.functional._get_sinc_resample_kernel(16000, 24000, gcd 8000): [3 phases, 16 taps] float32.
+    Phase p's filter is sinc(pi t) cos^2(pi t / 12) * 0.99 at t = 1.98 (k - 7) / 2 - 1.98 p / 3, t clamped to [-6, 6]
+    (the phase offset is formed in float32 first, as torch's int / int division does, then everything runs in float64)."""
+    base = min(RS_ORIG, RS_NEW) * RS_ROLLOFF
+    idx = np.arange(-RS_WIDTH, RS_WIDTH + RS_ORIG, dtype=np.float64)[None, :] / RS_ORIG
+    ph = (np.arange(0, -RS_NEW, -1).astype(np.float32) / np.float32(RS_NEW)).astype(np.float64)[:, None]
+    t = np.clip((ph + idx) * base, -RS_LPW, RS_LPW)
+    window = np.cos(t * np.pi / RS_LPW / 2) ** 2
+    t = t * np.pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+        k = np.where(t == 0, 1.0, np.sin(t) / t)
+    return (k * window * (base / RS_ORIG)).astype(np.float32)
+
+
+def resample_len(n_in):
+    """ceil(3 n / 2) (functional._apply_sinc_resample_kernel: target_length)."""
+    return (RS_NEW * int(n_in) + RS_ORIG - 1) // RS_ORIG
+
+
+def resample_16k_to_24k(x):
+    """x: [L] or [B, L] -> [B, ceil(3L/2)] float32: y[3 i + p] = sum_k xpad[2 i + k] h[p][k], xpad = x padded 7 left, 9 right."""
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[None]
+    L = x.shape[1]
+    h = resample_kernel().astype(np.float64)
+    xp = np.pad(x, ((0, 0), (RS_WIDTH, RS_WIDTH + RS_ORIG)))
+    n_i = (xp.shape[1] - RS_TAPS) // RS_ORIG + 1
+    idx = np.arange(n_i)[:, None] * RS_ORIG + np.arange(RS_TAPS)[None, :]
+    y = np.einsum("bik,pk->bip", xp[:, idx], h).reshape(x.shape[0], -1)
+    return y[:, :resample_len(L)].astype(np.float32)

@@ -60,7 +60,41 @@ def test_host_rejects_cpu_tensors_and_other_configs():
         mel_spectrogram(torch.zeros(1, 4800), n_fft=1024)           # only the CosyVoice2 feat_extractor is built
 
 
+def test_oracle_resample_matches_torchaudio_golden(golden):
+    """torchaudio.transforms.Resample(16000, 24000) is what frontend.py:495 calls; the golden entries are its outputs."""
+    g = golden("prompt_mel")
+    assert np.array_equal(PO.resample_kernel(), g["resample.kernel"])          # the 3 x 16 polyphase filter, bit for bit
+    for name in ("rs_a", "rs_odd", "rs_tiny"):
+        y = PO.resample_16k_to_24k(g[name + ".in"])[0]
+        assert y.shape == g[name + ".out"].shape == (PO.resample_len(len(g[name + ".in"])),)
+        assert np.abs(y - g[name + ".out"]).max() < 1e-6
+
+
 # ------------------------------------------------------------------------------------------ GPU: parity through the C ABI
+@pytest.mark.gpu
+def test_gpu_resample_matches_torchaudio_golden_and_chain(golden):
+    from cosyvoice2_eu_b200 import extract_speech_feat, resample_16k_to_24k
+    g = golden("prompt_mel")
+    for name in ("rs_a", "rs_odd", "rs_tiny"):
+        y = resample_16k_to_24k(torch.from_numpy(g[name + ".in"])[None])
+        ref = g[name + ".out"]
+        assert tuple(y.shape) == (1, len(ref))
+        assert np.abs(y[0].cpu().numpy() - ref).max() < 1e-6
+    # the chain a request runs (frontend.py:495-496): 16 kHz prompt -> 24 kHz -> log-mel, all on the device
+    y = resample_16k_to_24k(torch.from_numpy(g["rs_a.in"])[None])
+    feat, feat_len = extract_speech_feat(y)
+    assert np.abs(feat[0].cpu().numpy() - g["rs_a.mel"].T).max() < MEL_TOL
+    # ragged batch == single rows, bit for bit; padding is zero
+    xs = [g["rs_a.in"], g["rs_odd.in"], g["rs_tiny.in"]]
+    host = torch.zeros(3, 16000)
+    for i, x in enumerate(xs):
+        host[i, :len(x)] = torch.from_numpy(x)
+    yb, nb = resample_16k_to_24k(host, lengths=torch.tensor([len(x) for x in xs], dtype=torch.int32))
+    assert nb.tolist() == [PO.resample_len(len(x)) for x in xs]
+    for i, x in enumerate(xs):
+        one = resample_16k_to_24k(torch.from_numpy(x)[None])[0]
+        assert torch.equal(yb[i, :len(one)], one) and not yb[i, len(one):].any()
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
 def test_gpu_matches_reference_golden(golden, name):
