@@ -29,6 +29,7 @@ constexpr int kKpad = 976;         // padded to a multiple of the k step
 constexpr int kBinsPad = 1024;     // table / spectrum row length
 constexpr int kBandMax = 64;       // widest mel band in bins (top band: 49)
 constexpr int kTM = 128, kTN = 64, kTK = 16;
+constexpr int kDftSmemA = 2 * kTK * (kTM + 2) * 8, kDftSmem = kDftSmemA + 2 * kTK * kTN * 8;
 
 struct Tables {
   float2* cs = nullptr;     // [kKpad][kBinsPad] (cos, sin)(2 pi n k / N); zero outside n < 961, k < 961
@@ -62,13 +63,15 @@ __device__ __forceinline__ float wave_reflect(const float* __restrict__ w, int i
   return __ldg(w + i);
 }
 
-// grid (frame tiles, bin tiles, B), 256 threads; thread (ty, tx) owns frames ty*8..+7 and bins tx*4..+3 of the 128 x 64 tile
+// grid (frame tiles, bin tiles, B), 256 threads; thread (ty, tx) owns frames ty*8..+7 and bins tx*2, tx*2+1, 32+tx*2, 33+tx*2 of the 128 x 64 tile
 // (32 packed accumulators; per k: 6 LDS.128 feed 32 FFMA2).
 __global__ void __launch_bounds__(256, 2) pm_dft_mag_kernel(const float* __restrict__ wav, long long wav_stride,
                                                          const int* __restrict__ n_samples, const float2* __restrict__ cs,
                                                          const float* __restrict__ win, float* __restrict__ spec, int T_alloc) {
-  __shared__ __align__(16) float2 As[2][kTK][kTM];    // (e, o)
-  __shared__ __align__(16) float2 Bs[2][kTK][kTN];    // (cos, sin)
+  extern __shared__ __align__(16) uint8_t pm_smem[];
+  // (e, o) tile, rows padded by 16 B: the k-fastest stores below are 2-way conflicts, not 16-way; then the (cos, sin) tile
+  float2 (*As)[kTK][kTM + 2] = reinterpret_cast<float2 (*)[kTK][kTM + 2]>(pm_smem);
+  float2 (*Bs)[kTK][kTN] = reinterpret_cast<float2 (*)[kTK][kTN]>(pm_smem + kDftSmemA);
   const int b = blockIdx.z;
   const int L = __ldg(n_samples + b);
   const int T = frames_of(L);
@@ -78,7 +81,8 @@ __global__ void __launch_bounds__(256, 2) pm_dft_mag_kernel(const float* __restr
   const float* w = wav + (long long)b * wav_stride;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int lf = tid & 127, lk = tid >> 7;    // A loader: frame fastest (conflict-free smem stores), 2 k rows per pass
+  const int lj = tid & 15, lfs = tid >> 4;    // A loader: n fastest -- a warp reads two frames' 64-byte runs (forward and mirrored), 2-4 lines
+                                              // per instruction instead of 32 (ncu: the frame-fastest mapping was L1TEX bound at 92 %)
   const int bk = tid >> 4, bn = (tid & 15) * 4;  // B loader: one k row, 4 bins
 
   float2 acc[8][4];
@@ -90,16 +94,17 @@ __global__ void __launch_bounds__(256, 2) pm_dft_mag_kernel(const float* __restr
   float2 ra[8];
   float4 rb[2];
   auto fetch = [&](int kb) {
-    const int base = (t0 + lf) * kHop - kPad;      // first sample of the frame in the unpadded signal
-    const bool live = t0 + lf < T;
+    const int n = kb + lj;
+    const float wn = n < kKfold ? __ldg(win + n) : 0.f;
+    const bool single = n == 0 || n == kNfft / 2;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const int n = kb + lk + 2 * i;
+      const int f = lfs + 16 * i;
+      const int base = (t0 + f) * kHop - kPad;      // first sample of the frame in the unpadded signal
       float e = 0.f, o = 0.f;
-      if (live && n < kKfold) {
-        const float wn = __ldg(win + n);
+      if (t0 + f < T && n < kKfold) {
         const float a = wave_reflect(w, base + n, L) * wn;
-        if (n == 0 || n == kNfft / 2) {
+        if (single) {
           e = a;
         } else {
           const float c = wave_reflect(w, base + kNfft - n, L) * wn;
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(256, 2) pm_dft_mag_kernel(const float* __restr
   };
   auto stash = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) As[buf][lk + 2 * i][lf] = ra[i];
+    for (int i = 0; i < 8; i++) As[buf][lj][lfs + 16 * i] = ra[i];
     float4* dst = reinterpret_cast<float4*>(&Bs[buf][bk][bn]);
     dst[0] = rb[0];
     dst[1] = rb[1];
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(256, 2) pm_dft_mag_kernel(const float* __restr
       }
 #pragma unroll
       for (int j = 0; j < 2; j++) {
-        const float4 f = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4 + 2 * j]);
+        const float4 f = *reinterpret_cast<const float4*>(&Bs[buf][kk][32 * j + tx * 2]);   // 16 lanes x 16 B contiguous
         bb[2 * j] = make_float2(f.x, f.y);
         bb[2 * j + 1] = make_float2(f.z, f.w);
       }
@@ -157,12 +162,14 @@ __global__ void __launch_bounds__(256, 2) pm_dft_mag_kernel(const float* __restr
   for (int i = 0; i < 8; i++) {
     const int t = t0 + ty * 8 + i;
     if (t >= T) continue;
-    float4 m;
-    m.x = sqrtf(acc[i][0].x * acc[i][0].x + acc[i][0].y * acc[i][0].y + 1e-9f);
-    m.y = sqrtf(acc[i][1].x * acc[i][1].x + acc[i][1].y * acc[i][1].y + 1e-9f);
-    m.z = sqrtf(acc[i][2].x * acc[i][2].x + acc[i][2].y * acc[i][2].y + 1e-9f);
-    m.w = sqrtf(acc[i][3].x * acc[i][3].x + acc[i][3].y * acc[i][3].y + 1e-9f);
-    *reinterpret_cast<float4*>(spec + ((size_t)b * T_alloc + t) * kBinsPad + k0 + tx * 4) = m;
+    float* row = spec + ((size_t)b * T_alloc + t) * kBinsPad + k0 + tx * 2;    // bins tx*2, tx*2+1 and 32 + the same
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      float2 m;
+      m.x = sqrtf(acc[i][2 * j].x * acc[i][2 * j].x + acc[i][2 * j].y * acc[i][2 * j].y + 1e-9f);
+      m.y = sqrtf(acc[i][2 * j + 1].x * acc[i][2 * j + 1].x + acc[i][2 * j + 1].y * acc[i][2 * j + 1].y + 1e-9f);
+      *reinterpret_cast<float2*>(row + 32 * j) = m;
+    }
   }
 }
 
@@ -317,6 +324,7 @@ Tables& tables_for_device() {
   pm_table_kernel<<<dim3(kBinsPad / 256, kKpad), 256>>>(cs, t.win);
   CV2_CUDA(cudaGetLastError());
   CV2_CUDA(cudaDeviceSynchronize());
+  CV2_CUDA(cudaFuncSetAttribute(pm_dft_mag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDftSmem));
   t.cs = cs;
   return t;
 }
@@ -339,7 +347,7 @@ void launch_prompt_mel(const float* wav, long long wav_stride, const int* n_samp
   const int T_out = prompt_mel_frames(max_samples);
   const int T_alloc = t_alloc_of(max_samples);
   float* spec = static_cast<float*>(ws);
-  pm_dft_mag_kernel<<<dim3(T_alloc / kTM, kBinsPad / kTN, B), 256, 0, st>>>(wav, wav_stride, n_samples, t.cs, t.win, spec, T_alloc);
+  pm_dft_mag_kernel<<<dim3(T_alloc / kTM, kBinsPad / kTN, B), 256, kDftSmem, st>>>(wav, wav_stride, n_samples, t.cs, t.win, spec, T_alloc);
   CV2_CUDA(cudaGetLastError());
   pm_mel_log_kernel<<<dim3((T_out + 3) / 4, B), 128, 0, st>>>(spec, T_alloc, n_samples, t.mel_w, t.mel_lo, t.mel_cnt, mel, T_out, mel_len);
   CV2_CUDA(cudaGetLastError());
