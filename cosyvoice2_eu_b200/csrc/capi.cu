@@ -204,7 +204,8 @@ int cv2_flow_forward(cv2_engine* h, void* stream, const int32_t* token, int toke
   CV2_CHECK(token && token_len && prompt_token && prompt_len && prompt_feat && prompt_feat_len && embedding && rand_noise &&
                 t_steps_dev && dt_steps_host && mel_out && workspace,
             "null argument");
-  CV2_CHECK(B >= 1 && max_tok_total >= 4 && n_steps >= 1, "bad sizes B=%d max_tok_total=%d n_steps=%d", B, max_tok_total, n_steps);
+  CV2_CHECK(B >= 1 && max_tok_total >= (finalize ? 1 : 4) && n_steps >= 1,   // a non-final chunk keeps 3 look-ahead tokens back
+            "bad sizes B=%d max_tok_total=%d n_steps=%d", B, max_tok_total, n_steps);
   CV2_CHECK(2 * max_tok_total <= noise_stride, "sequence of %d mel frames exceeds the CFM noise buffer (%d)", 2 * max_tok_total,
             noise_stride);
   Arena ws;

@@ -179,6 +179,11 @@ class B200Flow:
         mel_lens = [2 * (a + b - drop) - c for a, b, c in zip(tl, pl, fl)]
         mel_T = max(mel_lens)
         assert min(mel_lens) > 0
+        if 2 * max_total > self.rand_noise.shape[2]:
+            # the reference slices its fixed noise buffer (flow_matching.py:195-198, z = rand_noise[:, :, :T]) and then fails on
+            # a shape mismatch: 15000 mel frames = 300 s is the longest sequence the CFM can take
+            raise _lib.Cv2Error(f"prompt + tokens = {max_total} tokens need {2 * max_total} mel frames; the CFM noise buffer holds "
+                                f"{self.rand_noise.shape[2]}")
         # pinned staging buffers -> async H2D on the current stream
         tok = self._staging("tok", (B, max(tl)), torch.int32)
         ptk = self._staging("ptk", (B, max(max(pl), 1)), torch.int32)

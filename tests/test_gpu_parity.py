@@ -340,3 +340,36 @@ def test_2sm_kernels_match_1sm_kernels(engine, golden):
     print("2-SM vs 1-SM kernels: max-abs mel diff", d, "mel std", mel_1sm.std())
     assert np.isfinite(mel_2sm).all()
     assert d < 2e-3
+
+
+@pytest.mark.parametrize("n_tok,n_prompt,seed", [(20, 0, 11), (1, 5, 12), (3, 0, 13), (2, 1, 14)])
+def test_edge_cases_against_oracle(engine, fixture_weights, n_tok, n_prompt, seed):
+    """No prompt at all (the SFT / instruct modes pass zeros(1, 0) tokens and zeros(1, 0, 80) mel, CV/cli/model.py:343-347 defaults),
+    a single token, and the shortest mixes: flow mel and hift waveform against the oracle restatement."""
+    import token2wav_oracle as O
+    flow, hift, _ = engine
+    fs, hs = fixture_weights
+    u = _utt(dict(n_tok=n_tok, n_prompt=n_prompt, seed=seed))
+    assert u["prompt_token"].shape == (1, n_prompt) and u["prompt_feat"].shape == (1, 2 * n_prompt, 80)
+    mel, _ = flow.inference(u["token"], None, u["prompt_token"], None, u["prompt_feat"], None, u["embedding"], False, True)
+    with torch.inference_mode():
+        ref = O.flow_inference(fs, flow.rand_noise.cpu(), u["token"].long(), u["prompt_token"].long(), u["prompt_feat"], u["embedding"])
+    assert tuple(mel.shape) == tuple(ref.shape) == (1, 80, 2 * n_tok)
+    err = float((mel.cpu() - ref).abs().max())
+    assert err < MEL_TOL, err
+    noise = T(weights.make_nsf_noise(2 * n_tok * 480, seed))
+    wav, _ = hift.inference(mel, noise=noise)
+    with torch.inference_mode():
+        wav_ref, _ = O.hift_inference(hs, mel.cpu(), noise=noise)
+    assert tuple(wav.shape) == tuple(wav_ref.shape) == (1, 2 * n_tok * 480)
+    s = snr_db(wav_ref.numpy(), wav.cpu().numpy())
+    assert s >= SNR_MIN, s
+
+
+def test_too_long_for_the_cfm_noise_buffer_is_rejected(engine):
+    from cosyvoice2_eu_b200.lib import Cv2Error
+    flow = engine[0]
+    n = flow.rand_noise.shape[2] // 2 + 1
+    with pytest.raises(Cv2Error):
+        flow.inference_batch([torch.zeros(n, dtype=torch.int32)], [torch.zeros(0, dtype=torch.int32)], [torch.zeros(0, 80)],
+                             [torch.zeros(192)])
