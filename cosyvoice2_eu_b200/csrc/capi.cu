@@ -277,6 +277,13 @@ int cv2_crossfade(void* stream, float* speech, const float* old_tail, const doub
   CV2_API_END
 }
 
+int cv2_mel_time_stretch(void* stream, const float* mel, int T_in, float* out, int T_out, int rows) {
+  CV2_API_BEGIN
+  CV2_CHECK(mel && out && T_in >= 1 && T_out >= 1 && rows >= 1, "cv2_mel_time_stretch: bad arguments");
+  launch_mel_time_stretch(mel, T_in, out, T_out, rows, (cudaStream_t)stream);
+  CV2_API_END
+}
+
 int cv2_prompt_mel_frames(int n_samples) { return prompt_mel_frames(n_samples); }
 
 size_t cv2_prompt_mel_workspace_bytes(int B, int max_samples) { return prompt_mel_workspace_bytes(B, max_samples); }

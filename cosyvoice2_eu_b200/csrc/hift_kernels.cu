@@ -545,4 +545,24 @@ void launch_crossfade(float* speech, const float* old_tail, const double* window
   CV2_LAUNCH_CHECK();
 }
 
+// speed change of an offline utterance (cosyvoice/cli/model.py:325-327): F.interpolate(mel, size = int(T / speed), mode = 'linear'),
+// align_corners = False: source position (j + 0.5) * T_in / T_out - 0.5 clamped at 0, neighbours blended linearly.
+__global__ void mel_time_stretch_kernel(const float* __restrict__ x, int T_in, float* __restrict__ y, int T_out, int rows) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (j >= T_out || r >= rows) return;
+  const float scale = (float)T_in / (float)T_out;
+  float src = ((float)j + 0.5f) * scale - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  const int i0 = min((int)src, T_in - 1);
+  const int i1 = min(i0 + 1, T_in - 1);
+  const float w1 = src - (float)i0, w0 = 1.f - w1;
+  const float* xr = x + (long long)r * T_in;
+  y[(long long)r * T_out + j] = w0 * xr[i0] + w1 * xr[i1];
+}
+void launch_mel_time_stretch(const float* x, int T_in, float* y, int T_out, int rows, cudaStream_t st) {
+  mel_time_stretch_kernel<<<dim3((T_out + 127) / 128, rows), 128, 0, st>>>(x, T_in, y, T_out, rows);
+  CV2_LAUNCH_CHECK();
+}
+
 }  // namespace cv2

@@ -15,5 +15,6 @@ void launch_reflect_row0(float* x, int B, int T_alloc, int C, cudaStream_t st);
 void launch_istft(const float* cp, int F_alloc, int ld, const int* lens, int len_all, float* wav, long long wav_bstride, int B, int max_len, cudaStream_t st,
                   short* pcm = nullptr);   // optional int16 PCM copy of the waveform (same layout)
 void launch_crossfade(float* speech, const float* old_tail, const double* window, int n, cudaStream_t st);
+void launch_mel_time_stretch(const float* x, int T_in, float* y, int T_out, int rows, cudaStream_t st);
 
 }  // namespace cv2

@@ -332,7 +332,12 @@ class B200Token2Wav:
         else:
             if speed != 1.0:
                 assert cache is None, 'speed change only support non-stream inference mode'
-                tts_mel = torch.nn.functional.interpolate(tts_mel, size=int(tts_mel.shape[2] / speed), mode='linear')
+                stretched = torch.empty(tts_mel.shape[0], tts_mel.shape[1], int(tts_mel.shape[2] / speed), dtype=torch.float32,
+                                        device=tts_mel.device)
+                src = tts_mel.contiguous()
+                _lib.check(self.flow.eng.lib.cv2_mel_time_stretch(_stream(), _lib.ptr(src), src.shape[2], _lib.ptr(stretched),
+                                                                  stretched.shape[2], src.shape[0] * src.shape[1]))
+                tts_mel = stretched
             tts_speech, tts_source = self.hift.inference(speech_feat=tts_mel, cache_source=hift_cache_source, noise=noise)
             if cache is not None:
                 tts_speech = self._fade_in_out(tts_speech, cache['speech'])

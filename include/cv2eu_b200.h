@@ -97,6 +97,10 @@ int cv2_hift_forward_pcm16(cv2_engine* e, void* stream, const float* mel, int me
 /* ---- streaming glue: fade_in_out (cosyvoice/utils/common.py:142-150) on the device.  window: [2n] f64 device. ---- */
 int cv2_crossfade(void* stream, float* speech, const float* old_tail, const double* window, int n);
 
+/* speed change of an offline utterance (cosyvoice/cli/model.py:325-327): out[r, :] = F.interpolate(mel[r, :], size = T_out,
+ * mode = 'linear') for `rows` = B * 80 rows; T_out = int(T_in / speed).  mel / out: fp32 device, contiguous rows. */
+int cv2_mel_time_stretch(void* stream, const float* mel, int T_in, float* out, int T_out, int rows);
+
 /* ---- prompt features: the 24 kHz log-mel of the prompt waveform, replacing
  * matcha.utils.audio.mel_spectrogram (third_party/Matcha-TTS/matcha/utils/audio.py:45-82) at the cosyvoice2.yaml:152-160
  * settings as called by CosyVoiceFrontEnd._extract_speech_feat (cosyvoice/cli/frontend.py:285-289), for a batch of prompts.

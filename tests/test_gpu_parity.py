@@ -373,3 +373,24 @@ def test_too_long_for_the_cfm_noise_buffer_is_rejected(engine):
     with pytest.raises(Cv2Error):
         flow.inference_batch([torch.zeros(n, dtype=torch.int32)], [torch.zeros(0, dtype=torch.int32)], [torch.zeros(0, 80)],
                              [torch.zeros(192)])
+
+
+@pytest.mark.parametrize("speed", [0.8, 1.25, 2.0])
+def test_speed_change_matches_linear_interpolation(engine, golden, speed):
+    """token2wav(speed != 1) (CV/cli/model.py:325-327): the mel is resampled in time with F.interpolate(mode='linear') before the
+    vocoder.  Kernel vs the torch fp32 op on the same mel, and the whole call's output length."""
+    import ctypes as C
+    from cosyvoice2_eu_b200 import lib
+    flow, hift, t2w = engine
+    g = golden("tiny")
+    mel = T(g["mel"]).cuda().contiguous()
+    T_out = int(mel.shape[2] / speed)
+    out = torch.empty(1, 80, T_out, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    lib.check(lib.load().cv2_mel_time_stretch(st, lib.ptr(mel), mel.shape[2], lib.ptr(out), T_out, 80))
+    ref = torch.nn.functional.interpolate(mel, size=T_out, mode="linear")
+    assert float((out - ref).abs().max()) < 1e-5
+    u = _utt(g)
+    wav = t2w.token2wav(u["token"], u["prompt_token"], u["prompt_feat"], u["embedding"], 0, "speed-test", stream=False, finalize=True,
+                        speed=speed)
+    assert wav.shape == (1, 480 * T_out)
