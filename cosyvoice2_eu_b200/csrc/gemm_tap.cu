@@ -527,6 +527,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (which == 1) qdst = p.q2;
             which = which < 2 ? 0 : which - 1;
           }
+          gtrace(tb, ti, 30 + which);
           if (which < 2) {
             const float sc = valid ? (which == 0 ? p.q_scale : 1.f) : 0.f;
             float w[32];

@@ -22,7 +22,7 @@ torch.cuda.synchronize()
 L.cv2_debug_set_ffn_trace(None)
 b = buf.cpu().numpy()[8192:]
 names = {1: "mma: tile start", 2: "mma: tmem_empty ok", 3: "mma: stage full", 4: "mma: tile committed",
-         10: "epi: wait tmem_full", 11: "epi: tmem_full ok", 12: "epi: chunk tmem_ld+bias done", 13: "epi: residual added", 14: "epi: out32 stored",
+         30: "epi: q chunk store", 31: "epi: k chunk store", 32: "epi: v chunk store", 10: "epi: wait tmem_full", 11: "epi: tmem_full ok", 12: "epi: chunk tmem_ld+bias done", 13: "epi: residual added", 14: "epi: out32 stored",
          15: "epi: chunks done", 16: "epi: pre bar1", 17: "epi: bar1 ok", 18: "epi: pre bar2", 19: "epi: bar2 ok", 20: "epi: tile done"}
 allev = []
 for off, who in ((0, "epi warp 0"), (2048, "epi warp 13"), (4096, "MMA thread")):
