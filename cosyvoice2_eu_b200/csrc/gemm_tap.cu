@@ -25,6 +25,11 @@ struct GemmSmem {
   static constexpr int kParts = BN >= 128 ? 4 : 2;        // column parts of a tile = epilogue warps per TMEM lane quarter
   static constexpr int kEpiWarps = 4 * kParts;            // 16 (8 for BN = 64): enough warps to hide TMEM / global / MUFU latency
   static constexpr int kThreads = 64 + kEpiWarps * 32;    // + TMA warp + MMA warp
+  // BN = 256: the 16 epilogue warps work as two independent groups of 8, group g draining accumulator buffer g (tiles of
+  // parity g).  One SM's store path drains ~32 B/clk however the stores are issued (profiles/micro/st_path.cu), and with all 16
+  // warps on one tile their accumulator-read / convert phases and their store phases alternated; two groups on two tiles run
+  // out of phase, so the store path stays busy while the other group computes.
+  static constexpr int kGroups = BN >= 256 ? 2 : 1;
   static constexpr int kBBytes = (BN / CS) * kKBlock * 2;   // CS = 2 (2-SM MMA): every CTA stages half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   // the GEMMs of this path are short-K (K = 256..1536) and TMA-latency bound: what matters is bytes in flight.  The epilogue
@@ -162,7 +167,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(&tmem_full[i], 1);               // CS = 2: multicast commit
-      mbar_init(&tmem_empty[i], CS * kEpiWarps); // CS = 2: leader's, released by the epilogue warps of both CTAs
+      mbar_init(&tmem_empty[i], CS * kEpiWarps / SM::kGroups); // released by the warps of the owning group (CS = 2: of both CTAs, on the leader's)
     }
     fence_barrier_init();
   }
@@ -246,23 +251,29 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // --------------------------------- epilogue -----------------------------------
-    const int ew = warp;
-    const int q = warp & 3;              // TMEM lane quarter accessible to this warp
+    constexpr int kGroups = SM::kGroups;
+    constexpr int kGWarps = kEpiWarps / kGroups;   // warps per group: 8
+    constexpr int kGParts = kParts / kGroups;      // column parts of a tile inside a group: 2 (BN = 256), 4 (128), 2 (64)
+    const int grp = warp / kGWarps;      // this warp's group = the accumulator buffer it drains
+    const int ew = warp % kGWarps;
+    const int q = warp & 3;              // TMEM lane quarter accessible to this warp (kGWarps is a multiple of 4)
     const int half = ew >> 2;            // which part of the tile's columns this thread owns
     const int r = q * 32 + lane;
-    constexpr int kHalfCols = BN / kParts;    // 64 / 32 / 32
-    constexpr int kChunks = kHalfCols / 32;   // 2 / 1 / 1
+    constexpr int kHalfCols = BN / kGParts;   // 128 / 32 / 32
+    constexpr int kChunks = kHalfCols / 32;   // 4 / 1 / 1
     float* stg = nullptr;                // (epilogue I/O is direct 256-bit global access: no staging tile)
-    float* red_a = red;                  // [kParts][128] each
-    float* red_b = red + kParts * 128;
-    float* red_c = red + 2 * kParts * 128;
-    float* red_d = red + 3 * kParts * 128;
+    float* red_g = red + grp * 4 * kGParts * 128;
+    float* red_a = red_g;                // [kGParts][128] each, per group
+    float* red_b = red_g + kGParts * 128;
+    float* red_c = red_g + 2 * kGParts * 128;
+    float* red_d = red_g + 3 * kGParts * 128;
     auto red_sum = [&](const float* a) {
       float t = 0.f;
 #pragma unroll
-      for (int k = 0; k < kParts; k++) t += a[k * 128 + r];
+      for (int k = 0; k < kGParts; k++) t += a[k * 128 + r];
       return t;
     };
+    auto group_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kGWarps * 32) : "memory"); };
     const int ek0 = Cfg::EMIT0 < 0 ? p.emit[0].kind : Cfg::EMIT0;
     const int ek1 = Cfg::EMIT1 < 0 ? p.emit[1].kind : Cfg::EMIT1;
     const int ek2 = Cfg::EMIT2 < 0 ? p.emit[2].kind : Cfg::EMIT2;
@@ -299,6 +310,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       TileCoord c;
       bool tvalid;
       if (!tile_coord<CS>(p, tile, n_tiles, t_tiles, BN, rank, row_count, c, tvalid)) continue;
+      if (kGroups > 1 && (lt & 1) != grp) {   // the other group's tile
+        lt++;
+        continue;
+      }
       if (CS > 1 && !tvalid) {   // filler tile of an odd tail: drain the accumulator, store nothing
         mbar_wait(&tmem_full[lt & 1], (lt >> 1) & 1);
         tc_fence_after();
@@ -350,7 +365,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (i < nv) sum += __uint_as_float(raw[i]) + bch[i];
         }
         red_a[half * 128 + r] = sum;
-        epi_bar<kEpiWarps * 32>();
+        group_bar();
         mean = red_sum(red_a) / (float)ncols;
         float sq = 0.f;
 #pragma unroll 1
@@ -370,7 +385,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
         red_b[half * 128 + r] = sq;
-        epi_bar<kEpiWarps * 32>();
+        group_bar();
         rstd = rsqrtf(red_sum(red_b) / (float)ncols + p.ln_eps);
       }
 
@@ -554,7 +569,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_st_wait();
         red_c[half * 128 + r] = sum2;
         gtrace(tb, ti, 16);
-        epi_bar<kEpiWarps * 32>();
+        group_bar();
         gtrace(tb, ti, 17);
         const float mean2 = red_sum(red_c) / (float)ncols;
         float sq2 = 0.f;
@@ -573,7 +588,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         red_d[half * 128 + r] = sq2;
         gtrace(tb, ti, 18);
-        epi_bar<kEpiWarps * 32>();
+        group_bar();
         gtrace(tb, ti, 19);
         const float var2 = red_sum(red_d) / (float)ncols;
 #pragma unroll 1
