@@ -13,6 +13,7 @@
 
 #include "attention.cuh"
 #include "common.cuh"
+#include "epi_util.cuh"
 #include "host_util.h"
 
 namespace cv2 {
@@ -713,23 +714,12 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       uint32_t raw[32];
       tmem_ld32(lane_addr + k9TmemO + c * 32, raw);
       tmem_ld_wait();
-      uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+      // lane-pair transposed 256-bit stores: 16 rows x 64 contiguous bytes per instruction (row-per-lane 16-byte stores drain at
+      // half the SM's store-path rate, profiles/micro/st_path.cu)
+      float w[32];
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; e++) f[e] = valid ? __uint_as_float(raw[i * 8 + e]) * inv : 0.f;
-        __half2 h0 = __floats2half2_rn(f[0], f[1]);
-        __half2 h1 = __floats2half2_rn(f[2], f[3]);
-        __half2 h2 = __floats2half2_rn(f[4], f[5]);
-        __half2 h3 = __floats2half2_rn(f[6], f[7]);
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&h0);
-        u.y = *reinterpret_cast<uint32_t*>(&h1);
-        u.z = *reinterpret_cast<uint32_t*>(&h2);
-        u.w = *reinterpret_cast<uint32_t*>(&h3);
-        d4[i] = u;
-      }
+      for (int e = 0; e < 32; e++) w[e] = valid ? __uint_as_float(raw[e]) * inv : 0.f;
+      tile_store_f16(dst - (long long)lane * (p.heads * 64) + c * 32, (long long)p.heads * 64, nullptr, lane, w);
     }
   }
 
