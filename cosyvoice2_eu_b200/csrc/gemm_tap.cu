@@ -35,8 +35,8 @@ struct GemmSmem {
   // the GEMMs of this path are short-K (K = 256..1536) and TMA-latency bound: what matters is bytes in flight.  The epilogue
   // needs no shared memory (256-bit global accesses), so the ring takes all of it: 192 KB = 4 / 6 / 8 stages.
   static constexpr int kStages = (192 * 1024) / kStageBytes;
-  static constexpr int kRedOff = kStages * kStageBytes;   // 4 x [kParts][128] floats for LayerNorm exchanges
-  static constexpr int kBarOff = kRedOff + 4 * kParts * 128 * 4;
+  static constexpr int kRedOff = kStages * kStageBytes;   // 2 x 4 x [kParts][128] floats for LayerNorm exchanges
+  static constexpr int kBarOff = kRedOff + 2 * 4 * kParts * 128 * 4;   // double-buffered by tile parity (one barrier per LayerNorm)
   // per-column parameter vectors of the epilogue, staged once per CTA (the streaming residual / output traffic keeps evicting
   // them from the small L1 that is left next to a 192 KB ring: in the clock64 trace every re-read cost an L2 round trip)
   static constexpr int kVecBias = 2048, kVecLn = 256;     // bias [N <= 2048]; LayerNorm gamma/beta + emitted-LN gamma/beta [N <= 256]
@@ -262,11 +262,9 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int kHalfCols = BN / kGParts;   // 128 / 32 / 32
     constexpr int kChunks = kHalfCols / 32;   // 4 / 1 / 1
     float* stg = nullptr;                // (epilogue I/O is direct 256-bit global access: no staging tile)
-    float* red_g = red + grp * 4 * kGParts * 128;
-    float* red_a = red_g;                // [kGParts][128] each, per group
-    float* red_b = red_g + kGParts * 128;
-    float* red_c = red_g + 2 * kGParts * 128;
-    float* red_d = red_g + 3 * kGParts * 128;
+    float* red_g = red + grp * 2 * 4 * kGParts * 128;
+    float *red_a, *red_b, *red_c, *red_d;   // [kGParts][128] each, per group; set per tile (two sets, alternating: with ONE barrier per
+                                            // LayerNorm a fast thread may already write the next tile's sums while a slow one reads)
     auto red_sum = [&](const float* a) {
       float t = 0.f;
 #pragma unroll
@@ -324,6 +322,13 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         continue;
       }
       const int acc = lt & 1;
+      {
+        float* rb = red_g + ((lt / kGroups) & 1) * 4 * kGParts * 128;
+        red_a = rb;
+        red_b = rb + kGParts * 128;
+        red_c = rb + 2 * kGParts * 128;
+        red_d = rb + 3 * kGParts * 128;
+      }
       const int t = c.t0 + r;
       const bool valid = t < c.len;
       const int ncols = min(BN, p.N - c.n0);                         // valid columns of this tile
@@ -349,25 +354,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float mean = 0.f, rstd = 1.f;
       uint32_t raw[32];
       float v[32];
-      if (has_ln) {  // LayerNorm over the N columns of the row (whole row lives in this tile)
-        float sum = 0.f;
-#pragma unroll 1
-        for (int ch = 0; ch < kChunks; ch++) {
-          const int cl = my_c0 + ch * 32;
-          const int nv = min(32, ncols - cl);
-          if (nv <= 0) break;
-          tmem_ld32(taddr + ch * 32, raw);
-          float bch[32];
-          vload(vec_bias, c_bias, p.bias, c.n0 + cl, bch, nv == 32, nv);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i++)
-            if (i < nv) sum += __uint_as_float(raw[i]) + bch[i];
-        }
-        red_a[half * 128 + r] = sum;
-        group_bar();
-        mean = red_sum(red_a) / (float)ncols;
-        float sq = 0.f;
+      if (has_ln) {  // LayerNorm over the N columns of the row (whole row lives in this tile).  One pass over the accumulator:
+                     // sum and sum of squares together, var = E[x^2] - mean^2 in fp32 (<= 256 values of O(1): the cancellation
+                     // costs ~1e-5 relative on var, far inside the 1e-2 mel budget) -- one TMEM sweep and one barrier less per tile
+        float sum = 0.f, sq = 0.f;
 #pragma unroll 1
         for (int ch = 0; ch < kChunks; ch++) {
           const int cl = my_c0 + ch * 32;
@@ -380,16 +370,19 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 32; i++)
             if (i < nv) {
-              const float d = __uint_as_float(raw[i]) + bch[i] - mean;
-              sq = fmaf(d, d, sq);
+              const float x = __uint_as_float(raw[i]) + bch[i];
+              sum += x;
+              sq = fmaf(x, x, sq);
             }
         }
+        red_a[half * 128 + r] = sum;
         red_b[half * 128 + r] = sq;
         group_bar();
-        rstd = rsqrtf(red_sum(red_b) / (float)ncols + p.ln_eps);
+        mean = red_sum(red_a) / (float)ncols;
+        rstd = rsqrtf(fmaxf(red_sum(red_b) / (float)ncols - mean * mean, 0.f) + p.ln_eps);
       }
 
-      float sum2 = 0.f;
+      float sum2 = 0.f, sq2 = 0.f;
       const float* rv = has_rv ? p.rowvec + (long long)c.s * p.rowvec_ld : nullptr;
 #pragma unroll 1
       for (int ch = 0; ch < kChunks; ch++) {
@@ -559,6 +552,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 32; i++) {
             sum2 += v[i];
+            sq2 = fmaf(v[i], v[i], sq2);
             raw[i] = __float_as_uint(v[i]);
           }
           tmem_st32(taddr + ch * 32, raw);
@@ -568,29 +562,12 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (stat2) {  // LayerNorm of the final row value (pre-norm of the next sub-block), emitted as 16-bit
         tmem_st_wait();
         red_c[half * 128 + r] = sum2;
+        red_d[half * 128 + r] = sq2;
         gtrace(tb, ti, 16);
         group_bar();
         gtrace(tb, ti, 17);
         const float mean2 = red_sum(red_c) / (float)ncols;
-        float sq2 = 0.f;
-#pragma unroll 1
-        for (int ch = 0; ch < kChunks; ch++) {
-          const int nv = min(32, ncols - (my_c0 + ch * 32));
-          if (nv <= 0) break;
-          tmem_ld32(taddr + ch * 32, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i++)
-            if (i < nv) {
-              const float d = __uint_as_float(raw[i]) - mean2;
-              sq2 = fmaf(d, d, sq2);
-            }
-        }
-        red_d[half * 128 + r] = sq2;
-        gtrace(tb, ti, 18);
-        group_bar();
-        gtrace(tb, ti, 19);
-        const float var2 = red_sum(red_d) / (float)ncols;
+        const float var2 = fmaxf(red_sum(red_d) / (float)ncols - mean2 * mean2, 0.f);   // one pass, see has_ln above
 #pragma unroll 1
         for (int ch = 0; ch < kChunks; ch++) {
           const int cl = my_c0 + ch * 32;
