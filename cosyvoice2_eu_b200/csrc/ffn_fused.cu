@@ -26,7 +26,7 @@ static constexpr int kSlotBytes = 16384;        // remaining shared memory is we
 static constexpr int kOffW = kHBytes;
 static constexpr int kEpiW = 16;                 // epilogue warps: four per TMEM lane quarter
 static constexpr int kOffRed = kOffW + kSlots * kSlotBytes;
-static constexpr int kOffBar = kOffRed + 2 * 4 * 128 * 4;
+static constexpr int kOffBar = kOffRed + 2 * 2 * 4 * 128 * 4;   // (sum, sum of squares) x [4][128], double-buffered by tile parity
 static constexpr int kFfnSmem = kOffBar + 256;
 static constexpr int kFfnThreads = 64 + kEpiW * 32;
 static constexpr uint32_t kAcc1 = 0, kAcc2 = 256;   // TMEM columns: acc1 = 2 x 128, acc2 = 256
@@ -234,8 +234,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
     const int part = ew >> 2;                // 0..3: which quarter of the columns
     const int r = q * 32 + lane;
     float* stg = nullptr;                    // (epilogue I/O is direct 256-bit global access: no staging tile)
-    float* red_c = red;                      // [4][128]
-    float* red_d = red + 512;
+    float *red_c, *red_d;                    // [4][128] each; two sets alternating by tile (one barrier per LayerNorm)
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     int lt = 0, use1[2] = {0, 0}, g = 0;
     long long* tb = (blockIdx.x == 0 && warp == 0 && lane == 0 && p.trace) ? p.trace + 4096 : nullptr;
@@ -287,7 +286,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
       ffn_trace(tb, ti, 21);
       const uint32_t taddr = lane_addr + kAcc2 + part * 64;
       const bool want_ln = p.emit_ln.ptr != nullptr;
-      float sum2 = 0.f;
+      float sum2 = 0.f, sq2 = 0.f;
       uint32_t raw[32];
       float v[32], tmp[32];
 #pragma unroll 1
@@ -315,6 +314,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 32; i++) {
             sum2 += v[i];
+            sq2 = fmaf(v[i], v[i], sq2);
             raw[i] = __float_as_uint(v[i]);
           }
           tmem_st32(taddr + ch * 32, raw);
@@ -322,23 +322,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
       }
       if (want_ln) {
         tmem_st_wait();
+        // one sweep: sum and sum of squares were taken while the row was written back; var = E[x^2] - mean^2 (fp32, 256 values)
+        red_c = red + (lt & 1) * 1024;
+        red_d = red_c + 512;
         red_c[part * 128 + r] = sum2;
-        ffn_bar();
-        const float mean2 = (red_c[r] + red_c[128 + r] + red_c[256 + r] + red_c[384 + r]) * (1.f / 256.f);
-        float sq2 = 0.f;
-#pragma unroll 1
-        for (int ch = 0; ch < 2; ch++) {
-          tmem_ld32(taddr + ch * 32, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i++) {
-            const float d = __uint_as_float(raw[i]) - mean2;
-            sq2 = fmaf(d, d, sq2);
-          }
-        }
         red_d[part * 128 + r] = sq2;
         ffn_bar();
-        const float rstd2 = rsqrtf((red_d[r] + red_d[128 + r] + red_d[256 + r] + red_d[384 + r]) * (1.f / 256.f) + p.emit_ln.f);
+        const float mean2 = (red_c[r] + red_c[128 + r] + red_c[256 + r] + red_c[384 + r]) * (1.f / 256.f);
+        const float rstd2 = rsqrtf(fmaxf((red_d[r] + red_d[128 + r] + red_d[256 + r] + red_d[384 + r]) * (1.f / 256.f) - mean2 * mean2, 0.f) + p.emit_ln.f);
 #pragma unroll 1
         for (int ch = 0; ch < 2; ch++) {
           const int cbase = part * 64 + ch * 32;
