@@ -165,6 +165,10 @@ def main_reference(args):
 
 
 def main():
+    if os.environ.get("CV2_DBG_SKIP_EPI"):
+        # the GEMM epilogue measurement switch skips work: a bench line taken with it would be invalid
+        sys.exit("bench.py refuses to run with CV2_DBG_SKIP_EPI set (work would be skipped inside the timed region); use "
+                 "profiles/prof_flow.py for that experiment")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
