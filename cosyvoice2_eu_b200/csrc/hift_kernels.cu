@@ -445,77 +445,91 @@ void launch_reflect_row0(float* x, int B, int T_alloc, int C, cudaStream_t st) {
 __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp, int F_alloc, int ld, const int* __restrict__ lens,
                                                     int len_all, float* __restrict__ wav, long long wav_bstride,
                                                     short* __restrict__ pcm) {
-  __shared__ float Xre[260][9];
-  __shared__ float Xim[260][9];
+  // Per frame ONCE: spectrum -> all 16 windowed samples of its inverse real DFT, using y[n] = A[n] - B[n], y[16-n] = A[n] + B[n]
+  // (A = cosine part, B = sine part) so that the (A[n], B[n]) pairs of n = 1..7 are 49 packed FFMA2 on (re_k, im_k) x (2 cos, 2 sin);
+  // the samples go through shared memory (rows padded to 80 B: conflict-free 16-byte accesses), then every thread overlap-adds the
+  // four frames covering its hop.  (The previous form re-evaluated 7 complex terms for each of the 16 (frame, sample) pairs of a
+  // hop: 504 instructions per thread, issue bound at 83 %.)
+  __shared__ __align__(16) float ys[259][20];
   const int b = blockIdx.y;
   const int len = lens ? lens[b] : len_all;
   const int F = len * 120 + 1;
   const int q0 = blockIdx.x * 256;          // first hop of this block; hop q covers samples n = 4q..4q+3
   if (q0 >= F - 1) return;
-  // frames q0-1 .. q0+257; a frame's 18 fp32 values are 72 contiguous bytes (8-byte aligned when ld is even)
+  // frames q0-1 .. q0+257; a frame's 18 fp32 values are 72 contiguous bytes (8-byte aligned when ld is even).  (Fetching the block's
+  // rows as one contiguous span into shared memory first was measured twice and is slower: 162 -> 270 us.)
   for (int e = threadIdx.x; e < 259; e += 256) {
     const int f = q0 - 1 + e;
-    if (f >= 0 && f < F) {
-      const float* c = cp + ((long long)b * F_alloc + f) * ld;
-      float cv[18];
-      if ((ld & 1) == 0 && (reinterpret_cast<uintptr_t>(cp) & 7) == 0) {
+    float4* out4 = reinterpret_cast<float4*>(&ys[e][0]);
+    if (f < 0 || f >= F) {
 #pragma unroll
-        for (int k = 0; k < 9; k++) {
-          const float2 t2 = __ldg(reinterpret_cast<const float2*>(c) + k);
-          cv[2 * k] = t2.x;
-          cv[2 * k + 1] = t2.y;
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 18; k++) cv[k] = c[k];
-      }
+      for (int i = 0; i < 4; i++) out4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    const float* c = cp + ((long long)b * F_alloc + f) * ld;
+    float cv[18];
+    if ((ld & 1) == 0 && (reinterpret_cast<uintptr_t>(cp) & 7) == 0) {
 #pragma unroll
       for (int k = 0; k < 9; k++) {
-        const float mag = fminf(__expf(cv[k]), 100.f);
-        const float ph = __sinf(cv[9 + k]);    // MUFU sine: abs error ~1e-6 on the conv_post phase logits (|x| of a few units),
-                                               // six orders below the 35 dB parity budget; |ph| <= 1 for the sincos below
-        float sn, cs;
-        __sincosf(ph, &sn, &cs);
-        Xre[e][k] = mag * cs;
-        Xim[e][k] = mag * sn;
+        const float2 t2 = __ldg(reinterpret_cast<const float2*>(c) + k);
+        cv[2 * k] = t2.x;
+        cv[2 * k + 1] = t2.y;
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < 9; k++) {
-        Xre[e][k] = 0.f;
-        Xim[e][k] = 0.f;
-      }
+      for (int k = 0; k < 18; k++) cv[k] = c[k];
     }
+    float2 X[9];                             // (re, im)
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      const float mag = fminf(__expf(cv[k]), 100.f);
+      const float ph = __sinf(cv[9 + k]);    // MUFU sine: abs error ~1e-6 on the conv_post phase logits (|x| of a few units),
+                                             // six orders below the 35 dB parity budget; |ph| <= 1 for the sincos below
+      float sn, cs;
+      __sincosf(ph, &sn, &cs);
+      X[k] = make_float2(mag * cs, mag * sn);
+    }
+    // n = 0 and n = 8: only cosines (+-1)
+    const float ev = X[2].x + X[4].x + X[6].x, od = X[1].x + X[3].x + X[5].x + X[7].x;
+    float y[16];
+    y[0] = X[0].x + X[8].x + 2.f * (ev + od);
+    y[8] = X[0].x + X[8].x + 2.f * (ev - od);
+#pragma unroll
+    for (int n = 1; n < 8; n++) {
+      float2 acc = make_float2(X[0].x + ((n & 1) ? -X[8].x : X[8].x), 0.f);
+#pragma unroll
+      for (int k = 1; k < 8; k++) {
+        const int idx = (k * n) & 15;
+        acc = ffma2(X[k], make_float2(2.f * c_cos16[idx], 2.f * c_sin16[idx]), acc);
+      }
+      y[n] = acc.x - acc.y;
+      y[16 - n] = acc.x + acc.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      out4[i] = make_float4(y[4 * i] * c_hann16[4 * i] * (1.f / 16.f), y[4 * i + 1] * c_hann16[4 * i + 1] * (1.f / 16.f),
+                            y[4 * i + 2] * c_hann16[4 * i + 2] * (1.f / 16.f), y[4 * i + 3] * c_hann16[4 * i + 3] * (1.f / 16.f));
   }
   __syncthreads();
   const int q = q0 + threadIdx.x;
   if (q >= F - 1) return;
-  float y[4] = {0.f, 0.f, 0.f, 0.f};
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   float env[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int df = -1; df <= 2; df++) {
     const int f = q + df;
     if (f < 0 || f >= F) continue;
-    const int e = threadIdx.x + 1 + df;
+    const int kp0 = 8 - 4 * df;             // position of the hop's first sample inside frame f: 12, 8, 4, 0
+    const float4 v = *reinterpret_cast<const float4*>(&ys[threadIdx.x + 1 + df][kp0]);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int kp = 4 * q + 8 + i - 4 * f;   // position inside frame f: 8 + i - 4 df in [0, 16)
-      float g = Xre[e][0] + ((kp & 1) ? -Xre[e][8] : Xre[e][8]);
-#pragma unroll
-      for (int k = 1; k < 8; k++) {
-        const int idx = (k * kp) & 15;
-        g += 2.f * (Xre[e][k] * c_cos16[idx] - Xim[e][k] * c_sin16[idx]);
-      }
-      const float w = c_hann16[kp];
-      y[i] += w * g * (1.f / 16.f);
-      env[i] += w * w;
-    }
+    for (int i = 0; i < 4; i++) env[i] = fmaf(c_hann16[kp0 + i], c_hann16[kp0 + i], env[i]);
   }
   float4 o;
-  o.x = fminf(fmaxf(y[0] / env[0], -0.99f), 0.99f);
-  o.y = fminf(fmaxf(y[1] / env[1], -0.99f), 0.99f);
-  o.z = fminf(fmaxf(y[2] / env[2], -0.99f), 0.99f);
-  o.w = fminf(fmaxf(y[3] / env[3], -0.99f), 0.99f);
+  o.x = fminf(fmaxf(acc.x / env[0], -0.99f), 0.99f);
+  o.y = fminf(fmaxf(acc.y / env[1], -0.99f), 0.99f);
+  o.z = fminf(fmaxf(acc.z / env[2], -0.99f), 0.99f);
+  o.w = fminf(fmaxf(acc.w / env[3], -0.99f), 0.99f);
   *reinterpret_cast<float4*>(wav + (long long)b * wav_bstride + 4 * (long long)q) = o;
   if (pcm) {   // the servers' wire format: (speech * 2**15).astype(int16), i.e. truncation toward zero (fastapi/server.py:42)
     short4 s4;
