@@ -45,3 +45,23 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("# oracle", ""), fn
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/cv2eu_b200.h must be consumable by a C compiler as is (the drop-in boundary is a C ABI: plain pointers and sizes)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no gcc")
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "cv2eu_b200.h"\n'
+                   "int probe(void) {\n"
+                   "  cv2_engine* e = 0;\n"
+                   "  size_t n = cv2_prompt_mel_workspace_bytes(1, 24000);\n"
+                   "  return cv2_version() + (int)n + (e != 0) + cv2_resample_16k_24k_len(16000) + cv2_prompt_mel_frames(24000);\n"
+                   "}\n")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
