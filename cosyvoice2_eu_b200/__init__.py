@@ -5,4 +5,5 @@ host that mirrors the reference's interface for the path (flow.inference / hift.
 from .engine import B200Flow, B200HiFT, B200Token2Wav, GraphedToken2Wav, euler_schedule, get_engine  # noqa: F401
 from .frontend import (align_prompt, extract_speech_feat, extract_speech_feat_batch, mel_spectrogram,  # noqa: F401
                        resample_16k_to_24k)
+from .scheduler import StreamScheduler  # noqa: F401
 from .lib import LIB_PATH, SYMBOLS, Cv2Error  # noqa: F401

@@ -394,3 +394,37 @@ def test_speed_change_matches_linear_interpolation(engine, golden, speed):
     wav = t2w.token2wav(u["token"], u["prompt_token"], u["prompt_feat"], u["embedding"], 0, "speed-test", stream=False, finalize=True,
                         speed=speed)
     assert wav.shape == (1, 480 * T_out)
+
+
+def test_stream_scheduler_on_the_engine(engine, golden):
+    """StreamScheduler (row F3) driving the real engine: three sessions fed token by token, chunks delivered through batched
+    steps; the (70, 10) session's chunk shapes are the golden ones of the reference's own chunk loop, every session's audio adds
+    up to 2 * 480 samples per token, and the vocoder caches are gone afterwards."""
+    from cosyvoice2_eu_b200 import B200Token2Wav, StreamScheduler
+    flow, hift, _ = engine
+    g = golden("stream")
+    t2w = B200Token2Wav(flow, hift)
+    sch = StreamScheduler(t2w, token_hop_len=25)
+    specs = {"s0": (70, 10, 3), "s1": (95, 25, 8), "s2": (55, 12, 9)}
+    utts = {u: _utt(dict(n_tok=n, n_prompt=p, seed=s)) for u, (n, p, s) in specs.items()}
+    for u, ut in utts.items():
+        sch.open(u, ut["prompt_token"], ut["prompt_feat"], ut["embedding"])
+    chunks = {u: [] for u in specs}
+    pos = {u: 0 for u in specs}
+    while sch.sessions:
+        for u, (n, _, _) in specs.items():
+            if pos[u] < n:
+                k = min(7, n - pos[u])
+                sch.push(u, utts[u]["token"][0, pos[u]:pos[u] + k].tolist())
+                pos[u] += k
+                if pos[u] == n:
+                    sch.close(u)
+        while sch.pending():
+            for u, speech, fin in sch.step():
+                chunks[u].append(speech.cpu())
+    assert [tuple(c.shape) for c in chunks["s0"]] == [g[f"chunk{i}"].shape for i in range(len(chunks["s0"]))]
+    for u, (n, _, _) in specs.items():
+        assert sum(c.shape[1] for c in chunks[u]) == 2 * 480 * n
+        # (a crossfaded head is w0 * new + w1 * old of two signals clamped to 0.99: Hamming halves sum to at most 1.08)
+        assert all(bool(torch.isfinite(c).all()) and float(c.abs().max()) <= 0.99 * 1.09 for c in chunks[u])
+        assert u not in t2w.hift_cache_dict

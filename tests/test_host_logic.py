@@ -57,3 +57,102 @@ def test_pack_names_cover_state_dict(fixture_weights):
     # weight-norm fold agrees with the oracle's
     w = O.fold_weight_norm(hs, "conv_post")
     assert torch.allclose(ph["hift.conv_post.w"].float().reshape(18, 7, 64).permute(0, 2, 1), w, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------ StreamScheduler
+class _StubT2W:
+    """Records what the scheduler asks for; stands in for B200Token2Wav (no GPU)."""
+
+    def __init__(self):
+        import types
+        self.flow = types.SimpleNamespace(pre_lookahead_len=3)
+        self.hift_cache_dict = {}
+        self.calls = []
+
+    def token2wav_stream_batch(self, requests, finalize, noises=None):
+        import torch
+        self.calls.append((finalize, [(r["uuid"], int(r["token"].shape[1]), int(r["token_offset"])) for r in requests]))
+        for r in requests:
+            assert r["token"].dtype == torch.int32 and r["token"].dim() == 2
+        return [torch.full((1, 4), float(r["token"].shape[1])) for r in requests]
+
+
+def _per_session(calls):
+    seen = {}
+    for fin, reqs in calls:
+        for uuid, n_vis, off in reqs:
+            seen.setdefault(uuid, []).append((n_vis, off, fin))
+    return seen
+
+
+def test_stream_scheduler_reproduces_the_reference_chunk_schedule():
+    """Whatever the arrival pattern of the tokens, every session gets exactly the calls CosyVoice2Model.tts(stream=True) would make
+    (CV/cli/model.py:351-381, restated as token2wav_oracle.stream_schedule), and sessions that are ready together share a call."""
+    import numpy as np
+    import torch
+    import token2wav_oracle as O
+    from cosyvoice2_eu_b200 import StreamScheduler
+    specs = {"a": (70, 10), "b": (95, 25), "c": (55, 12), "d": (5, 0), "e": (28, 50)}
+    rng = np.random.Generator(np.random.Philox(key=5))
+    t2w = _StubT2W()
+    sch = StreamScheduler(t2w, token_hop_len=25)
+    left = {}
+    for u, (n, p) in specs.items():
+        sch.open(u, torch.zeros(1, p, dtype=torch.int32), torch.zeros(1, 2 * p, 80), torch.zeros(1, 192))
+        left[u] = list(range(n))
+        assert t2w.hift_cache_dict[u] is None
+    delivered = []
+    while sch.sessions:
+        for u in list(left):
+            k = int(rng.integers(0, 40))
+            if left[u]:
+                sch.push(u, left[u][:k])
+                left[u] = left[u][k:]
+            if not left[u]:
+                sch.close(u)
+                del left[u]
+        while sch.pending():
+            delivered.extend(sch.step())
+    got = _per_session(t2w.calls)
+    for u, (n, p) in specs.items():
+        assert got[u] == O.stream_schedule(n, p), u
+        assert u not in t2w.hift_cache_dict                          # dropped after the final chunk (model.py:395-396)
+    assert [d[2] for d in delivered if d[0] == "a"] == [False] * (len(got["a"]) - 1) + [True]
+    assert any(len(reqs) > 1 for _, reqs in t2w.calls)                # concurrent sessions were batched
+    for fin, reqs in t2w.calls:
+        assert len({r[0] for r in reqs}) == len(reqs)                # a session appears at most once per call
+
+
+def test_stream_scheduler_is_event_driven_across_threads():
+    """Producer threads push tokens one by one; the consumer sleeps on the condition variable (no polling) and still makes the
+    reference's calls for every session."""
+    import threading
+    import time
+    import torch
+    import token2wav_oracle as O
+    from cosyvoice2_eu_b200 import StreamScheduler
+    specs = {"x": (64, 10), "y": (31, 0), "z": (90, 25)}
+    t2w = _StubT2W()
+    sch = StreamScheduler(t2w, token_hop_len=25)
+    for u, (n, p) in specs.items():
+        sch.open(u, torch.zeros(1, p, dtype=torch.int32), torch.zeros(1, 2 * p, 80), torch.zeros(1, 192))
+
+    def produce(u, n):
+        for i in range(n):
+            sch.push(u, i)
+            if i % 16 == 0:
+                time.sleep(0.001)
+        sch.close(u)
+
+    threads = [threading.Thread(target=produce, args=(u, n)) for u, (n, _) in specs.items()]
+    chunks = []
+    for t in threads:
+        t.start()
+    sch.run(lambda u, sp, fin: chunks.append((u, fin)), idle_timeout=5.0)
+    for t in threads:
+        t.join()
+    assert not sch.sessions
+    got = _per_session(t2w.calls)
+    for u, (n, p) in specs.items():
+        assert got[u] == O.stream_schedule(n, p), u
+    assert sorted(u for u, fin in chunks if fin) == sorted(specs)
