@@ -118,6 +118,9 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
+_CPU_ENGINE = {}
+
+
 def cpu_reference_run(n_tok, threads=None):
     """Oracle port of the reference CPU token2wav on one utterance; returns (seconds, audio_seconds)."""
     import torch
@@ -126,9 +129,11 @@ def cpu_reference_run(n_tok, threads=None):
     from synth import weights
     if threads:
         torch.set_num_threads(threads)
-    fs, hs = weights.to_torch(weights.make_flow_state()), weights.to_torch(weights.make_hift_state())
+    if "eng" not in _CPU_ENGINE:
+        fs, hs = weights.to_torch(weights.make_flow_state()), weights.to_torch(weights.make_hift_state())
+        _CPU_ENGINE["eng"] = O.OracleToken2Wav(fs, hs, weights.cfm_rand_noise())
+    eng = _CPU_ENGINE["eng"]
     u = {k: torch.from_numpy(v) for k, v in weights.make_utterance(n_tok, N_PROMPT, seed=7).items()}
-    eng = O.OracleToken2Wav(fs, hs, weights.cfm_rand_noise())
     eng.hift_cache_dict["b"] = None
     t0 = time.perf_counter()
     wav = eng.token2wav(u["token"], u["prompt_token"], u["prompt_feat"], u["embedding"], 0, "b", finalize=True)
@@ -136,15 +141,27 @@ def cpu_reference_run(n_tok, threads=None):
     return dt, wav.shape[1] / 24000.0
 
 
+def workload_config(world, batch=BATCH):
+    """`config` of the JSON line: the same dictionary in both arms (the reference arm runs a bounded SAMPLE of it)."""
+    n0 = workload(0, batch)
+    return {"workload": "BASELINE configs[2] per GPU: 64 utterances, durations U[4,20] s (100-500 tokens) + 75-token "
+                        "prompt, offline token2wav, 10 Euler steps with CFG, length-sorted ragged batch",
+            "utterances_per_gpu": len(n0), "audio_seconds_per_step_per_gpu": sum(2 * n * 480 for n in n0) / 24000.0,
+            "parallelism": f"utterance-sharded dp{world}",
+            "l2": "per-step working set (GBs of activations) is far larger than the 126 MB L2; no explicit flush",
+            "weights": "random-init CosyVoice2-0.5B-EU architecture (synth/weights.py)"}
+
+
 def main_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the Python reference cannot
-    travel to the GPU box), all host threads, bounded sample = one median-length (12 s) utterance of the workload per step."""
+    travel to the GPU box), all host threads, bounded sample = one median-length (12 s) utterance of the workload per step.
+    Under torchrun only rank 0 works; the other ranks exit at once."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     cores = os.cpu_count()
-    torch.set_num_threads(cores)
+    torch.set_num_threads(cores)           # torchrun exports OMP_NUM_THREADS=1: undo that for the CPU arm
     n_tok = 300
     times, audio = [], 0.0
     for i in range(args.warmup + args.steps):
@@ -154,14 +171,25 @@ def main_reference(args):
             audio += a
     total = sum(times)
     val = audio / total
+    sample = "one 12 s utterance (300 tokens + 75-token prompt) of the workload per step, oracle port of the reference CPU " \
+             "token2wav, torch fp32, all host threads"
     line = {"impl": "reference", "metric": "token2wav_audio_seconds_per_second", "value": val, "unit": "audio-s/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * total / max(len(times), 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[2] sample: one 12 s utterance (300 tokens + 75-token prompt) per step, offline, 10 Euler steps"},
-            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                             "sample": "one 12 s utterance per step, torch fp32 CPU, all host threads"},
+            "config": workload_config(args.gpus, args.batch),
+            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def kernel_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures of this very command, as
+    extracted into profiles/kernel_traffic.json by profiles/extract_traffic.py (tracked; names the capture it came from)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
 
 
 def main():
@@ -175,14 +203,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--corpus", type=int, default=4096, help="utterances of the configs[4] corpus leg (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-legs", action="store_true", help="skip batch-1 / streaming / prompt-mel legs (quick runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)
 
+    import datetime
+    import ctypes as C
     import torch
     import torch.distributed as dist
-    from cosyvoice2_eu_b200 import B200Flow, B200HiFT, B200Token2Wav
+    from cosyvoice2_eu_b200 import B200Flow, B200HiFT, B200Token2Wav, shard
+    from cosyvoice2_eu_b200.scheduler import chunk_schedule
     from synth import weights
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -191,7 +224,9 @@ def main():
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+        # Nothing slow ever sits between two collectives below (the CPU legs run after destroy_process_group); the explicit
+        # timeout only bounds a genuinely wedged rank.
+        dist.init_process_group("nccl", device_id=torch.device(dev), timeout=datetime.timedelta(minutes=20))
 
     # ---- engine with random-init weights of the CosyVoice2-0.5B-EU architecture ----
     flow, hift = B200Flow(dev), B200HiFT(dev)
@@ -211,6 +246,9 @@ def main():
     B = len(n_tokens)
     max_total = max(n_tokens) + N_PROMPT
     mel_T = 2 * max(n_tokens)
+    # every rank's batch has its own longest utterance: the gather needs ONE shape, the longest over all ranks (workload() is
+    # deterministic, so every rank computes it without a collective)
+    gmax_samples = 960 * max(max(workload(r, args.batch)) for r in range(world))
 
     # device-resident inputs for the kernel-only measurement
     tok_d = torch.zeros(B, max(n_tokens), dtype=torch.int32)
@@ -227,21 +265,24 @@ def main():
 
     def step_resident():
         (mel,) = flow._forward_device(tok_d, tl_d, ptk_d, pl_d, pf_d, fl_d, emb_d, B, max_total, mel_T, False, True)
-        n1 = eng.last_launches()
         speech, _ = hift.inference(mel, lens=mel_lens_d)
-        return speech, n1 + eng.last_launches()
+        return speech, flow.last_launches + hift.last_launches
 
     gather_buf = {}
 
     def step_e2e():
         speech, lens = t2w.token2wav_batch(tokens, ptoks, pfeats, embs)
         if world > 1:                                        # final gather of (lengths, padded audio) on rank 0 (the only collective)
-            lens_d = lens.to(dev, non_blocking=True)
-            if rank == 0 and not gather_buf:                 # receive buffers are allocated once, not per step
-                gather_buf["lens"] = [torch.empty_like(lens_d) for _ in range(world)]
-                gather_buf["aud"] = [torch.empty_like(speech) for _ in range(world)]
-            dist.gather(lens_d, gather_buf.get("lens"), dst=0)
-            dist.gather(speech, gather_buf.get("aud"), dst=0)
+            if not gather_buf:                               # send / receive buffers are allocated once, not per step
+                gather_buf["send"] = torch.zeros(B, gmax_samples, dtype=torch.float32, device=dev)
+                gather_buf["lens_send"] = torch.zeros(B, dtype=torch.int32, device=dev)
+                if rank == 0:
+                    gather_buf["lens"] = [torch.empty_like(gather_buf["lens_send"]) for _ in range(world)]
+                    gather_buf["aud"] = [torch.empty_like(gather_buf["send"]) for _ in range(world)]
+            gather_buf["lens_send"].copy_(lens, non_blocking=True)
+            gather_buf["send"][:, :speech.shape[1]].copy_(speech)
+            dist.gather(gather_buf["lens_send"], gather_buf.get("lens"), dst=0)
+            dist.gather(gather_buf["send"], gather_buf.get("aud"), dst=0)
         if "host" not in gather_buf or gather_buf["host"].shape != speech.shape:
             gather_buf["host"] = torch.empty(speech.shape, dtype=speech.dtype).pin_memory()   # pinned once, reused every step
         out = gather_buf["host"]
@@ -262,7 +303,6 @@ def main():
     stop, clk = threading.Event(), []
     th = threading.Thread(target=sample_clocks, args=(stop, clk), daemon=True)
     th.start()
-    import ctypes as C
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -305,6 +345,161 @@ def main():
     h2d = flow.last_h2d_bytes
     d2h = out.numel() * 4 + 4 * B
 
+    # ---- BASELINE configs[4]: a 4096-utterance corpus sharded by utterance over the ranks (strong scaling): cost-balanced
+    #      shards, length-bucketed batches of <= 64 through the public batched API (host inputs), audio packed into one flat
+    #      buffer per rank, ONE NCCL gather to rank 0, D2H of everything there ----
+    corpus = None
+    if args.corpus > 0:
+        crng = np.random.Generator(np.random.Philox(key=4096))
+        c_tok = [int(round(25 * d)) for d in crng.uniform(4.0, 20.0, size=args.corpus)]
+        plan, flat_len = shard.corpus_plan(c_tok, [N_PROMPT] * len(c_tok), world)
+        mine = plan[rank]
+        c_utts = {i: weights.make_utterance(c_tok[i], N_PROMPT, seed=7_000_000 + i) for i in mine["indices"]}
+
+        def corpus_batch(idx):
+            us = [c_utts[i] for i in idx]
+            return t2w.token2wav_batch([torch.from_numpy(u["token"][0]) for u in us], [torch.from_numpy(u["prompt_token"][0]) for u in us],
+                                       [torch.from_numpy(u["prompt_feat"][0]) for u in us], [torch.from_numpy(u["embedding"][0]) for u in us])
+
+        flat = torch.zeros(flat_len, dtype=torch.float32, device=dev)
+        recv = [torch.empty_like(flat) for _ in range(world)] if (rank == 0 and world > 1) else None
+        host = torch.empty((world if rank == 0 else 0) * flat_len, dtype=torch.float32).pin_memory() if rank == 0 else None
+        # warm-up: the largest batch (grows the workspaces to their final size) and the smallest one
+        big = max(mine["batches"], key=lambda b: len(b) * (c_tok[b[-1]] + N_PROMPT) ** 2)
+        corpus_batch(big)
+        corpus_batch(mine["batches"][0])
+        barrier()
+        e0.record()
+        shard.run_corpus_shard(mine, c_tok, corpus_batch, flat)
+        if world > 1:
+            shard.gather_flat(flat, dst=0, out=recv)
+        if rank == 0:
+            for r in range(world):
+                host[r * flat_len:(r + 1) * flat_len].copy_(recv[r] if world > 1 else flat, non_blocking=True)
+        e1.record()
+        barrier()
+        ms_corpus = e0.elapsed_time(e1)
+        corpus = {"ms": ms_corpus, "utterances": len(c_tok), "audio_s": sum(c_tok) * 960 / 24000.0,
+                  "batches_this_rank": len(mine["batches"]), "utterances_this_rank": len(mine["indices"]),
+                  "gather_bytes": int(4 * flat_len * (world - 1)) if world > 1 else 0, "d2h_bytes": int(4 * flat_len * world)}
+        del flat, recv, host, c_utts
+        torch.cuda.empty_cache()
+
+    # ---- reduce over ranks: the last collectives; after them ranks >= 1 are done ----
+    red = torch.tensor([ms, ms_e2e, corpus["ms"] if corpus else 0.0], dtype=torch.float64, device=dev)
+    aud = torch.tensor([audio_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(aud, op=dist.ReduceOp.SUM)
+    ms, ms_e2e = float(red[0]), float(red[1])
+    if corpus:
+        corpus["ms"] = float(red[2])
+    total_audio = float(aud[0])
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+    if rank != 0:
+        return          # every other rank exits here: rank 0's side legs and CPU baseline run with the box to themselves
+
+    peaks, peak_src = load_peaks()
+    side = {}
+    if not args.no_side_legs:
+        side = side_legs(args, t2w, flow, hift, dev, peaks, clk, chunk_schedule, weights)
+
+    flops = algorithmic_flops(n_tokens)
+    fam = {n: {"ms_per_step": fam_ms[i] / args.steps, "launches_per_step": fam_n[i] / args.steps,
+               "algorithmic_tflop_per_step": flops[n] / 1e12,
+               "tflops": (flops[n] / 1e12) / (fam_ms[i] / args.steps / 1e3) if fam_ms[i] > 0 else None}
+           for i, n in enumerate(FAMILIES) if fam_n[i] > 0}
+    # dominant KERNEL by device time: gemm_tap<256> is one template with many epilogue specialisations that serve different
+    # layers; its two big instances (QKV projection, out-proj + residual + LayerNorm) are ranked on their own
+    rows2 = 20.0 * sum(2 * (n + N_PROMPT) for n in n_tokens)          # estimator rows x Euler steps x CFG
+    spec_flops = {"qkv_split": rows2 * 56 * 2 * 256 * 1536.0, "res+ln_emit": rows2 * 56 * 2 * 512 * 256.0}
+    cand = {n: v for n, v in fam.items() if n != "gemm_tap<256>"}
+    for sname, fl in spec_flops.items():
+        if sname in g256:
+            cand["gemm_tap<256>:" + sname] = {"ms_per_step": g256[sname]["ms_per_step"], "launches_per_step": g256[sname]["launches_per_step"],
+                                              "algorithmic_tflop_per_step": fl / 1e12,
+                                              "tflops": fl / 1e12 / (g256[sname]["ms_per_step"] / 1e3)}
+    dom = max(cand, key=lambda n: cand[n]["ms_per_step"])
+    d = cand[dom]
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    ach = d["tflops"] or 0.0
+    traffic = kernel_traffic().get(dom, {})
+    roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": traffic.get("dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
+                "peak_source": peak_src + " sustained dense bf16 (kernel timed inside a long step)",
+                "avg_launch_ms": d["ms_per_step"] / d["launches_per_step"],
+                "algorithmic_gflop_per_launch": 1e3 * d["algorithmic_tflop_per_step"] / d["launches_per_step"],
+                "share_of_step": d["ms_per_step"] / (ms_prof / args.steps), "ms_per_step_profiled_pass": ms_prof / args.steps}
+    # bandwidth-bound vocoder kernels: algorithmic bytes (fp32 I/O per output sample) / event-timed launch
+    samples = float(sum(2 * n * 480 for n in n_tokens))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_bytes = {"source_stft": 22.0, "istft": 22.0, "nsf_source": 4.0 + 4.0 / 480}
+    hbm_kernels = {}
+    for k, bps in hbm_bytes.items():
+        if k in fam and fam[k]["ms_per_step"] > 0:
+            gbs = samples * bps / (fam[k]["ms_per_step"] / fam[k]["launches_per_step"] * 1e-3) / 1e9
+            hbm_kernels[k] = {"algorithmic_bytes_per_sample": bps, "ms_per_launch": fam[k]["ms_per_step"] / fam[k]["launches_per_step"],
+                              "achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": gbs / hbm_peak}
+    if "one_directional" in side:
+        od = side["one_directional"]
+        hbm_kernels["one_directional_peaks_gbs_measured_here"] = od
+        if "source_stft" in hbm_kernels and "write_only_fill" in od:
+            hbm_kernels["source_stft"]["frac_of_write_only"] = hbm_kernels["source_stft"]["achieved_gbs"] / od["write_only_fill"]
+        if "istft" in hbm_kernels and "read_only_sum" in od:
+            hbm_kernels["istft"]["frac_of_read_only"] = hbm_kernels["istft"]["achieved_gbs"] / od["read_only_sum"]
+    hbm_kernels["note"] = ("peak = measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs); nsf_source in production mode draws its "
+                           "noise in-kernel (9 sines + 9 normals per 4-byte sample), i.e. it is ALU/MUFU bound there and only "
+                           "bandwidth bound in parity mode (36 B/sample noise read)")
+    total_flop = sum(flops.values()) * world
+    cfg = workload_config(world, args.batch)
+    cfg["utterances_per_gpu"], cfg["audio_seconds_per_step_per_gpu"] = B, audio_s
+    line = {
+        "metric": "token2wav_audio_seconds_per_second", "value": total_audio * args.steps / (ms / 1e3), "unit": "audio-s/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp16 operands, fp32 accumulate (tcgen05 kind::f16)",
+        "data": "synthetic", "config": cfg,
+        "e2e": {"value": total_audio * args.steps / (ms_e2e / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "roofline": roofline,
+        "families": fam,
+        "hbm_kernels": hbm_kernels,
+        "gemm256_by_epilogue": g256,
+        "whole_step_tflops": total_flop / 1e12 / (ms / args.steps / 1e3) / world,
+        "clocks": clocks_summary(clk),
+    }
+    if corpus:
+        line["corpus4096"] = {
+            "workload": f"BASELINE configs[4]: {corpus['utterances']} utterances, U[4,20] s + 75-token prompt, sharded by cost over "
+                        f"{world} GPU(s) (shard_by_cost), length-bucketed batches <= 64 (bucket_batches), host inputs, one NCCL "
+                        "gather of the packed audio to rank 0, D2H there; ONE timed pass, strong scaling",
+            "scaling": "strong", "audio_s_per_s": corpus["audio_s"] / (corpus["ms"] / 1e3), "seconds": corpus["ms"] / 1e3,
+            "audio_seconds": corpus["audio_s"], "utterances_rank0": corpus["utterances_this_rank"],
+            "batches_rank0": corpus["batches_this_rank"], "gather_bytes": corpus["gather_bytes"], "d2h_bytes": corpus["d2h_bytes"]}
+    for k in ("rtf_batch1", "stream32", "prompt_mel"):
+        if k in side:
+            line[k] = side[k]
+    if not args.no_cpu_baseline:
+        # the GPU legs are over and the other ranks have exited: all host cores belong to this leg
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)        # torchrun exports OMP_NUM_THREADS=1
+        runs = [cpu_reference_run(200, cores) for _ in range(4)]       # 1 warm-up + 3 timed
+        dts = sorted(r[0] for r in runs[1:])
+        dt, a = dts[1], runs[1][1]
+        line["cpu_baseline"] = {"value": a / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                "sample": "one 8 s utterance (200 tokens + 75-token prompt, configs[0]) through the oracle port of "
+                                          "the reference CPU token2wav (torch fp32, all host threads): 1 warm-up, median of 3",
+                                "seconds": dt, "seconds_all": [r[0] for r in runs]}
+    print(json.dumps(line))
+
+
+def side_legs(args, t2w, flow, hift, dev, peaks, clk, chunk_schedule, weights):
+    """Rank 0 only, after every collective: configs[1] latency, configs[3] streaming, prompt features, one-directional HBM peaks."""
+    import torch
+    out = {}
+    peak_burst = float(peaks.get("bf16_tflops", 1590.0))
     # ---- configs[1]: batch-1 latency / RTF (single 10 s utterance) ----
     u1 = weights.make_utterance(250, N_PROMPT, seed=99)
     a1 = [torch.from_numpy(u1[k][0]) for k in ("token", "prompt_token", "prompt_feat", "embedding")]
@@ -326,25 +521,21 @@ def main():
         w, _ = t2w.token2wav_batch([a1[0]], [a1[1]], [a1[2]], [a1[3]])
         w.cpu()
         lat_eager.append(time.perf_counter() - t0)
+    fl1 = sum(algorithmic_flops([250]).values())
+    out["rtf_batch1"] = {"workload": "BASELINE configs[1]: single 10 s utterance (250 tokens + 75-token prompt), batch 1",
+                         "latency_s": lat1, "rtf": lat1 / 10.0, "audio_s_per_s": 10.0 / lat1,
+                         "how": "CUDA-graph replay, host in / host out",
+                         "latency_s_eager_launches": float(np.median(lat_eager)),
+                         "roofline": {"bound": "tensor", "algorithmic_tflop": fl1 / 1e12, "achieved": fl1 / 1e12 / lat1,
+                                      "peak": peak_burst, "unit": "TFLOP/s", "frac": fl1 / 1e12 / lat1 / peak_burst,
+                                      "note": "whole call, host to host; burst peak (a short call is not power capped); 650 x 2 "
+                                              "estimator rows are 12 row tiles of 128 for 148 SMs: occupancy bound, not pipe bound"}}
 
     # ---- configs[3]: 32 concurrent streaming sessions (hop 25, lookahead 3, mel cache 8, source cache 3840), N = 250 ----
-    def stream_schedule(n_tokens, n_prompt, hop=25, lookahead=3):        # chunk schedule of CosyVoice2Model.tts (model.py:351-381)
-        pad = int(np.ceil(n_prompt / hop) * hop - n_prompt)
-        calls, off = [], 0
-        while True:
-            this_hop = hop + pad if off == 0 else hop
-            if n_tokens - off >= this_hop + lookahead:
-                calls.append((off + this_hop + lookahead, off, False))
-                off += this_hop
-            else:
-                break
-        calls.append((n_tokens, off, True))
-        return calls
-
     n_sess, n_tok_s = 32, 250
     sess = [weights.make_utterance(n_tok_s, N_PROMPT, seed=5000 + i) for i in range(n_sess)]
     sess = [{k: torch.from_numpy(v) for k, v in u.items()} for u in sess]
-    sched = stream_schedule(n_tok_s, N_PROMPT)
+    sched = chunk_schedule(n_tok_s, N_PROMPT)
 
     def run_streams():
         for i in range(n_sess):
@@ -364,124 +555,41 @@ def main():
     t0 = time.perf_counter()
     lat_s, total_samples = run_streams()
     t_stream = time.perf_counter() - t0
-    stream32 = {"workload": "BASELINE configs[3]: 32 concurrent sessions x 250 tokens (10 s), hop 25, the reference's prefix-recompute "
-                            "schedule, every step = one ragged batch over all sessions, chunks copied to the host",
-                "audio_s_per_s": total_samples / 24000.0 / t_stream, "chunks": len(sched),
-                "chunk_latency_s_median": float(np.median(lat_s)), "first_chunk_latency_s": lat_s[0], "wall_s": t_stream}
-
-    # ---- reduce over ranks ----
-    t_max = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    aud = torch.tensor([audio_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-        dist.all_reduce(aud, op=dist.ReduceOp.SUM)
-    ms, ms_e2e = float(t_max[0]), float(t_max[1])
-    total_audio = float(aud[0])
-
-    if rank == 0:
-        peaks, peak_src = load_peaks()
-        flops = algorithmic_flops(n_tokens)
-        fam = {n: {"ms_per_step": fam_ms[i] / args.steps, "launches_per_step": fam_n[i] / args.steps,
-                   "algorithmic_tflop_per_step": flops[n] / 1e12,
-                   "tflops": (flops[n] / 1e12) / (fam_ms[i] / args.steps / 1e3) if fam_ms[i] > 0 else None}
-               for i, n in enumerate(FAMILIES) if fam_n[i] > 0}
-        # dominant KERNEL by device time: gemm_tap<256> is one template with many epilogue specialisations that serve different
-        # layers; its two big instances (QKV projection, out-proj + residual + LayerNorm) are ranked on their own
-        rows2 = 20.0 * sum(2 * (n + N_PROMPT) for n in n_tokens)          # estimator rows x Euler steps x CFG
-        spec_flops = {"qkv_split": rows2 * 56 * 2 * 256 * 1536.0, "res+ln_emit": rows2 * 56 * 2 * 512 * 256.0}
-        cand = {n: v for n, v in fam.items() if n != "gemm_tap<256>"}
-        for sname, fl in spec_flops.items():
-            if sname in g256:
-                cand["gemm_tap<256>:" + sname] = {"ms_per_step": g256[sname]["ms_per_step"], "launches_per_step": g256[sname]["launches_per_step"],
-                                                  "algorithmic_tflop_per_step": fl / 1e12,
-                                                  "tflops": fl / 1e12 / (g256[sname]["ms_per_step"] / 1e3)}
-        dom = max(cand, key=lambda n: cand[n]["ms_per_step"])
-        d = cand[dom]
-        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        ach = d["tflops"] or 0.0
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` on this very command
-        # (profiles/README.md, round 1): only captured for flash_attn and the QKV GEMM
-        ncu_traffic = {"flash_attn": 405.4e6}   # flash_attn_v9_kernel inside `bench.py --steps 1` (profiles/README.md): 315.5 MB read + 89.8 MB written
-        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": ncu_traffic.get(dom), "peak_source": peak_src + " sustained dense bf16 (kernel timed inside a long step)",
-                    "avg_launch_ms": d["ms_per_step"] / d["launches_per_step"],
-                    "algorithmic_gflop_per_launch": 1e3 * d["algorithmic_tflop_per_step"] / d["launches_per_step"],
-                    "share_of_step": d["ms_per_step"] / (ms_prof / args.steps), "ms_per_step_profiled_pass": ms_prof / args.steps}
-        # bandwidth-bound vocoder kernels: algorithmic bytes (fp32 I/O per output sample) / event-timed launch
-        samples = float(sum(2 * n * 480 for n in n_tokens))
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        hbm_bytes = {"source_stft": 22.0, "istft": 22.0, "nsf_source": 4.0 + 4.0 / 480}
-        hbm_kernels = {}
-        for k, bps in hbm_bytes.items():
-            if k in fam and fam[k]["ms_per_step"] > 0:
-                gbs = samples * bps / (fam[k]["ms_per_step"] / fam[k]["launches_per_step"] * 1e-3) / 1e9
-                hbm_kernels[k] = {"algorithmic_bytes_per_sample": bps, "ms_per_launch": fam[k]["ms_per_step"] / fam[k]["launches_per_step"],
-                                  "achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": gbs / hbm_peak}
-        # the copy figure is a read+write mix; the STFT is 82 % writes and the iSTFT 82 % reads, so also measure one-directional
-        # streams on this box (1 GiB fill / 1 GiB sum reduction, best of 5, CUDA events)
-        try:
-            buf = torch.empty(1 << 28, dtype=torch.float32, device=dev)
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            wr, rd = [], []
-            for _ in range(5):
-                ev0.record(); buf.fill_(1.0); ev1.record(); torch.cuda.synchronize(); wr.append(buf.numel() * 4 / ev0.elapsed_time(ev1) / 1e6)
-                ev0.record(); buf.sum(); ev1.record(); torch.cuda.synchronize(); rd.append(buf.numel() * 4 / ev0.elapsed_time(ev1) / 1e6)
-            del buf
-            hbm_kernels["one_directional_peaks_gbs_measured_here"] = {"write_only_fill": max(wr), "read_only_sum": max(rd)}
-            if "source_stft" in hbm_kernels:
-                hbm_kernels["source_stft"]["frac_of_write_only"] = hbm_kernels["source_stft"]["achieved_gbs"] / max(wr)
-            if "istft" in hbm_kernels:
-                hbm_kernels["istft"]["frac_of_read_only"] = hbm_kernels["istft"]["achieved_gbs"] / max(rd)
-        except Exception as exc:   # never let the side measurement break the bench line
-            hbm_kernels["one_directional_peaks_gbs_measured_here"] = {"error": str(exc)}
-        hbm_kernels["note"] = ("peak = measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs); nsf_source in production mode draws its "
-                               "noise in-kernel (9 sines + 9 normals per 4-byte sample), i.e. it is ALU/MUFU bound there and only "
-                               "bandwidth bound in parity mode (36 B/sample noise read)")
-        # SURVEY.md 8f row F2 (the step before the path): prompt log-mel of 64 prompts of U[3, 30] s, device-resident input, and
-        # the same call with host buffers; the oracle (numpy float64 rFFT, one thread) on one 30 s prompt beside it
-        prompt_mel = None
-        if rank == 0:
-            try:
-                prompt_mel = bench_prompt_mel(dev, peaks, clk, with_cpu=not args.no_cpu_baseline)
-            except Exception as exc:   # side measurement: never break the bench line
-                prompt_mel = {"error": str(exc)}
-        total_flop = sum(flops.values()) * world
-        line = {
-            "metric": "token2wav_audio_seconds_per_second", "value": total_audio * args.steps / (ms / 1e3), "unit": "audio-s/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "fp16 operands, fp32 accumulate (tcgen05 kind::f16)",
-            "data": "synthetic",
-            "config": {"workload": "BASELINE configs[2] per GPU: 64 utterances, durations U[4,20] s (100-500 tokens) + 75-token "
-                                   "prompt, offline token2wav, 10 Euler steps with CFG, length-sorted ragged batch",
-                       "utterances_per_gpu": B, "audio_seconds_per_step_per_gpu": audio_s, "parallelism": f"utterance-sharded dp{world}",
-                       "l2": "per-step working set (GBs of activations) is far larger than the 126 MB L2; no explicit flush",
-                       "weights": "random-init CosyVoice2-0.5B-EU architecture (synth/weights.py)"},
-            "e2e": {"value": total_audio * args.steps / (ms_e2e / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches_per_step * args.steps),
-            "roofline": roofline,
-            "families": fam,
-            "hbm_kernels": hbm_kernels,
-            "gemm256_by_epilogue": g256,
-            "whole_step_tflops": total_flop / 1e12 / (ms / args.steps / 1e3) / world,
-            "rtf_batch1": {"workload": "BASELINE configs[1]: single 10 s utterance (250 tokens + 75-token prompt), batch 1",
-                           "latency_s": lat1, "rtf": lat1 / 10.0, "audio_s_per_s": 10.0 / lat1, "how": "CUDA-graph replay, host in / host out",
-                           "latency_s_eager_launches": float(np.median(lat_eager))},
-            "stream32": stream32,
-            "prompt_mel": prompt_mel,
-            "clocks": clocks_summary(clk),
-        }
-        if not args.no_cpu_baseline:
-            cores = os.cpu_count()
-            dt, a = cpu_reference_run(200, cores)
-            line["cpu_baseline"] = {"value": a / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                                    "sample": "one 8 s utterance (200 tokens + 75-token prompt, configs[0]) run once through the "
-                                              "oracle port of the reference CPU token2wav (torch fp32, all host threads)",
-                                    "seconds": dt}
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    # algorithmic FLOPs of a session in the INCREMENTAL unit: every frame of the non-final chunks computed once
+    # with the block-causal attention term, plus the full final pass
+    def est_flops(T, causal):
+        att = 114688.0 * ((T + 50) / 2 if causal else T)
+        return 20.0 * T * (132161536.0 + att)
+    T_last_nonfinal = 2 * (N_PROMPT + sched[-2][0] - 3) if len(sched) > 1 else 0
+    T_final = 2 * (N_PROMPT + n_tok_s)
+    fl_sess = est_flops(T_last_nonfinal, True) + est_flops(T_final, False) + 612.3e6 * 2 * n_tok_s
+    out["stream32"] = {"workload": "BASELINE configs[3]: 32 concurrent sessions x 250 tokens (10 s), hop 25, chunk schedule of "
+                                   "CosyVoice2Model.tts, every step = one ragged batch over all sessions, chunks copied to the host",
+                       "audio_s_per_s": total_samples / 24000.0 / t_stream, "chunks": len(sched),
+                       "chunk_latency_s_median": float(np.median(lat_s)), "first_chunk_latency_s": lat_s[0], "wall_s": t_stream,
+                       "roofline": {"bound": "tensor", "unit": "TFLOP/s", "algorithmic_tflop": n_sess * fl_sess / 1e12,
+                                    "achieved": n_sess * fl_sess / 1e12 / t_stream, "peak": peak_burst,
+                                    "frac": n_sess * fl_sess / 1e12 / t_stream / peak_burst,
+                                    "note": "incremental unit: each non-final frame counted once (block-causal attention) + the "
+                                            "full final pass + the vocoder; prefix recomputation is not counted as useful work"}}
+    # one-directional HBM peaks (the copy figure is a read+write mix; the STFT is 82 % writes and the iSTFT 82 % reads)
+    try:
+        buf = torch.empty(1 << 28, dtype=torch.float32, device=dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wr, rd = [], []
+        for _ in range(5):
+            ev0.record(); buf.fill_(1.0); ev1.record(); torch.cuda.synchronize(); wr.append(buf.numel() * 4 / ev0.elapsed_time(ev1) / 1e6)
+            ev0.record(); buf.sum(); ev1.record(); torch.cuda.synchronize(); rd.append(buf.numel() * 4 / ev0.elapsed_time(ev1) / 1e6)
+        del buf
+        out["one_directional"] = {"write_only_fill": max(wr), "read_only_sum": max(rd)}
+    except Exception as exc:   # never let a side measurement break the bench line
+        out["one_directional"] = {"error": str(exc)}
+    # SURVEY.md 8f row F2 (the step before the path): prompt log-mel of 64 prompts of U[3, 30] s
+    try:
+        out["prompt_mel"] = bench_prompt_mel(dev, peaks, clk, with_cpu=not args.no_cpu_baseline)
+    except Exception as exc:
+        out["prompt_mel"] = {"error": str(exc)}
+    return out
 
 
 def bench_prompt_mel(dev, peaks, clk, with_cpu=True, reps=10):

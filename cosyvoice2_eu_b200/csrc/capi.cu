@@ -27,6 +27,9 @@ struct cv2_engine {
   }                                                \
   return 0;
 
+// every forward runs on the engine's own device whatever the caller's current device is
+static void use_device(const cv2_engine* h) { CV2_CUDA(cudaSetDevice(h->e.device)); }
+
 static void require_sm100(int device) {
   cudaDeviceProp prop;
   CV2_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -55,7 +58,10 @@ int cv2_engine_create(cv2_engine** out, int device) {
   CV2_API_END
 }
 
-void cv2_engine_destroy(cv2_engine* e) { delete e; }
+void cv2_engine_destroy(cv2_engine* e) {
+  if (e && e->e.range_dev) cudaFree(e->e.range_dev);
+  delete e;
+}
 
 int cv2_engine_set_tensor(cv2_engine* h, const char* name, const void* dptr, int dtype, int ndim, const int64_t* shape) {
   CV2_API_BEGIN
@@ -112,7 +118,31 @@ int cv2_engine_set_option(cv2_engine* h, const char* name, int value) {
   else if (n == "f0_split") h->e.f0_split = value != 0;
   else if (n == "cluster_mc") h->e.cluster_mc = value != 0;
   else if (n == "ffn_2cta") h->e.ffn_2cta = value != 0;
+  else if (n == "min_2sm_tiles") h->e.min_2sm_tiles = value;
+  else if (n == "range_check") {
+    use_device(h);
+    if (value && !h->e.range_dev) CV2_CUDA(cudaMalloc(&h->e.range_dev, Engine::R_COUNT * sizeof(unsigned)));
+    if (h->e.range_dev) CV2_CUDA(cudaMemset(h->e.range_dev, 0, Engine::R_COUNT * sizeof(unsigned)));
+    h->e.range_check = value != 0;
+  }
   else fail("unknown engine option '%s'", name);
+  CV2_API_END
+}
+
+int cv2_engine_read_ranges(cv2_engine* h, float* max_abs, int n) {
+  CV2_API_BEGIN
+  CV2_CHECK(h && max_abs && n >= 1, "null argument");
+  CV2_CHECK(h->e.range_dev, "range_check was never enabled (cv2_engine_set_option(e, \"range_check\", 1))");
+  use_device(h);
+  unsigned bits[Engine::R_COUNT];
+  CV2_CUDA(cudaDeviceSynchronize());
+  CV2_CUDA(cudaMemcpy(bits, h->e.range_dev, sizeof(bits), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) {
+    float f = 0.f;
+    if (i < Engine::R_COUNT) memcpy(&f, &bits[i], 4);
+    max_abs[i] = f;
+  }
+  CV2_CUDA(cudaMemset(h->e.range_dev, 0, sizeof(bits)));
   CV2_API_END
 }
 
@@ -171,6 +201,7 @@ int cv2_estimator_forward(cv2_engine* h, void* stream, const float* x, const flo
   CV2_API_BEGIN
   CV2_CHECK(h && h->e.has_flow, "engine not finalized for flow");
   CV2_CHECK(x && mask && mu && t && spks && cond && out && workspace, "null argument");
+  use_device(h);
   Arena ws;
   ws.base = static_cast<uint8_t*>(workspace);
   ws.cap = workspace_bytes;
@@ -208,6 +239,7 @@ int cv2_flow_forward(cv2_engine* h, void* stream, const int32_t* token, int toke
             "bad sizes B=%d max_tok_total=%d n_steps=%d", B, max_tok_total, n_steps);
   CV2_CHECK(2 * max_tok_total <= noise_stride, "sequence of %d mel frames exceeds the CFM noise buffer (%d)", 2 * max_tok_total,
             noise_stride);
+  use_device(h);
   Arena ws;
   ws.base = static_cast<uint8_t*>(workspace);
   ws.cap = workspace_bytes;
@@ -220,6 +252,39 @@ int cv2_flow_forward(cv2_engine* h, void* stream, const int32_t* token, int toke
   a.B = B; a.max_tok_total = max_tok_total; a.streaming = streaming; a.finalize = finalize;
   a.t_steps = t_steps_dev; a.dt_steps = dt_steps_host; a.n_steps = n_steps; a.cfg = cfg_rate;
   a.mel_out = mel_out; a.mel_out_T = mel_out_T; a.mu_out = mu_out; a.enc_out = enc_out;
+  h->e.launches = 0;
+  flow_forward(h->e, (cudaStream_t)stream, a, ws);
+  CV2_API_END
+}
+
+size_t cv2_encoder_workspace_bytes(cv2_engine* h, int B, int T, int with_context) {
+  try {
+    Arena ws;
+    FlowArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.enc_only = 1; a.enc_T = T; a.max_tok_total = T + (with_context ? 3 : 0); a.n_steps = 1; a.finalize = !with_context;
+    return flow_forward(h->e, nullptr, a, ws) + 4096;
+  } catch (const std::exception& ex) {
+    last_error_ref() = ex.what();
+    return 0;
+  }
+}
+
+int cv2_encoder_forward(cv2_engine* h, void* stream, const float* xs, int T, const int32_t* xs_lens, const float* context,
+                        int streaming, float* out, int B, void* workspace, size_t workspace_bytes) {
+  CV2_API_BEGIN
+  CV2_CHECK(h && h->e.has_flow, "engine not finalized for flow");
+  CV2_CHECK(xs && xs_lens && out && workspace, "null argument");
+  CV2_CHECK(B >= 1 && T >= 1, "bad sizes B=%d T=%d", B, T);
+  use_device(h);
+  Arena ws;
+  ws.base = static_cast<uint8_t*>(workspace);
+  ws.cap = workspace_bytes;
+  FlowArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.enc_only = 1; a.enc_xs = xs; a.enc_T = T; a.enc_lens = xs_lens; a.enc_ctx = context;
+  a.max_tok_total = T + (context ? 3 : 0);
+  a.streaming = streaming; a.finalize = context == nullptr; a.n_steps = 1; a.enc_out = out;
   h->e.launches = 0;
   flow_forward(h->e, (cudaStream_t)stream, a, ws);
   CV2_API_END
@@ -245,6 +310,7 @@ static int hift_forward_impl(cv2_engine* h, void* stream, const float* mel, int 
   CV2_CHECK(h && h->e.has_hift, "engine not finalized for hift");
   CV2_CHECK(mel && speech && source && workspace, "null argument");
   CV2_CHECK(B >= 1 && mel_T >= 1, "bad sizes");
+  use_device(h);
   Arena ws;
   ws.base = static_cast<uint8_t*>(workspace);
   ws.cap = workspace_bytes;

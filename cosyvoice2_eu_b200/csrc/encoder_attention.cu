@@ -273,11 +273,8 @@ rel_attn_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_constant_
 void launch_rel_attn(const RelAttnParams& p, cudaStream_t stream) {
   CV2_CHECK(p.T_alloc % 128 == 0, "rel_attn: T_alloc %d not a multiple of 128", p.T_alloc);
   CV2_CHECK(p.R_alloc >= 2 * p.Tmax - 1, "rel_attn: position table has %d rows, need %d", p.R_alloc, 2 * p.Tmax - 1);
-  static bool configured = false;
-  if (!configured) {
-    CV2_CUDA(cudaFuncSetAttribute(rel_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRelSmem));
-    configured = true;
-  }
+  static PerDeviceOnce once;
+  once.run([] { CV2_CUDA(cudaFuncSetAttribute(rel_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRelSmem)); });
   const uint64_t SH = (uint64_t)p.S * 8;
   uint64_t dq[3] = {64, (uint64_t)p.T_alloc, SH};
   uint64_t sq[2] = {128, (uint64_t)p.T_alloc * 128};

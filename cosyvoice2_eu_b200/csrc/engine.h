@@ -46,6 +46,9 @@ struct Arena {
   template <class T>
   T* get(size_t n) { return reinterpret_cast<T*>(alloc(n * sizeof(T))); }
   bool measuring() const { return base == nullptr; }
+  // scoped reuse: everything allocated after mark() is handed back by rewind(mark) (peak keeps the high-water mark)
+  size_t mark() const { return off; }
+  void rewind(size_t m) { off = m; }
 };
 
 // A 16-bit weight matrix [N, Ktot] prepared for the tap GEMM (+ fp32 bias).
@@ -79,6 +82,18 @@ struct Engine {
   std::unordered_map<std::string, Weight> weights;      // lazily built from tensors
   std::unordered_map<uint64_t, CUtensorMap> amap_cache;  // activation tensor maps
   long long launches = 0;                                // kernels launched by the last forward (claims for bench)
+  int min_2sm_tiles = 148;   // the 2-SM (cta_group::2) GEMM / FFN forms switch on at this many row tiles (one per SM)
+
+  // ---- opt-in fp16 range telemetry (option "range_check"): operands are fp16 (saturates at 65504), so a trained checkpoint
+  //      can be checked for headroom: after every launch the 16-bit tensors it wrote are scanned for their max |x| ----
+  enum RangeCat { R_GEMM_EMIT = 0, R_Q, R_K, R_V, R_ATTN_OUT, R_FFN_EMIT, R_HIFT_EMIT, R_COUNT };
+  bool range_check = false;
+  bool in_hift = false;
+  unsigned* range_dev = nullptr;   // [R_COUNT] fp32 bit patterns of the running max |x| (device, owned by the engine)
+  void range_scan(cudaStream_t st, int cat, const __half* ptr, long long rows, int cols, long long ld);
+  void range_scan_emit(cudaStream_t st, int cat, const Emit& em, long long rows, int cols) {
+    if (em.kind != EMIT_NONE && em.ptr) range_scan(st, cat, em.ptr + em.col_off, rows, cols, em.ld);
+  }
 
   // compact active-tile lists keyed by (lens pointer, T_alloc): gemm() attaches them automatically
   struct TileList { const int* list; const int* count; };
@@ -158,7 +173,13 @@ struct FlowArgs {
   float* mel_out;               // [B, 80, mel_out_T] NCT; frames after the prompt; zero padded
   int mel_out_T;
   float* mu_out;                // optional [B, 80, 2*T] (debug / tests) or null
-  float* enc_out;               // optional [B, 2*T_enc_alloc... see capi] or null
+  float* enc_out;               // optional [B, 2*max_tok_total, 512] (encoder slot: [B, 2*enc_T, 512]) or null
+  // encoder slot (boundary #5, cv2_encoder_forward): UpsampleConformerEncoder.forward alone on caller-made embeddings
+  int enc_only;
+  const float* enc_xs;          // [B, enc_T, 512] fp32 (input_embedding(token) * mask), replaces the table lookup
+  int enc_T;
+  const int* enc_lens;          // [B] valid rows of enc_xs (values above enc_T are clamped, like make_pad_mask(xs_lens, T))
+  const float* enc_ctx;         // [B, 3, 512] look-ahead context (flow.py:262-263) or null
 };
 size_t flow_forward(Engine& e, cudaStream_t st, const FlowArgs& a, Arena& ws);
 

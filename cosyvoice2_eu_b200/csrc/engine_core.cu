@@ -1,7 +1,13 @@
 // Engine plumbing shared by the flow and HiFT forwards: weight lookup, tensor-map caches, GEMM front-end.
 #include "engine.h"
+#include "flow_kernels.cuh"
 
 namespace cv2 {
+
+void Engine::range_scan(cudaStream_t st, int cat, const __half* ptr, long long rows, int cols, long long ld) {
+  if (!range_check || !range_dev || !ptr) return;
+  launch_absmax16(ptr, rows, cols, ld, range_dev + (in_hift && cat == R_GEMM_EMIT ? (int)R_HIFT_EMIT : cat), st);
+}
 
 Weight& Engine::W(const std::string& name) {
   auto it = weights.find(name);
@@ -81,12 +87,18 @@ void Engine::ffn(cudaStream_t st, const __half* H, int S, int T_alloc, Weight& w
   }
   const CUtensorMap& th = amap(H, S, T_alloc, 256, 256);
   prof_begin(st, F_FFN_FUSED);
-  if (ffn_2cta && p.tile_list && (long long)S * (T_alloc / 128) >= 148) {
+  if (ffn_2cta && p.tile_list && (long long)S * (T_alloc / 128) >= min_2sm_tiles) {
     launch_ffn_fused2(th, wmap(w1, 64), wmap(w2, 128), p, st);   // 2-SM MMAs, each CTA stages half of every weight tile
   } else {
     launch_ffn_fused(th, wmap(w1, 128), wmap(w2, 128), p, st);
   }
   prof_end(st);
+  if (range_check) {
+    const long long rows = (long long)S * T_alloc;
+    range_scan_emit(st, R_FFN_EMIT, p.emit_ln, rows, 256);
+    range_scan_emit(st, R_FFN_EMIT, p.emit_plain[0], rows, 256);
+    range_scan_emit(st, R_FFN_EMIT, p.emit_plain[1], rows, 256);
+  }
 }
 
 void Engine::gemm(cudaStream_t st, const __half* A, int S, int T_alloc, int Kc, long long ldA, Weight& w, int bn, int ntaps,
@@ -117,12 +129,21 @@ void Engine::gemm(cudaStream_t st, const __half* A, int S, int T_alloc, int Kc, 
   // 2-CTA clusters with TMA multicast of the weight operand: big launches only (>= 2 row tiles per SM pair), compact list required
   { extern long long* g_ffn_trace_ptr(); static const int tq = getenv("CV2_TRACE_QKV") != nullptr; p.trace = (tq ? p.q != nullptr : (p.res != nullptr && p.N == 256 && p.emit[0].kind != 0 && bn == 256 && p.ntaps == 1)) && g_ffn_trace_ptr() ? g_ffn_trace_ptr() + 8192 : nullptr; }
   { static const int dbg = getenv("CV2_DBG_SKIP_EPI") ? atoi(getenv("CV2_DBG_SKIP_EPI")) : 0; p.dbg_skip_epi = (dbg == 1) || (dbg == 2 && p.q != nullptr) || (dbg == 3 && p.res != nullptr); }
-  if (cluster_mc && bn == 256 && p.tile_list && (long long)S * (T_alloc / 128) >= 148) p.tmB_half = &wmap(w, 128);
+  if (cluster_mc && bn == 256 && p.tile_list && (long long)S * (T_alloc / 128) >= min_2sm_tiles) p.tmB_half = &wmap(w, 128);
   const CUtensorMap& tb = wmap(w, bn);
   const CUtensorMap& ta = amap(A, p.S_map > 0 ? p.S_map : S, T_alloc, Kc, ldA);
   prof_begin(st, bn == 256 ? F_COUNT + gemm_tap_spec(bn, p) : bi);
   launch_gemm_tap(bn, ta, tb, p, st);
   prof_end(st);
+  if (range_check && !p.flat) {
+    const long long rows = (long long)S * T_alloc;
+    for (int i = 0; i < 3; i++) range_scan_emit(st, R_GEMM_EMIT, p.emit[i], rows, p.N);
+    const long long hd = (long long)S * p.heads * T_alloc;     // rows of 64 per head tensor
+    if (p.q) range_scan(st, R_Q, p.q, hd, 64, 64);
+    if (p.q2) range_scan(st, R_Q, p.q2, hd, 64, 64);
+    if (p.k) range_scan(st, R_K, p.k, hd, 64, 64);
+    if (p.vt) range_scan(st, R_V, p.vt, hd, 64, 64);
+  }
 }
 
 }  // namespace cv2

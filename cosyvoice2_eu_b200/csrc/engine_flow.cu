@@ -133,6 +133,7 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
           e.prof_begin(st, Engine::F_FLASH_ATTN);
           launch_flash_attn(ap, st);
           e.prof_end(st);
+          e.range_scan(st, Engine::R_ATTN_OUT, b.ATT16, (long long)S * T, 512, 512);
         }
       }
       {  // out-proj + bias + residual ; emit LN(norm3)
@@ -300,6 +301,7 @@ static void enc_layer(Engine& e, cudaStream_t st, const EncBuffers& b, const std
       e.prof_begin(st, Engine::F_REL_ATTN);
       launch_rel_attn(ap, st);
       e.prof_end(st);
+      e.range_scan(st, Engine::R_ATTN_OUT, b.ATT16, (long long)S * T, 512, 512);
     }
   }
   {  // linear_out + residual
@@ -334,6 +336,7 @@ static void enc_layer(Engine& e, cudaStream_t st, const EncBuffers& b, const std
 
 size_t flow_forward(Engine& e, cudaStream_t st, const FlowArgs& a, Arena& ws) {
   const bool dry = ws.measuring();
+  e.in_hift = false;
   const int B = a.B;
   const int Tt = round_up(a.max_tok_total + 4, 128);          // token-rate rows (+ lookahead reads)
   const int Tm = round_up(2 * a.max_tok_total, 128);          // mel-rate rows
@@ -344,9 +347,14 @@ size_t flow_forward(Engine& e, cudaStream_t st, const FlowArgs& a, Arena& ws) {
   int* len_enc = ws.get<int>(B);       // tokens the encoder keeps (minus the 3 lookahead tokens when not final)
   int* len_mel = ws.get<int>(2 * B);   // mel frames, duplicated for the two CFG rows
   e.launches += 4;
-  if (!dry) {
+  if (!dry && a.enc_only) {
+    launch_lens_clamp(a.enc_lens, a.enc_T, 0, len_enc, B, st);
+    launch_lens_clamp(a.enc_lens, a.enc_T, a.enc_ctx ? 3 : 0, len_ctx, B, st);
+  } else if (!dry) {
     launch_lens_affine(a.prompt_len, a.token_len, 1, 0, len_ctx, B, st);
     launch_lens_affine(len_ctx, nullptr, 1, a.finalize ? 0 : -3, len_enc, B, st);
+  }
+  if (!dry) {
     launch_lens_affine(len_enc, nullptr, 2, 0, len_mel, B, st);
     launch_lens_affine(len_enc, nullptr, 2, 0, len_mel + B, B, st);
   }
@@ -373,18 +381,28 @@ size_t flow_forward(Engine& e, cudaStream_t st, const FlowArgs& a, Arena& ws) {
   eb.H16 = ws.get<__half>((size_t)B * Tm * 512);
   eb.ATT16 = ws.get<__half>((size_t)B * Tm * 512);
   eb.F16 = ws.get<__half>((size_t)B * Tm * 2048);
-  float* MU32 = ws.get<float>((size_t)B * Tm * 80);
-  float* COND32 = ws.get<float>((size_t)B * Tm * 80);
-  float* SPK32 = ws.get<float>((size_t)B * 80);
-  float* Xst = ws.get<float>((size_t)B * Tm * 80);
-  __half* XIN16 = ws.get<__half>((size_t)2 * B * Tm * 320);
-  EstBuffers sb = est_alloc(ws, 2 * B, Tm);
-  float* tres = est_time(e, st, ws, a.t_steps, a.n_steps, dry);
+  float *MU32 = nullptr, *COND32 = nullptr, *SPK32 = nullptr, *Xst = nullptr, *tres = nullptr;
+  __half* XIN16 = nullptr;
+  EstBuffers sb;
+  memset(&sb, 0, sizeof(sb));
+  if (!a.enc_only) {
+    MU32 = ws.get<float>((size_t)B * Tm * 80);
+    COND32 = ws.get<float>((size_t)B * Tm * 80);
+    SPK32 = ws.get<float>((size_t)B * 80);
+    Xst = ws.get<float>((size_t)B * Tm * 80);
+    XIN16 = ws.get<__half>((size_t)2 * B * Tm * 320);
+    sb = est_alloc(ws, 2 * B, Tm);
+    tres = est_time(e, st, ws, a.t_steps, a.n_steps, dry);
+  }
 
   e.launches += 1;
-  if (!dry)
-    launch_embed_tokens(a.prompt_token, a.prompt_len, a.prompt_stride, a.token, a.token_len, a.token_stride,
-                        e.f32("flow.embedding"), A0, B, Tt, 6561, st);
+  if (!dry) {
+    if (a.enc_only)
+      launch_embed_rows(a.enc_xs, a.enc_T, len_enc, a.enc_ctx, 3, A0, B, Tt, st);
+    else
+      launch_embed_tokens(a.prompt_token, a.prompt_len, a.prompt_stride, a.token, a.token_len, a.token_stride,
+                          e.f32("flow.embedding"), A0, B, Tt, 6561, st);
+  }
   {  // embed: Linear -> (LN * sqrt(512) folded into gamma/beta)
     GemmParams p = base_params(len_ctx);
     p.out32 = E32; p.out32_ld = 512;
@@ -458,10 +476,12 @@ size_t flow_forward(Engine& e, cudaStream_t st, const FlowArgs& a, Arena& ws) {
   if (!dry) {
     LN ln = e.ln("enc.after_norm");
     launch_layernorm512(eb.X32, ln.g, ln.b, 1e-5f, eb.H16, a.enc_out ? E32 : nullptr, len_mel, 0, B, Tm, st);
+    const size_t enc_rows = a.enc_only ? (size_t)2 * a.enc_T : (size_t)2 * a.max_tok_total;
     if (a.enc_out)
-      CV2_CUDA(cudaMemcpy2DAsync(a.enc_out, (size_t)2 * a.max_tok_total * 512 * 4, E32, (size_t)Tm * 512 * 4,
-                                 (size_t)2 * a.max_tok_total * 512 * 4, B, cudaMemcpyDeviceToDevice, st));
+      CV2_CUDA(cudaMemcpy2DAsync(a.enc_out, enc_rows * 512 * 4, E32, (size_t)Tm * 512 * 4, enc_rows * 512 * 4, B,
+                                 cudaMemcpyDeviceToDevice, st));
   }
+  if (a.enc_only) return ws.peak;
   {  // encoder_proj 512 -> 80
     GemmParams p = base_params(len_mel);
     p.out32 = MU32; p.out32_ld = 80;

@@ -366,15 +366,14 @@ void launch_ffn_fused(const CUtensorMap& tmH, const CUtensorMap& tmW1, const CUt
                       cudaStream_t stream) {
   FfnParams p = p_in;
   p.trace = g_ffn_trace;
-  static bool configured = false;
-  static int num_sms = 0;
-  if (!configured) {
+  static PerDeviceOnce once;
+  static int num_sms = 0;      // every device of a box is the same part
+  once.run([] {
     CV2_CUDA(cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem));
     int dev = 0;
     CV2_CUDA(cudaGetDevice(&dev));
     CV2_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
-  }
+  });
   CV2_CHECK(p.T_alloc % 128 == 0, "ffn_fused: T_alloc %d not a multiple of 128", p.T_alloc);
   const int total = (p.T_alloc / 128) * p.S;
   const int grid = total < num_sms ? total : num_sms;

@@ -418,8 +418,8 @@ extern long long* g_ffn_trace_ptr();
 
 void launch_ffn_fused2(const CUtensorMap& tmH, const CUtensorMap& tmW1h, const CUtensorMap& tmW2h, const FfnParams& p_in,
                        cudaStream_t stream) {
-  static bool configured = false;
-  static int max_clusters = 0;
+  static PerDeviceOnce once;
+  static int max_clusters = 0;   // every device of a box is the same part
   FfnParams p = p_in;
   p.trace = g_ffn_trace_ptr();
   CV2_CHECK(p.tile_list && p.tile_count && p.lens, "ffn_fused2: the 2-SM path needs the compact tile list");
@@ -432,7 +432,7 @@ void launch_ffn_fused2(const CUtensorMap& tmH, const CUtensorMap& tmW1h, const C
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   q.attrs = at;
   q.numAttrs = 1;
-  if (!configured) {
+  once.run([&] {
     CV2_CUDA(cudaFuncSetAttribute(ffn_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem));
     int dev = 0, sms = 0;
     CV2_CUDA(cudaGetDevice(&dev));
@@ -440,8 +440,7 @@ void launch_ffn_fused2(const CUtensorMap& tmH, const CUtensorMap& tmW1h, const C
     q.gridDim = dim3(sms / 2 * 2);
     CV2_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, ffn_fused2_kernel, &q));
     CV2_CHECK(max_clusters > 0, "ffn_fused2: no 2-CTA cluster fits");
-    configured = true;
-  }
+  });
   CV2_CHECK(p.T_alloc % 128 == 0, "ffn_fused2: T_alloc %d not a multiple of 128", p.T_alloc);
   const int units = ((p.T_alloc / 128) * p.S + 1) / 2;
   const int clusters = units < max_clusters ? units : max_clusters;

@@ -33,6 +33,50 @@ void launch_embed_tokens(const int* prompt_tok, const int* prompt_len, int promp
   CV2_LAUNCH_CHECK();
 }
 
+// ---- encoder slot (upsample_encoder.py:243-251): the caller hands over input_embedding(token) * mask and, for a non-final
+//      streaming chunk, the 3 look-ahead embeddings as `context`; rows [len, len + n_ctx) of the A operand take the context
+__global__ void embed_rows_kernel(const float* __restrict__ xs, int T_in, const int* __restrict__ lens, const float* __restrict__ ctx,
+                                  int n_ctx, __half* __restrict__ out, int T_alloc) {
+  const int t = blockIdx.x, b = blockIdx.y;
+  const int len = lens[b];
+  const float* row = nullptr;
+  if (t < len) row = xs + ((long long)b * T_in + t) * 512;
+  else if (ctx && t < len + n_ctx) row = ctx + ((long long)b * n_ctx + (t - len)) * 512;
+  __half* o = out + ((long long)b * T_alloc + t) * 512;
+  for (int c = threadIdx.x; c < 512; c += blockDim.x) o[c] = __float2half_rn(row ? row[c] : 0.f);
+}
+void launch_embed_rows(const float* xs, int T_in, const int* lens, const float* ctx, int n_ctx, __half* out, int B, int T_alloc,
+                       cudaStream_t st) {
+  embed_rows_kernel<<<dim3(T_alloc, B), 128, 0, st>>>(xs, T_in, lens, ctx, n_ctx, out, T_alloc);
+  CV2_LAUNCH_CHECK();
+}
+__global__ void absmax16_kernel(const __half* __restrict__ p, long long rows, int cols, long long ld, unsigned* __restrict__ slot) {
+  float m = 0.f;
+  const long long n = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const float v = fabsf(__half2float(p[r * ld + (i - r * cols)]));
+    m = fmaxf(m, v == v ? v : INFINITY);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(m));
+}
+void launch_absmax16(const __half* p, long long rows, int cols, long long ld, unsigned* slot, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return;
+  const long long n = rows * cols;
+  const unsigned grid = (unsigned)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  absmax16_kernel<<<grid, 256, 0, st>>>(p, rows, cols, ld, slot);
+  CV2_LAUNCH_CHECK();
+}
+__global__ void lens_clamp_kernel(const int* a, int hi, int add, int* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = min(a[i], hi) + add;
+}
+void launch_lens_clamp(const int* a, int hi, int add, int* out, int n, cudaStream_t st) {
+  lens_clamp_kernel<<<(n + 127) / 128, 128, 0, st>>>(a, hi, add, out, n);
+  CV2_LAUNCH_CHECK();
+}
+
 // ---- LayerNorm over 512 channels, fp32 in -> 16-bit out (warp per row) ---------------------------------
 __global__ void layernorm512_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ bta,
                                     float eps, __half* __restrict__ out16, float* __restrict__ out32, const int* __restrict__ lens,

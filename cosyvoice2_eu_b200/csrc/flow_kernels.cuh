@@ -24,4 +24,11 @@ void launch_f32_to_f16(const float* in, __half* out, long long n, cudaStream_t s
 
 void launch_split16(const float* x, int C, __half* out, int ld, int lo_off, long long rows, cudaStream_t st);
 
+// encoder slot: fp32 embeddings [B, T_in, 512] (+ optional 3-row look-ahead context) -> 16-bit A operand rows, zero padded
+void launch_embed_rows(const float* xs, int T_in, const int* lens, const float* ctx, int n_ctx, __half* out, int B, int T_alloc,
+                       cudaStream_t st);
+// max |x| of a strided 16-bit matrix into *slot (fp32 bit pattern, atomicMax; NaN counts as +inf)
+void launch_absmax16(const __half* p, long long rows, int cols, long long ld, unsigned* slot, cudaStream_t st);
+// out[i] = min(a[i], hi) + add
+void launch_lens_clamp(const int* a, int hi, int add, int* out, int n, cudaStream_t st);
 }  // namespace cv2

@@ -648,14 +648,14 @@ static int g_num_sms = 0;
 
 template <int BN, class Cfg, int CS>
 static void launch_cfg_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  static bool configured = false;
-  static int max_clusters = 0;
+  static PerDeviceOnce once;
+  static int max_clusters = 0;   // every device of a box is the same part
   if (g_num_sms == 0) {
     int dev = 0;
     CV2_CUDA(cudaGetDevice(&dev));
     CV2_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  if (!configured) {
+  once.run([&] {
     CV2_CUDA(cudaFuncSetAttribute(gemm_tap_kernel<BN, Cfg, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, CS>::kTotal));
     if (CS > 1) {
       cudaLaunchConfig_t q = {};
@@ -670,8 +670,7 @@ static void launch_cfg_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
       CV2_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, gemm_tap_kernel<BN, Cfg, CS>, &q));
       CV2_CHECK(max_clusters > 0, "gemm_tap: no cluster of %d CTAs fits", CS);
     }
-    configured = true;
-  }
+  });
   const int rows = (p.T_alloc / kTileM) * p.S;                         // upper bound on row tiles (the list may hold fewer)
   const int total = ((p.N + BN - 1) / BN) * ((rows + CS - 1) / CS);    // work units
   if (CS == 1) {

@@ -254,9 +254,8 @@ void launch_nsf_source(const float* f0, int f0_stride, float* P, int T_alloc, co
 __constant__ float c_cos16[16];
 __constant__ float c_sin16[16];
 __constant__ float c_hann16[16];
-static bool g_tables_ready = false;
-static void ensure_tables() {
-  if (g_tables_ready) return;
+static PerDeviceOnce g_tables_once;   // __constant__ memory is per device
+static void upload_tables() {
   float c[16], s[16], w[16];
   for (int i = 0; i < 16; i++) {
     c[i] = (float)cos(2.0 * M_PI * i / 16.0);
@@ -266,8 +265,8 @@ static void ensure_tables() {
   CV2_CUDA(cudaMemcpyToSymbol(c_cos16, c, sizeof(c)));
   CV2_CUDA(cudaMemcpyToSymbol(c_sin16, s, sizeof(s)));
   CV2_CUDA(cudaMemcpyToSymbol(c_hann16, w, sizeof(w)));
-  g_tables_ready = true;
 }
+static void ensure_tables() { g_tables_once.run(upload_tables); }
 void hift_init_tables() { ensure_tables(); }
 
 // One block = 256 consecutive frames of one utterance: the 1036 source samples they cover are staged in shared memory

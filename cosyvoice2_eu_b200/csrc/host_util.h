@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <stdexcept>
 #include <string>
 
@@ -45,6 +46,23 @@ struct Error : std::runtime_error {
   } while (0)
 
 #define CV2_LAUNCH_CHECK() CV2_CUDA(cudaGetLastError())
+
+// One-time setup that is PER DEVICE (cudaFuncSetAttribute, __constant__ uploads): a process may hold engines on several GPUs
+// (get_engine("cuda:1")), and a process-wide `static bool configured` would leave every device but the first unconfigured.
+// run(f) calls f() the first time it is reached with a given current device; thread safe.
+struct PerDeviceOnce {
+  std::mutex m;
+  unsigned long long done = 0;   // bit per device ordinal (<= 64 devices)
+  template <class F>
+  void run(F&& f) {
+    int dev = 0;
+    CV2_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> g(m);
+    if ((done >> (dev & 63)) & 1ull) return;
+    f();
+    done |= 1ull << (dev & 63);
+  }
+};
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -23,8 +23,8 @@ from . import pack as _pack
 _DT = {torch.float32: 0, torch.float16: 1, torch.int32: 2}
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def euler_schedule(n_timesteps=10):
@@ -44,20 +44,27 @@ def euler_schedule(n_timesteps=10):
 
 
 class _Engine:
-    """Owns the C engine handle, the packed device weights and the workspaces."""
+    """Owns the C engine handle, the packed device weights, the workspaces and the pinned staging buffers.
+
+    Concurrency (boundary #1 is called from a thread pool by the reference's servers, runtime/python/grpc/server.py:75): the C
+    engine keeps per-forward scratch state (tile lists, launch counter, tensor-map cache) and the workspaces are per stream, so
+    every "fill staging -> H2D -> workspace -> C call" sequence runs under `self.lock`.  The lock covers host-side launch
+    submission only (a few ms); the GPU work of different threads is ordered by the stream they share."""
 
     def __init__(self, device="cuda:0"):
         if not torch.cuda.is_available():
             raise _lib.Cv2Error("cosyvoice2_eu_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device(device)
-        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         h = C.c_void_p()
-        _lib.check(self.lib.cv2_engine_create(C.byref(h), idx))
+        _lib.check(self.lib.cv2_engine_create(C.byref(h), self.device.index))
         self.h = h
         self.tensors = {}
-        self.ws = {}
-        self.lock = threading.Lock()
+        self.ws = {}          # (kind, stream) -> [buffer, layout key]
+        self.pinned = {}      # (name, stream) -> [flat pinned buffer, event of the last H2D copy out of it]
+        self.lock = threading.RLock()
 
     def __del__(self):
         try:
@@ -76,14 +83,48 @@ class _Engine:
     def finalize(self, flow, hift):
         _lib.check(self.lib.cv2_engine_finalize(self.h, int(flow), int(hift)))
 
-    def workspace(self, key, nbytes):
-        """Zero-initialised, cached per (kind, shape, stream)."""
-        key = key + (torch.cuda.current_stream().cuda_stream,)
-        w = self.ws.get(key)
-        if w is None or w.numel() < nbytes:
-            w = torch.zeros(int(nbytes), dtype=torch.uint8, device=self.device)
-            self.ws[key] = w
-        return w
+    def stream(self):
+        return _stream(self.device)
+
+    def workspace(self, kind, layout, nbytes):
+        """ONE grow-only device buffer per (kind, stream) -- a server that sees a new shape on every streaming chunk must not
+        accumulate one workspace per shape.  The C side carves it with a bump allocator, so a different `layout` (the rounded
+        sizes the carve-up depends on) puts tensors at different offsets: the buffer is re-zeroed (stream ordered) whenever the
+        layout changes or it had to grow, which restores the "zero-initialised workspace" contract of include/cv2eu_b200.h."""
+        key = (kind, torch.cuda.current_stream(self.device).cuda_stream)
+        ent = self.ws.get(key)
+        if ent is None or ent[0].numel() < nbytes:
+            ent = [torch.zeros(int(nbytes), dtype=torch.uint8, device=self.device), layout]
+            self.ws[key] = ent
+        elif ent[1] != layout:
+            ent[0][:int(nbytes)].zero_()
+            ent[1] = layout
+        return ent[0]
+
+    def staging(self, name, shape, dtype):
+        """Zeroed pinned host buffer of `shape`, one grow-only allocation per (name, stream).  Reuse waits for the H2D copy that
+        last read it (an event, not a whole-stream synchronise)."""
+        key = (name, torch.cuda.current_stream(self.device).cuda_stream)
+        n = int(np.prod(shape)) if len(shape) else 1
+        ent = self.pinned.get(key)
+        if ent is None or ent[0].numel() < n or ent[0].dtype != dtype:
+            ent = [torch.zeros(max(n, 1), dtype=dtype).pin_memory(), None]
+            self.pinned[key] = ent
+        else:
+            if ent[1] is not None:
+                ent[1].synchronize()
+            ent[0][:n].zero_()
+        return ent[0][:n].view(*shape)
+
+    def staged_to_device(self, names_bufs):
+        """Async H2D of staging views on the current stream; records the event their reuse waits for."""
+        st = torch.cuda.current_stream(self.device)
+        out = [b.to(self.device, non_blocking=True) for _, b in names_bufs]
+        ev = torch.cuda.Event()
+        ev.record(st)
+        for name, _ in names_bufs:
+            self.pinned[(name, st.cuda_stream)][1] = ev
+        return out
 
     def last_launches(self):
         return int(self.lib.cv2_engine_last_launches(self.h))
@@ -100,6 +141,49 @@ def get_engine(device="cuda:0"):
     return e
 
 
+class B200Encoder:
+    """The `flow.encoder` slot (boundary #5): UpsampleConformerEncoder.forward (cosyvoice/transformer/upsample_encoder.py:243-306),
+    the module CosyVoice2Model.load_jit swaps in (cosyvoice/cli/model.py:285-287) and flow.inference calls as
+    `encoder(token, token_len, context=..., streaming=...)` (cosyvoice/flow/flow.py:258-263).  Backed by cv2_encoder_forward."""
+
+    def __init__(self, flow):
+        self._eng = flow.eng
+        self.device = flow.eng.device
+
+    def output_size(self):
+        return 512        # read by CausalMaskedDiffWithXvec.__init__ (flow.py:183)
+
+    def eval(self):
+        return self
+
+    @torch.inference_mode()
+    def forward(self, xs, xs_lens, context=torch.zeros(0, 0, 0), decoding_chunk_size=0, num_decoding_left_chunks=-1, streaming=False):
+        """xs [B,T,512] (embedded tokens * mask), xs_lens [B], context [B,3,512] or empty -> (h [B,2T,512] f32, masks [B,1,2T] bool)."""
+        eng, dev = self._eng, self.device
+        xs = xs.to(dev, torch.float32).contiguous()
+        B, T, D = xs.shape
+        assert D == 512
+        lens = xs_lens.to(dev, torch.int32).contiguous()
+        ctx = None
+        if context is not None and context.dim() == 3 and context.shape[1] != 0:
+            assert tuple(context.shape) == (B, 3, 512), "context must hold the pre_lookahead_len = 3 look-ahead embeddings"
+            ctx = context.to(dev, torch.float32).contiguous()
+        out = torch.empty(B, 2 * T, 512, dtype=torch.float32, device=dev)
+        with eng.lock, torch.cuda.device(dev):
+            n = eng.lib.cv2_encoder_workspace_bytes(eng.h, B, T, int(ctx is not None))
+            if n == 0:
+                raise _lib.Cv2Error(eng.lib.cv2_last_error().decode())
+            tot = T + (3 if ctx is not None else 0)
+            ws = eng.workspace("enc", (B, -(-(tot + 4) // 128), -(-2 * tot // 128)), n)
+            _lib.check(eng.lib.cv2_encoder_forward(eng.h, eng.stream(), _lib.ptr(xs), T, _lib.ptr(lens), _lib.ptr(ctx), int(streaming),
+                                                   _lib.ptr(out), B, _lib.ptr(ws), ws.numel()))
+        up_lens = torch.clamp(lens, max=T) * 2        # Upsample1D doubles the lengths (upsample_encoder.py:63)
+        masks = (torch.arange(2 * T, device=dev)[None, :] < up_lens[:, None]).unsqueeze(1)
+        return out, masks
+
+    __call__ = forward
+
+
 class B200Flow:
     """Drop-in for the reference flow object (CausalMaskedDiffWithXvec) on the inference path."""
 
@@ -112,6 +196,8 @@ class B200Flow:
     def __init__(self, device="cuda:0", engine=None):
         self.eng = engine or get_engine(device)
         self.device = self.eng.device
+        self.vocab_size = 6561
+        self.encoder = B200Encoder(self)          # boundary #5 (model.py:285-287 assigns flow.encoder)
         g = torch.Generator(device="cpu")
         g.manual_seed(0)  # CausalConditionalCFM.__init__: set_all_random_seed(0); randn([1,80,15000])  (flow_matching.py:195-198)
         self.rand_noise = torch.randn([1, 80, 50 * 300], generator=g).to(self.device)
@@ -142,27 +228,16 @@ class B200Flow:
         f = lambda a: a.to(self.device, torch.float32).contiguous()
         x, mask, mu, t, spks, cond = map(f, (x, mask, mu, t, spks, cond))
         out = torch.empty_like(x)
-        n = self.eng.lib.cv2_estimator_workspace_bytes(self.eng.h, B2, T)
-        if n == 0:
-            raise _lib.Cv2Error(self.eng.lib.cv2_last_error().decode())
-        ws = self.eng.workspace(("est", B2, T), n)
-        _lib.check(self.eng.lib.cv2_estimator_forward(self.eng.h, _stream(), _lib.ptr(x), _lib.ptr(mask), _lib.ptr(mu), _lib.ptr(t),
-                                                      _lib.ptr(spks), _lib.ptr(cond), _lib.ptr(out), B2, T, int(streaming),
-                                                      _lib.ptr(ws), ws.numel()))
+        eng = self.eng
+        with eng.lock, torch.cuda.device(self.device):
+            n = eng.lib.cv2_estimator_workspace_bytes(eng.h, B2, T)
+            if n == 0:
+                raise _lib.Cv2Error(eng.lib.cv2_last_error().decode())
+            ws = eng.workspace("est", (B2, -(-T // 128)), n)
+            _lib.check(eng.lib.cv2_estimator_forward(eng.h, eng.stream(), _lib.ptr(x), _lib.ptr(mask), _lib.ptr(mu), _lib.ptr(t),
+                                                     _lib.ptr(spks), _lib.ptr(cond), _lib.ptr(out), B2, T, int(streaming),
+                                                     _lib.ptr(ws), ws.numel()))
         return out
-
-    def _staging(self, name, shape, dtype):
-        """Zeroed pinned host buffer, cached per (name, shape)."""
-        key = (name, tuple(shape), torch.cuda.current_stream().cuda_stream)
-        cache = self.__dict__.setdefault("_pinned", {})
-        buf = cache.get(key)
-        if buf is None:
-            buf = torch.zeros(*shape, dtype=dtype).pin_memory()
-            cache[key] = buf
-        else:
-            torch.cuda.current_stream().synchronize()   # previous async copy out of this buffer must have finished
-            buf.zero_()
-        return buf
 
     # ---- batched flow ----
     def inference_batch(self, tokens, prompt_tokens, prompt_feats, embeddings, streaming=False, finalize=True,
@@ -184,39 +259,51 @@ class B200Flow:
             # a shape mismatch: 15000 mel frames = 300 s is the longest sequence the CFM can take
             raise _lib.Cv2Error(f"prompt + tokens = {max_total} tokens need {2 * max_total} mel frames; the CFM noise buffer holds "
                                 f"{self.rand_noise.shape[2]}")
-        # pinned staging buffers -> async H2D on the current stream
-        tok = self._staging("tok", (B, max(tl)), torch.int32)
-        ptk = self._staging("ptk", (B, max(max(pl), 1)), torch.int32)
-        pf = self._staging("pf", (B, max(max(fl), 1), 80), torch.float32)
-        for b in range(B):
-            tok[b, :tl[b]] = tokens[b].reshape(-1).to(torch.int32).cpu()
-            ptk[b, :pl[b]] = prompt_tokens[b].reshape(-1).to(torch.int32).cpu()
-            pf[b, :fl[b]] = prompt_feats[b].reshape(-1, 80).float().cpu()
-        emb = self._staging("emb", (B, 192), torch.float32)
-        for b in range(B):
-            emb[b] = embeddings[b].reshape(192).float().cpu()
-        lens = self._staging("lens", (3, B), torch.int32)
-        lens.copy_(torch.tensor([tl, pl, fl], dtype=torch.int32))
-        self.last_h2d_bytes = sum(a.numel() * a.element_size() for a in (tok, ptk, pf, emb, lens))
-        tok, ptk, pf, emb, lens = (a.to(dev, non_blocking=True) for a in (tok, ptk, pf, emb, lens))
-        return self._forward_device(tok, lens[0], ptk, lens[1], pf, lens[2], emb, B, max_total, mel_T, streaming, finalize,
-                                    return_intermediates) + (torch.tensor(mel_lens, dtype=torch.int32),)
+        # nn.Embedding raises on an id outside the table (flow.py:256 clamps negatives to 0 first); the lookup kernel only
+        # clamps for memory safety, so the range check happens here, on the host copies
+        host_tok = [t.reshape(-1).to(torch.int32).cpu() for t in tokens]
+        host_ptk = [t.reshape(-1).to(torch.int32).cpu() for t in prompt_tokens]
+        for t in host_tok + host_ptk:
+            if t.numel() and int(t.max()) >= self.vocab_size:
+                raise IndexError(f"speech token id {int(t.max())} is out of range for the {self.vocab_size}-entry embedding table")
+        eng = self.eng
+        with eng.lock, torch.cuda.device(dev):
+            # pinned staging buffers -> async H2D on the current stream
+            tok = eng.staging("tok", (B, max(tl)), torch.int32)
+            ptk = eng.staging("ptk", (B, max(max(pl), 1)), torch.int32)
+            pf = eng.staging("pf", (B, max(max(fl), 1), 80), torch.float32)
+            emb = eng.staging("emb", (B, 192), torch.float32)
+            lens = eng.staging("lens", (3, B), torch.int32)
+            for b in range(B):
+                tok[b, :tl[b]] = host_tok[b]
+                ptk[b, :pl[b]] = host_ptk[b]
+                pf[b, :fl[b]] = prompt_feats[b].reshape(-1, 80).float().cpu()
+                emb[b] = embeddings[b].reshape(192).float().cpu()
+            lens.copy_(torch.tensor([tl, pl, fl], dtype=torch.int32))
+            self.last_h2d_bytes = sum(a.numel() * a.element_size() for a in (tok, ptk, pf, emb, lens))
+            tok, ptk, pf, emb, lens = eng.staged_to_device([("tok", tok), ("ptk", ptk), ("pf", pf), ("emb", emb), ("lens", lens)])
+            out = self._forward_device(tok, lens[0], ptk, lens[1], pf, lens[2], emb, B, max_total, mel_T, streaming, finalize,
+                                       return_intermediates)
+        return out + (torch.tensor(mel_lens, dtype=torch.int32),)
 
     def _forward_device(self, tok, tok_len, ptk, ptk_len, pf, pf_len, emb, B, max_total, mel_T, streaming, finalize,
                         return_intermediates=False):
-        dev = self.device
-        mel = torch.empty(B, 80, mel_T, dtype=torch.float32, device=dev)
-        mu = torch.empty(B, 80, 2 * max_total, dtype=torch.float32, device=dev) if return_intermediates else None
-        enc = torch.empty(B, 2 * max_total, 512, dtype=torch.float32, device=dev) if return_intermediates else None
-        n = self.eng.lib.cv2_flow_workspace_bytes(self.eng.h, B, max_total, self.n_timesteps)
-        if n == 0:
-            raise _lib.Cv2Error(self.eng.lib.cv2_last_error().decode())
-        ws = self.eng.workspace(("flow", B, max_total), n)
-        _lib.check(self.eng.lib.cv2_flow_forward(
-            self.eng.h, _stream(), _lib.ptr(tok), tok.shape[1], _lib.ptr(tok_len), _lib.ptr(ptk), ptk.shape[1], _lib.ptr(ptk_len),
-            _lib.ptr(pf), pf.shape[1] * 80, _lib.ptr(pf_len), _lib.ptr(emb), _lib.ptr(self.rand_noise), self.rand_noise.shape[2], B,
-            max_total, int(streaming), int(finalize), _lib.ptr(self._t_dev), self._dt_host, self.n_timesteps,
-            self.inference_cfg_rate, _lib.ptr(mel), mel_T, _lib.ptr(mu), _lib.ptr(enc), _lib.ptr(ws), ws.numel()))
+        dev, eng = self.device, self.eng
+        with eng.lock, torch.cuda.device(dev):
+            mel = torch.empty(B, 80, mel_T, dtype=torch.float32, device=dev)
+            mu = torch.empty(B, 80, 2 * max_total, dtype=torch.float32, device=dev) if return_intermediates else None
+            enc = torch.empty(B, 2 * max_total, 512, dtype=torch.float32, device=dev) if return_intermediates else None
+            n = eng.lib.cv2_flow_workspace_bytes(eng.h, B, max_total, self.n_timesteps)
+            if n == 0:
+                raise _lib.Cv2Error(eng.lib.cv2_last_error().decode())
+            # the carve-up depends on the row counts rounded to 128 (engine_flow.cu: Tt, Tm)
+            ws = eng.workspace("flow", (B, -(-(max_total + 4) // 128), -(-2 * max_total // 128)), n)
+            _lib.check(eng.lib.cv2_flow_forward(
+                eng.h, eng.stream(), _lib.ptr(tok), tok.shape[1], _lib.ptr(tok_len), _lib.ptr(ptk), ptk.shape[1], _lib.ptr(ptk_len),
+                _lib.ptr(pf), pf.shape[1] * 80, _lib.ptr(pf_len), _lib.ptr(emb), _lib.ptr(self.rand_noise), self.rand_noise.shape[2],
+                B, max_total, int(streaming), int(finalize), _lib.ptr(self._t_dev), self._dt_host, self.n_timesteps,
+                self.inference_cfg_rate, _lib.ptr(mel), mel_T, _lib.ptr(mu), _lib.ptr(enc), _lib.ptr(ws), ws.numel()))
+            self.last_launches = eng.last_launches()
         if return_intermediates:
             return mel, dict(mu=mu, encoder_out=enc)
         return (mel,)
@@ -269,15 +356,18 @@ class B200HiFT:
         if lens is not None:
             speech.zero_()
             source.zero_()
-        n = self.eng.lib.cv2_hift_workspace_bytes(self.eng.h, B, T)
-        if n == 0:
-            raise _lib.Cv2Error(self.eng.lib.cv2_last_error().decode())
-        ws = self.eng.workspace(("hift", B, T), n)
-        self._seed += 1
+        eng = self.eng
         pcm = torch.zeros(B, 480 * T, dtype=torch.int16, device=dev) if return_pcm16 else None
-        _lib.check(self.eng.lib.cv2_hift_forward_pcm16(self.eng.h, _stream(), _lib.ptr(mel), T, _lib.ptr(ln), _lib.ptr(cs), cache_len,
-                                                       _lib.ptr(nz), self._seed, _lib.ptr(speech), _lib.ptr(source), _lib.ptr(f0),
-                                                       _lib.ptr(pcm), B, _lib.ptr(ws), ws.numel()))
+        with eng.lock, torch.cuda.device(dev):
+            n = eng.lib.cv2_hift_workspace_bytes(eng.h, B, T)
+            if n == 0:
+                raise _lib.Cv2Error(eng.lib.cv2_last_error().decode())
+            ws = eng.workspace("hift", (B, T), n)
+            self._seed += 1
+            _lib.check(eng.lib.cv2_hift_forward_pcm16(eng.h, eng.stream(), _lib.ptr(mel), T, _lib.ptr(ln), _lib.ptr(cs), cache_len,
+                                                      _lib.ptr(nz), self._seed, _lib.ptr(speech), _lib.ptr(source), _lib.ptr(f0),
+                                                      _lib.ptr(pcm), B, _lib.ptr(ws), ws.numel()))
+            self.last_launches = eng.last_launches()
         out = (speech, source)
         if return_f0:
             out = out + (f0,)
@@ -298,15 +388,27 @@ class B200Token2Wav:
         self.source_cache_len = int(self.mel_cache_len * 480)
         self.speech_window = np.hamming(2 * self.source_cache_len)
         self._window_dev = torch.from_numpy(self.speech_window).to(self.device)   # float64, like the reference's maths
-        self.lock = threading.Lock()
+        self.lock = threading.Lock()     # guards hift_cache_dict, like CosyVoice2Model.lock (model.py:343-345, 395-398)
         self.hift_cache_dict = {}
 
     def _fade_in_out(self, speech, old_tail):
+        """fade_in_out (CV/utils/common.py:142-150) on the device: the first n samples of `speech` are cross-faded in place with
+        the last n of `old_tail` under the float64 Hamming window."""
         n = self.source_cache_len
         speech = speech.contiguous()
         old = old_tail[..., -n:].contiguous()
-        _lib.check(self.flow.eng.lib.cv2_crossfade(_stream(), _lib.ptr(speech), _lib.ptr(old), _lib.ptr(self._window_dev), n))
+        eng = self.flow.eng
+        with eng.lock, torch.cuda.device(self.device):
+            _lib.check(eng.lib.cv2_crossfade(eng.stream(), _lib.ptr(speech), _lib.ptr(old), _lib.ptr(self._window_dev), n))
         return speech
+
+    def _cache_get(self, uuid):
+        with self.lock:
+            return self.hift_cache_dict.get(uuid)
+
+    def _cache_put(self, uuid, entry):
+        with self.lock:
+            self.hift_cache_dict[uuid] = entry
 
     @torch.inference_mode()
     def token2wav(self, token, prompt_token, prompt_feat, embedding, token_offset, uuid, stream=False, finalize=False, speed=1.0,
@@ -315,7 +417,7 @@ class B200Token2Wav:
                                          prompt_feat=prompt_feat, prompt_feat_len=None, embedding=embedding, streaming=stream,
                                          finalize=finalize)
         tts_mel = tts_mel[:, :, token_offset * self.flow.token_mel_ratio:]
-        cache = self.hift_cache_dict.get(uuid)
+        cache = self._cache_get(uuid)
         if cache is not None:
             tts_mel = torch.concat([cache['mel'], tts_mel], dim=2)
             hift_cache_source = cache['source']
@@ -325,9 +427,9 @@ class B200Token2Wav:
             tts_speech, tts_source = self.hift.inference(speech_feat=tts_mel, cache_source=hift_cache_source, noise=noise)
             if cache is not None:
                 tts_speech = self._fade_in_out(tts_speech, cache['speech'])
-            self.hift_cache_dict[uuid] = {'mel': tts_mel[:, :, -self.mel_cache_len:],
-                                          'source': tts_source[:, :, -self.source_cache_len:],
-                                          'speech': tts_speech[:, -self.source_cache_len:]}
+            self._cache_put(uuid, {'mel': tts_mel[:, :, -self.mel_cache_len:],
+                                   'source': tts_source[:, :, -self.source_cache_len:],
+                                   'speech': tts_speech[:, -self.source_cache_len:]})
             tts_speech = tts_speech[:, :-self.source_cache_len]
         else:
             if speed != 1.0:
@@ -335,8 +437,10 @@ class B200Token2Wav:
                 stretched = torch.empty(tts_mel.shape[0], tts_mel.shape[1], int(tts_mel.shape[2] / speed), dtype=torch.float32,
                                         device=tts_mel.device)
                 src = tts_mel.contiguous()
-                _lib.check(self.flow.eng.lib.cv2_mel_time_stretch(_stream(), _lib.ptr(src), src.shape[2], _lib.ptr(stretched),
-                                                                  stretched.shape[2], src.shape[0] * src.shape[1]))
+                eng = self.flow.eng
+                with eng.lock, torch.cuda.device(self.device):
+                    _lib.check(eng.lib.cv2_mel_time_stretch(eng.stream(), _lib.ptr(src), src.shape[2], _lib.ptr(stretched),
+                                                            stretched.shape[2], src.shape[0] * src.shape[1]))
                 tts_mel = stretched
             tts_speech, tts_source = self.hift.inference(speech_feat=tts_mel, cache_source=hift_cache_source, noise=noise)
             if cache is not None:
@@ -373,12 +477,12 @@ class B200Token2Wav:
         mels = []
         for b, r in enumerate(requests):
             m = mel[b:b + 1, :, r["token_offset"] * self.flow.token_mel_ratio:int(mel_lens[b])]
-            cache = self.hift_cache_dict.get(r["uuid"])
+            cache = self._cache_get(r["uuid"])
             if cache is not None:
                 m = torch.concat([cache["mel"], m], dim=2)
             mels.append(m)
         out = [None] * len(requests)
-        cached = [self.hift_cache_dict.get(r["uuid"]) is not None for r in requests]   # decided once: the loop updates the caches
+        cached = [self._cache_get(r["uuid"]) is not None for r in requests]   # decided once: the loop updates the caches
         for has_cache in (False, True):
             idx = [b for b in range(len(requests)) if cached[b] == has_cache]
             if not idx:
@@ -388,7 +492,7 @@ class B200Token2Wav:
             lens = torch.tensor([mels[b].shape[2] for b in idx], dtype=torch.int32)
             for k, b in enumerate(idx):
                 mb[k, :, :mels[b].shape[2]] = mels[b][0]
-            cs = torch.cat([self.hift_cache_dict[requests[b]["uuid"]]["source"] for b in idx], dim=0) if has_cache \
+            cs = torch.cat([self._cache_get(requests[b]["uuid"])["source"] for b in idx], dim=0) if has_cache \
                 else torch.zeros(len(idx), 1, 0)
             nz = None
             if noises is not None:
@@ -401,11 +505,11 @@ class B200Token2Wav:
                 sp, so = speech[k:k + 1, :L], source[k:k + 1, :, :L]
                 uuid = requests[b]["uuid"]
                 if has_cache:
-                    sp = self._fade_in_out(sp.contiguous(), self.hift_cache_dict[uuid]["speech"])
+                    sp = self._fade_in_out(sp.contiguous(), self._cache_get(uuid)["speech"])
                 if not finalize:
-                    self.hift_cache_dict[uuid] = {"mel": mels[b][:, :, -self.mel_cache_len:].clone(),
-                                                  "source": so[:, :, -self.source_cache_len:].clone(),
-                                                  "speech": sp[:, -self.source_cache_len:].clone()}
+                    self._cache_put(uuid, {"mel": mels[b][:, :, -self.mel_cache_len:].clone(),
+                                           "source": so[:, :, -self.source_cache_len:].clone(),
+                                           "speech": sp[:, -self.source_cache_len:].clone()})
                     sp = sp[:, :-self.source_cache_len]
                 out[b] = sp
         return out
@@ -450,11 +554,11 @@ class GraphedToken2Wav:
 
         _lib.check(eng.lib.cv2_engine_set_seed_ptr(eng.h, _lib.ptr(self.seed)))
         side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream())
+        side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):          # warm-up on the capture stream: workspaces, func attributes, tensor-map caches
             run()
             run()
-        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=side):

@@ -10,8 +10,8 @@ LIB_PATH = os.path.join(_HERE, "libcv2eu_b200.so")
 # every symbol include/cv2eu_b200.h declares (checked by tests/test_cabi_symbols.py)
 SYMBOLS = [
     "cv2_last_error", "cv2_version", "cv2_engine_create", "cv2_engine_destroy", "cv2_engine_set_tensor", "cv2_engine_finalize",
-    "cv2_engine_last_launches", "cv2_engine_set_option", "cv2_debug_set_ffn_trace", "cv2_engine_set_seed_ptr", "cv2_engine_set_profiling", "cv2_engine_read_profile", "cv2_estimator_workspace_bytes", "cv2_estimator_forward", "cv2_flow_workspace_bytes",
-    "cv2_flow_forward", "cv2_hift_workspace_bytes", "cv2_hift_forward", "cv2_hift_forward_pcm16", "cv2_crossfade", "cv2_mel_time_stretch", "cv2_prompt_mel_frames", "cv2_prompt_mel_workspace_bytes",
+    "cv2_engine_last_launches", "cv2_engine_set_option", "cv2_engine_read_ranges", "cv2_debug_set_ffn_trace", "cv2_engine_set_seed_ptr", "cv2_engine_set_profiling", "cv2_engine_read_profile", "cv2_estimator_workspace_bytes", "cv2_estimator_forward", "cv2_flow_workspace_bytes",
+    "cv2_flow_forward", "cv2_encoder_workspace_bytes", "cv2_encoder_forward", "cv2_hift_workspace_bytes", "cv2_hift_forward", "cv2_hift_forward_pcm16", "cv2_crossfade", "cv2_mel_time_stretch", "cv2_prompt_mel_frames", "cv2_prompt_mel_workspace_bytes",
     "cv2_prompt_mel", "cv2_resample_16k_24k_len", "cv2_resample_16k_24k", "cv2_op_gemm_tap", "cv2_op_flash_attn",
     "cv2_op_rel_attn", "cv2_op_source_stft", "cv2_op_istft", "cv2_op_nsf_source",
 ]
@@ -42,6 +42,7 @@ def load():
     lib.cv2_engine_last_launches.argtypes = [vp]
     lib.cv2_engine_last_launches.restype = i64
     lib.cv2_engine_set_option.argtypes = [vp, C.c_char_p, i32]
+    lib.cv2_engine_read_ranges.argtypes = [vp, C.POINTER(f32), i32]
     lib.cv2_debug_set_ffn_trace.argtypes = [vp]
     lib.cv2_engine_set_seed_ptr.argtypes = [vp, vp]
     lib.cv2_engine_set_profiling.argtypes = [vp, i32]
@@ -53,6 +54,9 @@ def load():
     lib.cv2_flow_workspace_bytes.restype = sz
     lib.cv2_flow_forward.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, vp,
                                      C.POINTER(f32), i32, f32, vp, i32, vp, vp, vp, sz]
+    lib.cv2_encoder_workspace_bytes.argtypes = [vp, i32, i32, i32]
+    lib.cv2_encoder_workspace_bytes.restype = sz
+    lib.cv2_encoder_forward.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, i32, vp, sz]
     lib.cv2_hift_workspace_bytes.argtypes = [vp, i32, i32]
     lib.cv2_hift_workspace_bytes.restype = sz
     lib.cv2_hift_forward.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, u64, vp, vp, vp, i32, vp, sz]

@@ -14,14 +14,36 @@ The chunk arithmetic is the reference's, per session:
     (model.py:369-380; it runs with full attention, the quirk SURVEY.md section 8a lists), and the session's cache is dropped
     (model.py:395-396).
 
+  * the loop's break test (model.py:369) reuses the hop computed before `token_offset` moved.  That only differs from the
+    recomputed hop right after the FIRST chunk (hop + pad), and only if the producer had already finished: the reference then
+    finalizes as soon as fewer than hop + pad + lookahead tokens remain.  Reproduced here (`_Session.force_final`), and pinned
+    against the reference's own loop in tests/golden/tts_schedule.npz.
+
 Host logic only: no arithmetic happens here, and nothing here needs a GPU (tests/test_host_logic.py drives it with a stub).
 """
 import math
 import threading
 
 
+def chunk_schedule(n_tokens, n_prompt, hop=25, lookahead=3, all_tokens_ready=False):
+    """The (n_tokens_visible, token_offset, finalize) calls CosyVoice2Model.tts(stream=True) makes for one session
+    (model.py:351-381).  `all_tokens_ready`: the producer had finished before the first chunk went out (vc_job, model.py:141-143)."""
+    pad = int(math.ceil(n_prompt / hop) * hop - n_prompt)
+    calls, off = [], 0
+    while True:
+        this_hop = hop + pad if off == 0 else hop
+        if n_tokens - off < this_hop + lookahead:
+            break
+        calls.append((off + this_hop + lookahead, off, False))
+        off += this_hop
+        if all_tokens_ready and n_tokens - off < this_hop + lookahead:
+            break
+    calls.append((n_tokens, off, True))
+    return calls
+
+
 class _Session:
-    __slots__ = ("uuid", "prompt_token", "prompt_feat", "embedding", "tokens", "token_offset", "pad", "ended", "done")
+    __slots__ = ("uuid", "prompt_token", "prompt_feat", "embedding", "tokens", "token_offset", "pad", "ended", "done", "force_final")
 
     def __init__(self, uuid, prompt_token, prompt_feat, embedding, hop):
         self.uuid = uuid
@@ -32,6 +54,7 @@ class _Session:
         self.pad = int(math.ceil(n_prompt / hop) * hop - n_prompt)
         self.ended = False
         self.done = False
+        self.force_final = False
 
 
 class StreamScheduler:
@@ -77,10 +100,10 @@ class StreamScheduler:
         return self.token_hop_len + s.pad if s.token_offset == 0 else self.token_hop_len
 
     def _ready(self, s):
-        return len(s.tokens) - s.token_offset >= self._this_hop(s) + self.pre_lookahead_len
+        return not s.force_final and len(s.tokens) - s.token_offset >= self._this_hop(s) + self.pre_lookahead_len
 
     def _final_due(self, s):
-        return s.ended and not self._ready(s)
+        return s.force_final or (s.ended and not self._ready(s))
 
     def pending(self):
         with self.cv:
@@ -102,7 +125,11 @@ class StreamScheduler:
                 if self._ready(s):
                     n_vis = s.token_offset + self._this_hop(s) + self.pre_lookahead_len
                     chunk.append((s, n_vis, s.token_offset))
-                    s.token_offset += self._this_hop(s)
+                    hop = self._this_hop(s)
+                    s.token_offset += hop
+                    # model.py:369: the break test still holds the hop of the chunk just emitted
+                    if s.ended and len(s.tokens) - s.token_offset < hop + self.pre_lookahead_len:
+                        s.force_final = True
                 elif self._final_due(s):
                     final.append((s, len(s.tokens), s.token_offset))
                     s.done = True

@@ -66,3 +66,60 @@ def gather_audio(speech, lengths, dst=0, group=None):
         res_s.append(outs[r][:n])
         res_l.append(louts[r][:n])
     return res_s, res_l
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: a corpus sharded by utterance over the ranks of one box, one gather at the end
+# ---------------------------------------------------------------------------------------------------------------------
+SAMPLES_PER_TOKEN = 2 * 480          # token_mel_ratio x hop: 960 samples (40 ms at 24 kHz) per speech token
+
+
+def corpus_plan(n_tokens, n_prompts, world, max_batch=64, max_ratio=1.35):
+    """The whole job as every rank computes it for itself (deterministic, no collective): per rank the utterance indices
+    (cost balanced, length sorted), the length-bucketed batches, and where each utterance's samples go in that rank's flat
+    audio buffer.  `flat_len` = the largest per-rank sample count: every rank allocates that much, so the final gather has one
+    shape on all ranks (gathering ragged shapes is undefined behaviour in NCCL)."""
+    shards = shard_by_cost(n_tokens, n_prompts, world)
+    plan = []
+    for r in range(world):
+        offs, o = {}, 0
+        for i in shards[r]:
+            offs[i] = o
+            o += SAMPLES_PER_TOKEN * n_tokens[i]
+        plan.append({"indices": shards[r], "batches": bucket_batches(shards[r], n_tokens, max_batch, max_ratio), "offsets": offs,
+                     "samples": o})
+    flat_len = max(p["samples"] for p in plan)
+    return plan, flat_len
+
+
+def run_corpus_shard(plan_r, n_tokens, batch_fn, flat):
+    """Run one rank's batches: batch_fn(indices) -> (speech [b, L] on the device, zero padded; anything else is ignored);
+    every utterance's 960 * n_tokens samples are packed into `flat` at the planned offset."""
+    for batch in plan_r["batches"]:
+        speech = batch_fn(batch)[0]
+        for k, i in enumerate(batch):
+            n = SAMPLES_PER_TOKEN * n_tokens[i]
+            o = plan_r["offsets"][i]
+            flat[o:o + n].copy_(speech[k, :n], non_blocking=True)
+    return flat
+
+
+def gather_flat(flat, dst=0, group=None, out=None):
+    """The one collective of the path: every rank's flat audio buffer (same length everywhere, see corpus_plan) to `dst`.
+    `out`: optional preallocated receive buffers (list of world tensors like `flat`) reused across calls."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if rank == dst and out is None:
+        out = [torch.empty_like(flat) for _ in range(world)]
+    dist.gather(flat, out if rank == dst else None, dst=dst, group=group)
+    return out if rank == dst else None
+
+
+def unpack_corpus(gathered, plan, n_tokens):
+    """dst side: {utterance index: 1-D audio tensor (a view into the gathered buffers)}."""
+    res = {}
+    for r, p in enumerate(plan):
+        for i in p["indices"]:
+            o = p["offsets"][i]
+            res[i] = gathered[r][o:o + SAMPLES_PER_TOKEN * n_tokens[i]]
+    return res

@@ -48,6 +48,12 @@ int cv2_engine_set_seed_ptr(cv2_engine* e, const unsigned long long* seed_dev);
 /* engine switches (tests / A-B measurements): "fuse_euler" (CFG combine + Euler update inside final_proj, default 1),
  * "fuse_ffn" (FF1+GELU+FF2 in one kernel, default 1) */
 int cv2_engine_set_option(cv2_engine* e, const char* name, int value);
+/* fp16 range telemetry (opt in with cv2_engine_set_option(e, "range_check", 1); costs one scan kernel per launch): the MMA
+ * operands are fp16, which saturates at 65504 -- after any forward(s), max_abs[i] = largest |x| written to a 16-bit tensor of
+ * category i since the last read (0 GEMM emits of the flow, 1 q, 2 k, 3 v, 4 attention output, 5 FFN emits, 6 vocoder emits);
+ * the read synchronises the device and resets the maxima.  Other options: "min_2sm_tiles" (row tiles at which the
+ * cta_group::2 kernels take over, default 148). */
+int cv2_engine_read_ranges(cv2_engine* e, float* max_abs, int n);
 /* debug: CTA 0 of the following ffn_fused launches logs (clock64 << 8 | event) records into dev_buf[8192] (profiles/ffn_trace.py) */
 int cv2_debug_set_ffn_trace(long long* dev_buf);
 int cv2_engine_set_profiling(cv2_engine* e, int on);
@@ -77,6 +83,17 @@ int cv2_flow_forward(cv2_engine* e, void* stream, const int32_t* token, int toke
                      const float* rand_noise, int noise_stride, int B, int max_tok_total, int streaming, int finalize,
                      const float* t_steps_dev, const float* dt_steps_host, int n_steps, float cfg_rate, float* mel_out,
                      int mel_out_T, float* mu_out, float* enc_out, void* workspace, size_t workspace_bytes);
+
+/* ---- encoder slot (boundary #5): UpsampleConformerEncoder.forward (cosyvoice/transformer/upsample_encoder.py:243-306), the
+ *      module CosyVoice2Model.load_jit swaps in as `flow.encoder` (cosyvoice/cli/model.py:285-287), called by flow.inference as
+ *      `encoder(token, token_len, context=..., streaming=...)` (cosyvoice/flow/flow.py:258-263).
+ *      xs [B,T,512] f32 = input_embedding(token) * mask; xs_lens [B] i32 on the device (values above T are clamped, which is
+ *      what make_pad_mask(xs_lens, T) does to flow.py's `token_len` that still counts the 3 context tokens);
+ *      context [B,3,512] f32 = the look-ahead embeddings of a non-final chunk, or NULL; out [B,2T,512] f32.
+ *      Rows of `out` at or beyond 2*xs_lens[b] are padding (unspecified, finite). ---- */
+size_t cv2_encoder_workspace_bytes(cv2_engine* e, int B, int T, int with_context);
+int cv2_encoder_forward(cv2_engine* e, void* stream, const float* xs, int T, const int32_t* xs_lens, const float* context,
+                        int streaming, float* out, int B, void* workspace, size_t workspace_bytes);
 
 /* ---- hift: HiFTGenerator.inference (cosyvoice/hifigan/generator.py:570-582), batched.
  *      mel [B,80,mel_T] f32; lens [B] i32 valid frames (NULL: all mel_T); cache_source [B,1,cache_len] or NULL;

@@ -57,9 +57,16 @@ def attention_mask(valid, chunk):
     return m
 
 
-def stream_schedule(n_tokens, n_prompt, hop=25, lookahead=3):
+def stream_schedule(n_tokens, n_prompt, hop=25, lookahead=3, all_tokens_ready=False):
     """Chunk schedule of CosyVoice2Model.tts(stream=True), CV/cli/model.py:351-381.
-    Returns list of (n_tokens_visible, token_offset, finalize)."""
+    Returns list of (n_tokens_visible, token_offset, finalize).
+
+    The loop computes `this_token_hop_len` at the top of an iteration (model.py:356) and its break test (model.py:369) reuses
+    that value after `token_offset` has moved.  That only matters in the iteration that emits the FIRST chunk (hop + pad), and
+    only if the LLM has already finished by then: `all_tokens_ready=True` (vc_job, model.py:141-143, or an LLM faster than the
+    first chunk) reproduces it -- the loop then finalizes as soon as fewer than hop + pad + lookahead tokens remain.  With
+    tokens still arriving (`False`) every later iteration recomputes the hop and the two tests agree.
+    tests/golden/tts_schedule.npz holds the reference's own call sequences for the first case."""
     pad = int(math.ceil(n_prompt / hop) * hop - n_prompt)
     calls, off = [], 0
     while True:
@@ -67,6 +74,8 @@ def stream_schedule(n_tokens, n_prompt, hop=25, lookahead=3):
         if n_tokens - off >= this_hop + lookahead:
             calls.append((off + this_hop + lookahead, off, False))
             off += this_hop
+            if all_tokens_ready and n_tokens - off < this_hop + lookahead:      # model.py:369 with the stale hop
+                break
         else:
             break
     calls.append((n_tokens, off, True))

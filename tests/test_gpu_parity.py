@@ -428,3 +428,264 @@ def test_stream_scheduler_on_the_engine(engine, golden):
         # (a crossfaded head is w0 * new + w1 * old of two signals clamped to 0.99: Hamming halves sum to at most 1.08)
         assert all(bool(torch.isfinite(c).all()) and float(c.abs().max()) <= 0.99 * 1.09 for c in chunks[u])
         assert u not in t2w.hift_cache_dict
+
+
+# ======================================================================================================================
+# round 2: stage-wise streaming parity, long sequences, encoder slot, concurrency, fp16 headroom
+# ======================================================================================================================
+def test_streaming_stage_wise_against_reference(engine, golden):
+    """Every stage of every chunk of a streaming session against what the UNMODIFIED reference computed at that stage
+    (tests/golden/stream_stages.npz, recorded inside CosyVoice2Model.token2wav by oracle/make_golden_r2.py):
+      flow mel of the chunk call (streaming masks for non-final chunks, full attention for the final one)  <= 1e-2
+      hift.inference(reference mel + 8 cached frames, cache_source = reference source tail, same noise)     >= 35 dB
+        ... and the cache_source overwrite of the source head (generator.py:578-580) is a bit-exact copy
+      cv2_crossfade(reference speech, reference cached tail) vs fade_in_out (common.py:142-150)            <= 1e-6
+      hift + crossfade chained vs the reference's post-crossfade speech                                     >= 35 dB"""
+    flow, hift, t2w = engine
+    g = golden("stream_stages")
+    seed = int(g["seed"])
+    u = _utt(g)
+    sched = [(int(a), int(b), bool(c)) for a, b, c in g["schedule"]]
+    assert len(sched) >= 3
+    for ci, (n_vis, off, fin) in enumerate(sched):
+        mel, _ = flow.inference(u["token"][:, :n_vis], None, u["prompt_token"], None, u["prompt_feat"], None, u["embedding"], not fin, fin)
+        ref_mel = g[f"flow_mel{ci}"]
+        assert tuple(mel.shape) == ref_mel.shape
+        mel_err = np.abs(mel.cpu().numpy() - ref_mel).max()
+        hm = T(g[f"hift_mel{ci}"])
+        cs = T(g[f"cache_source{ci}"])
+        noise = T(weights.make_nsf_noise(hm.shape[2] * 480, seed * 100 + ci))
+        speech, source = hift.inference(hm, cache_source=cs, noise=noise)
+        s_pre = snr_db(g[f"speech_pre{ci}"], speech.cpu().numpy())
+        s_src = snr_db(g[f"source{ci}"], source.cpu().numpy())
+        msg = f"chunk {ci}: mel err {mel_err:.2e}, hift SNR {s_pre:.1f} dB, source SNR {s_src:.1f} dB"
+        assert mel_err <= MEL_TOL, msg
+        assert s_pre >= SNR_MIN and s_src >= 45.0, msg
+        if ci > 0:
+            n = cs.shape[2]
+            assert n == 3840
+            assert torch.equal(source[:, :, :n].cpu(), cs)                      # overwrite = exact copy
+            old = T(g[f"fade_old{ci}"])
+            only = t2w._fade_in_out(T(g[f"speech_pre{ci}"]).cuda().clone(), old.cuda())
+            fade_err = np.abs(only.cpu().numpy() - g[f"speech_post{ci}"]).max()
+            chained = t2w._fade_in_out(speech.clone(), old.cuda())
+            s_post = snr_db(g[f"speech_post{ci}"], chained.cpu().numpy())
+            msg += f", crossfade err {fade_err:.2e}, post-crossfade SNR {s_post:.1f} dB"
+            assert fade_err <= 1e-6, msg
+            assert s_post >= SNR_MIN, msg
+        print(msg)
+
+
+def test_streaming_session_end_to_end_shapes_and_snr(engine, golden):
+    """The same session through token2wav itself (flow -> slice -> cache concat -> hift -> crossfade -> cache update): chunk
+    shapes bit-exact; the waveform SNR is reported per chunk and loosely gated (end to end it is governed by F0 -> phase
+    drift of the <= 1e-2 mel error; the stage-wise test above is the tight gate)."""
+    t2w = engine[2]
+    g = golden("stream_stages")
+    seed = int(g["seed"])
+    u = _utt(g)
+    t2w.hift_cache_dict["e2e"] = None
+    for ci, (n_vis, off, fin) in enumerate([(int(a), int(b), bool(c)) for a, b, c in g["schedule"]]):
+        noise = T(weights.make_nsf_noise(g[f"hift_mel{ci}"].shape[2] * 480, seed * 100 + ci))
+        w = t2w.token2wav(u["token"][:, :n_vis], u["prompt_token"], u["prompt_feat"], u["embedding"], token_offset=off, uuid="e2e",
+                          stream=not fin, finalize=fin, noise=noise)
+        ref = g[f"out{ci}"]
+        assert tuple(w.shape) == ref.shape
+        s = snr_db(ref, w.cpu().numpy())
+        print("stream chunk", ci, "e2e SNR", s)
+        assert np.isfinite(s) and s > 3.0
+        if not fin:      # the cache the reference keeps has the same shapes
+            c = t2w.hift_cache_dict["e2e"]
+            assert tuple(c["mel"].shape) == (1, 80, 8) and tuple(c["source"].shape) == (1, 1, 3840) and tuple(c["speech"].shape) == (1, 3840)
+
+
+@pytest.mark.parametrize("case", ["cfg2", "max"])
+def test_long_sequences_against_reference_with_2sm_kernels(engine, golden, case):
+    """BASELINE configs[1] (250 tokens, T = 650) and the longest utterance of configs[2] (500 tokens, T = 1150: 9 query tiles)
+    against the reference's own mel / waveform (tests/golden/long.npz), run INSIDE a batch large enough that the 2-SM
+    (tcgen05 cta_group::2) GEMM and FFN kernels and several persistent rounds are what computes it."""
+    flow, hift, _ = engine
+    g = golden("long")
+    n_tok, n_prompt, seed = int(g[f"{case}_n_tok"]), int(g[f"{case}_n_prompt"]), int(g[f"{case}_seed"])
+    target = _utt(dict(n_tok=n_tok, n_prompt=n_prompt, seed=seed))
+    others = [_utt(dict(n_tok=n, n_prompt=75, seed=300 + i)) for i, n in enumerate([310, 355, 402, 428, 447, 466, 481, 490, 496, 499, 500])]
+    utts = others[:5] + [target] + others[5:]
+    args = ([u["token"][0] for u in utts], [u["prompt_token"][0] for u in utts], [u["prompt_feat"][0] for u in utts],
+            [u["embedding"][0] for u in utts])
+    S, tiles = 2 * len(utts), -(-2 * (500 + 75) // 128)
+    assert S * tiles >= 148                                   # the 2-SM paths are on for this launch shape
+    mel_b, lens = flow.inference_batch(*args)
+    k = 5
+    assert int(lens[k]) == 2 * n_tok
+    mel = mel_b[k:k + 1, :, :2 * n_tok]
+    err = np.abs(mel.cpu().numpy() - g[f"{case}_mel"]).max()
+    noise = T(weights.make_nsf_noise(2 * n_tok * 480, seed))
+    speech, _, f0 = hift.inference(T(g[f"{case}_mel"]), noise=noise, return_f0=True)
+    s = snr_db(g[f"{case}_wav"], speech.cpu().numpy())
+    f0_err = np.abs(f0.cpu().numpy() - g[f"{case}_f0"]).max()
+    print(case, "T =", 2 * (n_tok + n_prompt), "mel max-abs err", err, "f0 err", f0_err, "hift SNR", s)
+    assert err <= MEL_TOL
+    assert f0_err < 5e-2
+    assert s >= SNR_MIN
+    # and alone (B = 1: the 1-SM kernels) it is the same utterance
+    mel_1, _ = flow.inference(target["token"], None, target["prompt_token"], None, target["prompt_feat"], None, target["embedding"], False, True)
+    assert np.abs(mel_1.cpu().numpy() - g[f"{case}_mel"]).max() <= MEL_TOL
+    assert float((mel_1 - mel).abs().max()) < 2e-3
+
+
+def test_forced_2sm_kernels_on_a_single_utterance(engine, golden):
+    """option min_2sm_tiles = 0: one 8 s utterance (S = 2 CFG rows, 5 tiles each) computed by the 2-SM kernels alone, against
+    the reference mel."""
+    flow = engine[0]
+    g = golden("cfg1")
+    u = _utt(g)
+    lib = flow.eng.lib
+    assert lib.cv2_engine_set_option(flow.eng.h, b"min_2sm_tiles", 0) == 0
+    try:
+        mel, _ = flow.inference(u["token"], None, u["prompt_token"], None, u["prompt_feat"], None, u["embedding"], False, True)
+    finally:
+        lib.cv2_engine_set_option(flow.eng.h, b"min_2sm_tiles", 148)
+    err = np.abs(mel.cpu().numpy() - g["mel"]).max()
+    print("cfg1 with 2-SM kernels forced: mel max-abs err", err)
+    assert err <= MEL_TOL
+
+
+def test_encoder_slot_matches_oracle_encoder(engine, fixture_weights, golden):
+    """Boundary #5: B200Flow.encoder(xs, xs_lens, context=, streaming=) == UpsampleConformerEncoder.forward
+    (upsample_encoder.py:243-306) on the embeddings flow.inference hands it (flow.py:253-263), offline and as a non-final
+    streaming chunk with the 3-token look-ahead context; plus the golden encoder_out of the reference itself."""
+    import token2wav_oracle as O
+    flow = engine[0]
+    fs = fixture_weights[0]
+    g = golden("tiny")
+    u = _utt(g)
+    tok = torch.cat([u["prompt_token"], u["token"]], 1).long()
+    emb = torch.nn.functional.embedding(torch.clamp(tok, min=0), fs["input_embedding.weight"])
+    n = tok.shape[1]
+    assert flow.encoder.output_size() == 512
+    h, masks = flow.encoder(emb, torch.tensor([n], dtype=torch.int32), streaming=False)
+    assert tuple(h.shape) == (1, 2 * n, 512) and tuple(masks.shape) == (1, 1, 2 * n) and bool(masks.all())
+    err = np.abs(h.cpu().numpy() - g["encoder_out"]).max()
+    print("encoder slot vs reference encoder_out: max-abs", err)
+    assert err < 2e-2
+    # non-final chunk: the caller splits off the look-ahead tokens and still passes the full token_len (flow.py:262-263)
+    with torch.inference_mode():
+        ref = O.encoder_forward(O._sub(fs, "encoder."), emb[:, :-3], torch.tensor([n]), context=emb[:, -3:], streaming=True)
+    h2, m2 = flow.encoder(emb[:, :-3], torch.tensor([n], dtype=torch.int32), context=emb[:, -3:], streaming=True)
+    assert tuple(h2.shape) == tuple(ref.shape) == (1, 2 * (n - 3), 512) and bool(m2.all())
+    err2 = float((h2.cpu() - ref).abs().max())
+    print("encoder slot (streaming, context) vs oracle: max-abs", err2)
+    assert err2 < 2e-2
+    # ragged batch of two: each row equals its own B = 1 call on the valid rows
+    emb_b = torch.zeros(2, n, 512)
+    emb_b[0] = emb[0]
+    emb_b[1, :n - 9] = emb[0, :n - 9]
+    hb, mb = flow.encoder(emb_b, torch.tensor([n, n - 9], dtype=torch.int32))
+    h1, _ = flow.encoder(emb[:, :n - 9], torch.tensor([n - 9], dtype=torch.int32))
+    assert mb[1, 0].sum().item() == 2 * (n - 9)
+    assert float((hb[1, :2 * (n - 9)] - h1[0]).abs().max()) < 1e-4
+    assert float((hb[0] - h[0]).abs().max()) < 1e-4
+
+
+def test_concurrent_token2wav_threads_equal_sequential(engine, golden):
+    """Boundary #1 under the reference's serving pattern (runtime/python/grpc/server.py:75: ThreadPoolExecutor; one uuid per
+    request): 8 threads x different uuids through token2wav(stream=True) chunk by chunk == the same sessions run one after
+    the other.  NSF noise is injected so that the comparison is exact up to run-to-run determinism."""
+    import concurrent.futures as cf
+    from cosyvoice2_eu_b200 import B200Token2Wav
+    from cosyvoice2_eu_b200.scheduler import chunk_schedule
+    flow, hift, _ = engine
+    specs = [(70, 10, 3), (95, 25, 8), (55, 12, 9), (64, 10, 21), (31, 0, 22), (90, 25, 23), (43, 10, 24), (120, 60, 25)]
+    utts = [_utt(dict(n_tok=n, n_prompt=p, seed=s)) for n, p, s in specs]
+
+    def run_session(t2w, si):
+        n, p, _ = specs[si]
+        u = utts[si]
+        uuid = f"thr{si}"
+        with t2w.lock:
+            t2w.hift_cache_dict[uuid] = None
+        chunks = []
+        for ci, (n_vis, off, fin) in enumerate(chunk_schedule(n, p)):
+            n_new = (n_vis - (0 if fin else 3)) * 2 - off * 2
+            mel_len = n_new + (8 if t2w.hift_cache_dict[uuid] is not None else 0)
+            noise = T(weights.make_nsf_noise(mel_len * 480, 1000 * si + ci))
+            chunks.append(t2w.token2wav(u["token"][:, :n_vis], u["prompt_token"], u["prompt_feat"], u["embedding"], off, uuid,
+                                        stream=not fin, finalize=fin, noise=noise).cpu())
+        with t2w.lock:
+            t2w.hift_cache_dict.pop(uuid)
+        return chunks
+
+    seq = B200Token2Wav(flow, hift)
+    want = [run_session(seq, si) for si in range(len(specs))]
+    par = B200Token2Wav(flow, hift)
+    for _ in range(2):                                           # twice: different interleavings
+        with cf.ThreadPoolExecutor(max_workers=8) as ex:
+            got = list(ex.map(lambda si: run_session(par, si), range(len(specs))))
+        for si in range(len(specs)):
+            assert len(got[si]) == len(want[si])
+            for a, b in zip(got[si], want[si]):
+                assert a.shape == b.shape
+                assert snr_db(b.numpy(), a.numpy()) > 60, (si, float((a - b).abs().max()))     # a race gives garbage, not rounding noise
+    assert not par.hift_cache_dict
+
+
+def test_fp16_range_telemetry_on_the_fixture(engine, golden):
+    """The MMA operands are fp16 (max 65504): the opt-in range check reports the largest |x| written to every class of 16-bit
+    tensor (q, k, v, attention output, GEMM / FFN emits, vocoder emits incl. Snake outputs) so that a trained checkpoint can be
+    checked for headroom.  On the fixture (flow + hift of configs[0]) every class stays below 1/16 of the fp16 range."""
+    import ctypes as C
+    flow, hift, _ = engine
+    g = golden("cfg1")
+    u = _utt(g)
+    lib = flow.eng.lib
+    assert lib.cv2_engine_set_option(flow.eng.h, b"range_check", 1) == 0
+    try:
+        mel, _ = flow.inference(u["token"], None, u["prompt_token"], None, u["prompt_feat"], None, u["embedding"], False, True)
+        hift.inference(T(g["mel"]))
+        out = (C.c_float * 7)()
+        assert lib.cv2_engine_read_ranges(flow.eng.h, out, 7) == 0
+    finally:
+        lib.cv2_engine_set_option(flow.eng.h, b"range_check", 0)
+    names = ["gemm_emit", "q", "k", "v", "attn_out", "ffn_emit", "hift_emit"]
+    vals = dict(zip(names, list(out)))
+    print("fp16 max-abs per class:", vals)
+    for k, v in vals.items():
+        assert np.isfinite(v) and 0.0 < v < 65504.0 / 16, (k, v)
+    assert np.abs(mel.cpu().numpy() - g["mel"]).max() <= MEL_TOL        # telemetry does not disturb the result
+
+
+def test_out_of_range_token_id_is_rejected_like_nn_embedding(engine):
+    """flow.py:256-257: negative ids are clamped to 0, ids >= vocab make nn.Embedding raise IndexError -- same here."""
+    flow = engine[0]
+    u = _utt(dict(n_tok=12, n_prompt=4, seed=31))
+    bad = u["token"].clone()
+    bad[0, 5] = 6561
+    with pytest.raises(IndexError):
+        flow.inference(bad, None, u["prompt_token"], None, u["prompt_feat"], None, u["embedding"], False, True)
+    neg = u["token"].clone()
+    neg[0, 5] = -7
+    zero = u["token"].clone()
+    zero[0, 5] = 0
+    a, _ = flow.inference(neg, None, u["prompt_token"], None, u["prompt_feat"], None, u["embedding"], False, True)
+    b, _ = flow.inference(zero, None, u["prompt_token"], None, u["prompt_feat"], None, u["embedding"], False, True)
+    assert torch.equal(a, b)
+
+
+def test_workspaces_do_not_accumulate_across_shapes(engine):
+    """A long-running server sees a new shape on every streaming chunk: the host keeps ONE grow-only workspace per
+    (kind, stream) and ONE pinned staging buffer per (input, stream), and results do not depend on what ran before."""
+    flow, hift, _ = engine
+    eng = flow.eng
+    u_small = _utt(dict(n_tok=20, n_prompt=6, seed=51))
+    u_big = _utt(dict(n_tok=180, n_prompt=40, seed=52))
+    call = lambda u: flow.inference(u["token"], None, u["prompt_token"], None, u["prompt_feat"], None, u["embedding"], False, True)[0].cpu()
+    first = call(u_small)
+    call(u_big)
+    for n in (33, 47, 61, 90):
+        call(_utt(dict(n_tok=n, n_prompt=10, seed=n)))
+    again = call(u_small)                       # same layout as the first call, workspace full of other calls' data
+    assert torch.equal(first, again)
+    kinds = [k[0] for k in eng.ws]
+    assert len(kinds) == len(set((k[0], k[1]) for k in eng.ws))
+    assert sum(1 for k in eng.ws if k[0] == "flow") <= 2          # default stream (+ a graph-capture side stream at most)
+    assert sum(1 for k in eng.pinned if k[0] == "tok") <= 2

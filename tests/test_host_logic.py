@@ -102,6 +102,7 @@ def test_stream_scheduler_reproduces_the_reference_chunk_schedule():
         left[u] = list(range(n))
         assert t2w.hift_cache_dict[u] is None
     delivered = []
+    ended_at_first = {}
     while sch.sessions:
         for u in list(left):
             k = int(rng.integers(0, 40))
@@ -112,15 +113,45 @@ def test_stream_scheduler_reproduces_the_reference_chunk_schedule():
                 sch.close(u)
                 del left[u]
         while sch.pending():
+            for u, s in sch.sessions.items():     # was the producer done when the first chunk went out? (model.py:369, stale hop)
+                if s.token_offset == 0 and sch._ready(s):
+                    ended_at_first[u] = s.ended
             delivered.extend(sch.step())
     got = _per_session(t2w.calls)
     for u, (n, p) in specs.items():
-        assert got[u] == O.stream_schedule(n, p), u
+        assert got[u] == O.stream_schedule(n, p, all_tokens_ready=ended_at_first.get(u, False)), u
         assert u not in t2w.hift_cache_dict                          # dropped after the final chunk (model.py:395-396)
     assert [d[2] for d in delivered if d[0] == "a"] == [False] * (len(got["a"]) - 1) + [True]
     assert any(len(reqs) > 1 for _, reqs in t2w.calls)                # concurrent sessions were batched
     for fin, reqs in t2w.calls:
         assert len({r[0] for r in reqs}) == len(reqs)                # a session appears at most once per call
+
+
+def test_schedules_match_the_references_own_tts_loop(golden):
+    """tests/golden/tts_schedule.npz = the token2wav calls made by the reference's CosyVoice2Model.tts(stream=True) itself with all
+    tokens present from the start (vc_job): the oracle restatement, the host helper and the StreamScheduler fed the same way
+    must make exactly those calls (including the early finalization caused by the stale hop in the break test, model.py:369)."""
+    import torch
+    from cosyvoice2_eu_b200 import StreamScheduler
+    from cosyvoice2_eu_b200.scheduler import chunk_schedule
+    g = golden("tts_schedule")
+    assert len(g) >= 10
+    for key, ref in g.items():
+        n, p = map(int, key.split("_"))
+        want = [(int(a), int(b), bool(c)) for a, b, c in ref.tolist()]
+        assert O.stream_schedule(n, p, all_tokens_ready=True) == want, key
+        assert chunk_schedule(n, p, all_tokens_ready=True) == want, key
+        assert chunk_schedule(n, p) == O.stream_schedule(n, p), key
+        t2w = _StubT2W()
+        sch = StreamScheduler(t2w, token_hop_len=25)
+        sch.open("u", torch.zeros(1, p, dtype=torch.int32), torch.zeros(1, 2 * p, 80), torch.zeros(1, 192))
+        sch.push("u", list(range(n)))
+        sch.close("u")
+        while sch.pending():
+            sch.step()
+        assert _per_session(t2w.calls)["u"] == want, key
+    # the (70, 10) session differs between the two arrival patterns: that is the case the stale hop decides
+    assert O.stream_schedule(70, 10) != O.stream_schedule(70, 10, all_tokens_ready=True)
 
 
 def test_stream_scheduler_is_event_driven_across_threads():

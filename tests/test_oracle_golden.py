@@ -82,3 +82,39 @@ def test_streaming_token2wav(golden, fixture_weights):
         ref = g[f"chunk{ci}"]
         assert w.shape == ref.shape            # shapes bit-exact
         assert snr_db(ref, w.numpy()) > 40
+
+
+def test_streaming_stages_pin_the_oracle(golden, fixture_weights):
+    """Stage-wise pin of the oracle's streaming pieces against the reference's own intermediate values
+    (tests/golden/stream_stages.npz): per-chunk flow mel, hift with the cache_source overwrite, fade_in_out."""
+    g = golden("stream_stages")
+    fs, hs = fixture_weights
+    seed = int(g["seed"])
+    u = weights.make_utterance(int(g["n_tok"]), int(g["n_prompt"]), seed)
+    window = np.hamming(2 * 3840)
+    with torch.inference_mode():
+        for ci, (n_vis, off, fin) in enumerate(g["schedule"]):
+            mel = O.flow_inference(fs, weights.cfm_rand_noise(), T(u["token"][:, :n_vis]), T(u["prompt_token"]), T(u["prompt_feat"]),
+                                   T(u["embedding"]), streaming=not bool(fin), finalize=bool(fin))
+            assert np.abs(mel.numpy() - g[f"flow_mel{ci}"]).max() < 1e-4
+            hm, cs = T(g[f"hift_mel{ci}"]), T(g[f"cache_source{ci}"])
+            noise = T(weights.make_nsf_noise(hm.shape[2] * 480, seed * 100 + ci))
+            speech, source = O.hift_inference(hs, hm, cs, noise)
+            assert snr_db(g[f"speech_pre{ci}"], speech.numpy()) > 50
+            assert snr_db(g[f"source{ci}"], source.numpy()) > 60
+            if ci > 0:
+                assert torch.equal(source[:, :, :3840], cs)
+                post = O.fade_in_out(T(g[f"speech_pre{ci}"]), T(g[f"fade_old{ci}"]), window)
+                assert np.array_equal(post.numpy(), g[f"speech_post{ci}"])          # same float64 window maths: bit-exact
+
+
+def test_long_hift_pins_the_oracle(golden, fixture_weights):
+    """configs[1] length (500 mel frames): oracle vocoder on the reference mel vs the reference waveform (the 650 / 1150-frame
+    flow passes are compared on the GPU side only -- they cost the CPU suite half a minute each)."""
+    g = golden("long")
+    hs = fixture_weights[1]
+    noise = T(weights.make_nsf_noise(g["cfg2_mel"].shape[2] * 480, int(g["cfg2_seed"])))
+    with torch.inference_mode():
+        wav, _, hi = O.hift_inference(hs, T(g["cfg2_mel"]), None, noise, return_intermediates=True)
+    assert np.abs(hi["f0"].numpy() - g["cfg2_f0"]).max() < 1e-2
+    assert snr_db(g["cfg2_wav"], wav.numpy()) > 50
