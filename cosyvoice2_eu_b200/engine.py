@@ -94,7 +94,8 @@ class _Engine:
         key = (kind, torch.cuda.current_stream(self.device).cuda_stream)
         ent = self.ws.get(key)
         if ent is None or ent[0].numel() < nbytes:
-            ent = [torch.zeros(int(nbytes), dtype=torch.uint8, device=self.device), layout]
+            with torch.inference_mode(False):     # a normal tensor: it is zeroed in place later, from any mode
+                ent = [torch.zeros(int(nbytes), dtype=torch.uint8, device=self.device), layout]
             self.ws[key] = ent
         elif ent[1] != layout:
             ent[0][:int(nbytes)].zero_()
@@ -108,7 +109,8 @@ class _Engine:
         n = int(np.prod(shape)) if len(shape) else 1
         ent = self.pinned.get(key)
         if ent is None or ent[0].numel() < n or ent[0].dtype != dtype:
-            ent = [torch.zeros(max(n, 1), dtype=dtype).pin_memory(), None]
+            with torch.inference_mode(False):     # a normal tensor: it is refilled in place by later calls, from any mode
+                ent = [torch.zeros(max(n, 1), dtype=dtype).pin_memory(), None]
             self.pinned[key] = ent
         else:
             if ent[1] is not None:
