@@ -537,7 +537,7 @@ def side_legs(args, t2w, flow, hift, dev, peaks, clk, chunk_schedule, weights):
     sess = [{k: torch.from_numpy(v) for k, v in u.items()} for u in sess]
     sched = chunk_schedule(n_tok_s, N_PROMPT)
 
-    def run_streams():
+    def run_streams(group):
         for i in range(n_sess):
             t2w.hift_cache_dict[f"bench{i}"] = None
         lat, total = [], 0
@@ -545,16 +545,27 @@ def side_legs(args, t2w, flow, hift, dev, peaks, clk, chunk_schedule, weights):
             t0 = time.perf_counter()
             reqs = [dict(token=u["token"][:, :n_vis], prompt_token=u["prompt_token"], prompt_feat=u["prompt_feat"],
                          embedding=u["embedding"], token_offset=off, uuid=f"bench{i}") for i, u in enumerate(sess)]
-            outs = t2w.token2wav_stream_batch(reqs, finalize=fin)
+            outs = t2w.token2wav_stream_batch(reqs, finalize=fin, group=group)
             host = [o.cpu() for o in outs]
             lat.append(time.perf_counter() - t0)
             total += sum(o.shape[1] for o in host)
         return lat, total
-    run_streams()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    lat_s, total_samples = run_streams()
-    t_stream = time.perf_counter() - t0
+
+    def timed_streams(group):
+        run_streams(group)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lat, total = run_streams(group)
+        return lat, total, time.perf_counter() - t0
+    # the reference's schedule as it stands (every chunk recomputes the whole prefix), then the same chunks computed
+    # incrementally on a StreamGroup (k / v^T + causal-conv state of earlier frames stay on the device, row F1)
+    lat_p, total_p, t_prefix = timed_streams(None)
+    T_need = 2 * (N_PROMPT + max(nv for nv, _, fin in sched if not fin) - 3) if len(sched) > 1 else 128
+    group = flow.open_stream_group(n_sess, max_mel_frames=T_need)
+    lat_s, total_samples, t_stream = timed_streams(group)
+    state_gb = group.state.numel() / 1e9
+    del group
+    torch.cuda.empty_cache()
     # algorithmic FLOPs of a session in the INCREMENTAL unit: every frame of the non-final chunks computed once
     # with the block-causal attention term, plus the full final pass
     def est_flops(T, causal):
@@ -564,9 +575,15 @@ def side_legs(args, t2w, flow, hift, dev, peaks, clk, chunk_schedule, weights):
     T_final = 2 * (N_PROMPT + n_tok_s)
     fl_sess = est_flops(T_last_nonfinal, True) + est_flops(T_final, False) + 612.3e6 * 2 * n_tok_s
     out["stream32"] = {"workload": "BASELINE configs[3]: 32 concurrent sessions x 250 tokens (10 s), hop 25, chunk schedule of "
-                                   "CosyVoice2Model.tts, every step = one ragged batch over all sessions, chunks copied to the host",
+                                   "CosyVoice2Model.tts, every step = one ragged batch over all sessions, chunks copied to the host; "
+                                   "non-final chunks incremental on a StreamGroup, final chunk = the reference's full-attention pass",
                        "audio_s_per_s": total_samples / 24000.0 / t_stream, "chunks": len(sched),
                        "chunk_latency_s_median": float(np.median(lat_s)), "first_chunk_latency_s": lat_s[0], "wall_s": t_stream,
+                       "chunk_latency_s": [round(x, 5) for x in lat_s], "stream_state_gb": state_gb,
+                       "prefix_recompute": {"audio_s_per_s": total_p / 24000.0 / t_prefix, "wall_s": t_prefix,
+                                            "chunk_latency_s_median": float(np.median(lat_p)), "first_chunk_latency_s": lat_p[0],
+                                            "note": "same sessions with every chunk recomputing the prefix (the reference's schedule "
+                                                    "as it stands, model.py:351-381)"},
                        "roofline": {"bound": "tensor", "unit": "TFLOP/s", "algorithmic_tflop": n_sess * fl_sess / 1e12,
                                     "achieved": n_sess * fl_sess / 1e12 / t_stream, "peak": peak_burst,
                                     "frac": n_sess * fl_sess / 1e12 / t_stream / peak_burst,

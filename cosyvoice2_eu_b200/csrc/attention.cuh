@@ -16,6 +16,7 @@ struct AttnParams {
   int chunk;         // 0: every valid key visible; >0: key j visible to query i iff j < (i/chunk+1)*chunk
   int halo;
   int reverse_seq;   // dispatch sequences S-1 .. 0 (longest first for an ascending length-sorted batch)
+  const int* lo;     // optional [S]: query tiles with t0 < floor(lo[s] / 128) * 128 are skipped (incremental streaming)
 };
 void launch_flash_attn(const AttnParams& p, cudaStream_t stream);
 

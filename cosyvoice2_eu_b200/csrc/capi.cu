@@ -257,6 +257,74 @@ int cv2_flow_forward(cv2_engine* h, void* stream, const int32_t* token, int toke
   CV2_API_END
 }
 
+size_t cv2_stream_state_bytes(int n_slots, int T_cap, int n_steps) {
+  try {
+    return stream_state_bytes(n_slots, T_cap, n_steps);
+  } catch (const std::exception& ex) {
+    last_error_ref() = ex.what();
+    return 0;
+  }
+}
+
+int cv2_stream_state_reset_slot(void* stream, void* state, size_t state_bytes, int n_slots, int T_cap, int n_steps, int slot) {
+  CV2_API_BEGIN
+  StreamState ss = stream_state_carve(state, state_bytes, n_slots, T_cap, n_steps);
+  CV2_CHECK(slot >= 0 && slot < n_slots, "slot %d out of range", slot);
+  CV2_CUDA(cudaMemsetAsync(ss.t_done + slot, 0, sizeof(int), (cudaStream_t)stream));
+  CV2_API_END
+}
+
+size_t cv2_flow_stream_workspace_bytes(cv2_engine* h, int n_slots, int T_cap, int n_steps) {
+  try {
+    Arena ws;
+    StreamState ss;
+    memset(&ss, 0, sizeof(ss));
+    ss.n_slots = n_slots; ss.T_cap = T_cap; ss.n_steps = n_steps;
+    CV2_CHECK(T_cap >= 128 && T_cap % 128 == 0, "T_cap must be a multiple of 128");
+    FlowArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = n_slots; a.max_tok_total = T_cap / 2 + 3; a.n_steps = n_steps; a.streaming = 1; a.stream_state = &ss;
+    return flow_forward(h->e, nullptr, a, ws) + 4096;
+  } catch (const std::exception& ex) {
+    last_error_ref() = ex.what();
+    return 0;
+  }
+}
+
+int cv2_flow_forward_stream(cv2_engine* h, void* stream, const int32_t* token, int token_stride, const int32_t* token_len,
+                            const int32_t* prompt_token, int prompt_stride, const int32_t* prompt_len, const float* prompt_feat,
+                            long long prompt_feat_bstride, const int32_t* prompt_feat_len, const float* embedding,
+                            const float* rand_noise, int noise_stride, int n_slots, int max_tok_total, const float* t_steps_dev,
+                            const float* dt_steps_host, int n_steps, float cfg_rate, float* mel_out, int mel_out_T, void* state,
+                            size_t state_bytes, int T_cap, void* workspace, size_t workspace_bytes) {
+  CV2_API_BEGIN
+  CV2_CHECK(h && h->e.has_flow, "engine not finalized for flow");
+  CV2_CHECK(token && token_len && prompt_token && prompt_len && prompt_feat && prompt_feat_len && embedding && rand_noise &&
+                t_steps_dev && dt_steps_host && mel_out && workspace && state,
+            "null argument");
+  CV2_CHECK(n_slots >= 1 && max_tok_total >= 4 && n_steps >= 1, "bad sizes");
+  CV2_CHECK(2 * max_tok_total <= noise_stride, "sequence of %d mel frames exceeds the CFM noise buffer (%d)", 2 * max_tok_total,
+            noise_stride);
+  use_device(h);
+  StreamState ss = stream_state_carve(state, state_bytes, n_slots, T_cap, n_steps);
+  Arena ws;
+  ws.base = static_cast<uint8_t*>(workspace);
+  ws.cap = workspace_bytes;
+  FlowArgs a;
+  memset(&a, 0, sizeof(a));
+  a.token = token; a.token_stride = token_stride; a.token_len = token_len;
+  a.prompt_token = prompt_token; a.prompt_stride = prompt_stride; a.prompt_len = prompt_len;
+  a.prompt_feat = prompt_feat; a.prompt_feat_bstride = prompt_feat_bstride; a.prompt_feat_len = prompt_feat_len;
+  a.embedding = embedding; a.rand_noise = rand_noise; a.noise_stride = noise_stride;
+  a.B = n_slots; a.max_tok_total = max_tok_total; a.streaming = 1; a.finalize = 0;
+  a.t_steps = t_steps_dev; a.dt_steps = dt_steps_host; a.n_steps = n_steps; a.cfg = cfg_rate;
+  a.mel_out = mel_out; a.mel_out_T = mel_out_T;
+  a.stream_state = &ss;
+  h->e.launches = 0;
+  flow_forward(h->e, (cudaStream_t)stream, a, ws);
+  CV2_API_END
+}
+
 size_t cv2_encoder_workspace_bytes(cv2_engine* h, int B, int T, int with_context) {
   try {
     Arena ws;

@@ -103,7 +103,7 @@ struct Engine {
   }
   // builds the list for `lens` (S sequences) and registers it under lens and every alias pointer (same or shorter lengths)
   void make_tile_list(cudaStream_t st, Arena& ws, const int* lens, int S, int T_alloc, int halo, bool dry,
-                      const int* alias0 = nullptr, const int* alias1 = nullptr);
+                      const int* alias0 = nullptr, const int* alias1 = nullptr, const int* lo = nullptr);
 
   // ---- optional per-launch timing (CUDA events on the launching stream), grouped by kernel family ----
   enum Family { F_GEMM64 = 0, F_GEMM128, F_GEMM256, F_FLASH_ATTN, F_REL_ATTN, F_F0_CONV, F_NSF, F_STFT, F_SRC_DOWN, F_ISTFT,
@@ -156,6 +156,7 @@ struct Engine {
 };
 
 // forward passes (engine_flow.cu / engine_hift.cu)
+struct StreamState;
 struct FlowArgs {
   const int* token; int token_stride; const int* token_len;
   const int* prompt_token; int prompt_stride; const int* prompt_len;
@@ -180,8 +181,30 @@ struct FlowArgs {
   int enc_T;
   const int* enc_lens;          // [B] valid rows of enc_xs (values above enc_T are clamped, like make_pad_mask(xs_lens, T))
   const float* enc_ctx;         // [B, 3, 512] look-ahead context (flow.py:262-263) or null
+  const StreamState* stream_state;   // non-null: incremental non-final streaming chunk over the state's slots (B == n_slots)
 };
 size_t flow_forward(Engine& e, cudaStream_t st, const FlowArgs& a, Arena& ws);
+
+// ---- incremental streaming state of the CFM estimator for a group of `n_slots` concurrent sessions ----
+// A non-final streaming chunk runs the estimator with block-causal attention (chunk 50) and causal convolutions only, so every
+// mel row it produced is final.  The state keeps, per Euler step and transformer block, the k / v^T of all rows computed so far,
+// and per Euler step and causal conv the two input rows in front of every 128-row tile boundary; the next chunk then computes
+// the row tiles from floor(t_done / 128) * 128 on, instead of the whole prefix (what the reference does, model.py:351-381).
+// Caller-owned, zero-initialised device memory of stream_state_bytes().
+struct StreamState {
+  int n_slots, T_cap, n_steps;
+  int* t_done;        // [n_slots] mel rows already final per slot (0 = fresh session)
+  __half* kcache;     // [n_steps][56][2*n_slots][8][T_cap][64]
+  __half* vcache;     // [n_steps][56][2*n_slots][8][64][T_cap]
+  __half* tails;      // [n_steps][31 convs][2*n_slots][T_cap/128 boundaries][2 rows][512]
+  size_t kv_block() const { return (size_t)2 * n_slots * 8 * T_cap * 64; }
+  size_t tail_block() const { return (size_t)2 * n_slots * (T_cap / 128) * 2 * 512; }
+};
+static const int kEstConvs = 31, kEstBlocks = 56;
+size_t stream_state_bytes(int n_slots, int T_cap, int n_steps);
+StreamState stream_state_carve(void* base, size_t bytes, int n_slots, int T_cap, int n_steps);
+// flow_forward with FlowArgs::stream_state set: a.B must equal n_slots (inactive slots: token_len = 0); mel_out rows in front of
+// the rows that are new in this call are unspecified
 
 struct EstArgs {
   const float* x; const float* mask; const float* mu; const float* t; const float* spks; const float* cond;

@@ -33,12 +33,12 @@ static inline uint64_t mix(uint64_t h, uint64_t v) {
 }
 
 void Engine::make_tile_list(cudaStream_t st, Arena& ws, const int* lens, int S, int T_alloc, int halo, bool dry,
-                            const int* alias0, const int* alias1) {
+                            const int* alias0, const int* alias1, const int* lo) {
   int* list = ws.get<int>((size_t)2 * S * (T_alloc / 128));
   int* count = ws.get<int>(1);
   launches++;
   if (dry) return;
-  launch_build_tile_list(lens, S, T_alloc, halo, list, count, st);
+  launch_build_tile_list(lens, S, T_alloc, halo, list, count, st, lo);
   TileList tl{list, count};
   tile_lists[tl_key(lens, T_alloc, S)] = tl;
   if (alias0) tile_lists[tl_key(alias0, T_alloc, S)] = tl;

@@ -74,11 +74,26 @@ struct EulerFuse {
   int B;
 };
 
+// Incremental streaming: the estimator call of Euler step `step` of a chunk that only computes the row tiles from t_lo on.
+struct EstStream {
+  const StreamState* ss;
+  int step;
+  const int* t_lo;     // [S] device
+};
+
 static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __half* xin16, const int* lens, int S, int T,
                      const float* temb_res, int nt, int trow, int trow_ld, int streaming, bool dry,
-                     const EulerFuse* ef = nullptr) {
+                     const EulerFuse* ef = nullptr, const EstStream* es = nullptr) {
   static const int causal3[3] = {-2, -1, 0};
   static const int tap1[1] = {0};
+  // a causal k=3 conv reads two rows in front of its first tile: with a stream state they come from / go to the tail cache
+  auto tails = [&](int conv, const __half* buf, int C, long long ld) {
+    if (!es) return;
+    e.launches++;
+    if (dry) return;
+    launch_tail_swap(const_cast<__half*>(buf), S, T, C, ld, lens, es->t_lo,
+                     es->ss->tails + ((size_t)es->step * kEstConvs + conv) * es->ss->tail_block(), st);
+  };
   const __half* cur = xin16;
   int cur_c = 320;
   long long cur_ld = 320;
@@ -87,6 +102,7 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
     if (r == 13) {  // up block: cat[x, skip]
       cur = b.CAT16; cur_c = 512; cur_ld = 512;
     }
+    tails(2 * r, cur, cur_c, cur_ld);
     // res_conv (1x1) -> R32
     {
       GemmParams p = base_params(lens, kEstHalo);
@@ -103,6 +119,7 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
       p.emit[0] = emit_plain(b.C16, 256);
       e.gemm(st, cur, S, T, cur_c, cur_ld, e.W(rp + ".c1"), 256, 3, causal3, p, dry);
     }
+    tails(2 * r + 1, b.C16, 256, 256);
     // block2: conv -> LN -> Mish -> mask -> + R32 -> X32 ; emit LN(norm1 of tfm 0) -> H16
     {
       GemmParams p = base_params(lens, kEstHalo);
@@ -117,17 +134,24 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
     }
     for (int j = 0; j < 4; j++) {
       const std::string tp = "est.tfm." + std::to_string(r) + "." + std::to_string(j);
+      __half *k16 = b.K16, *vt16 = b.VT16;
+      if (es) {   // k / v^T of this (Euler step, block) live in the stream state: earlier chunks' rows are already there
+        const size_t blk = ((size_t)es->step * kEstBlocks + r * 4 + j) * es->ss->kv_block();
+        k16 = es->ss->kcache + blk;
+        vt16 = es->ss->vcache + blk;
+      }
       {  // q,k,v (no bias); q pre-scaled by 1/sqrt(64)
         GemmParams p = base_params(lens, kEstHalo);
-        p.q = b.Q16; p.k = b.K16; p.vt = b.VT16; p.heads = 8; p.q_scale = 0.125f;
+        p.q = b.Q16; p.k = k16; p.vt = vt16; p.heads = 8; p.q_scale = 0.125f;
         e.gemm(st, b.H16, S, T, 256, 256, e.W(tp + ".qkv"), 256, 1, tap1, p, dry);
       }
       {
         AttnParams ap;
         memset(&ap, 0, sizeof(ap));
-        ap.q = b.Q16; ap.k = b.K16; ap.vt = b.VT16; ap.out = b.ATT16;
+        ap.q = b.Q16; ap.k = k16; ap.vt = vt16; ap.out = b.ATT16;
         ap.lens = lens; ap.S = S; ap.heads = 8; ap.T_alloc = T; ap.chunk = streaming ? 50 : 0; ap.halo = kEstHalo;
         ap.reverse_seq = 1;
+        ap.lo = es ? es->t_lo : nullptr;
         e.launches++;
         if (!dry) {
           e.prof_begin(st, Engine::F_FLASH_ATTN);
@@ -184,6 +208,7 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
       }
     }
     if (r == 0) {  // down_blocks.0.2 : CausalConv1d(256,256,3) on x*mask
+      tails(28, b.M16, 256, 256);
       GemmParams p = base_params(lens, kEstHalo);
       p.emit[0] = emit_plain(b.N16, 256);
       e.gemm(st, b.M16, S, T, 256, 256, e.W("est.down_conv"), 256, 3, causal3, p, dry);
@@ -192,11 +217,13 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
       cur = b.M16; cur_c = 256; cur_ld = 256;
     }
   }
+  tails(29, b.M16, 256, 256);
   {  // up_blocks.0.2
     GemmParams p = base_params(lens, kEstHalo);
     p.emit[0] = emit_plain(b.N16, 256);
     e.gemm(st, b.M16, S, T, 256, 256, e.W("est.up_conv"), 256, 3, causal3, p, dry);
   }
+  tails(30, b.N16, 256, 256);
   {  // final_block
     GemmParams p = base_params(lens, kEstHalo);
     LN ln = e.ln("est.final.ln");
@@ -338,29 +365,41 @@ size_t flow_forward(Engine& e, cudaStream_t st, const FlowArgs& a, Arena& ws) {
   const bool dry = ws.measuring();
   e.in_hift = false;
   const int B = a.B;
-  const int Tt = round_up(a.max_tok_total + 4, 128);          // token-rate rows (+ lookahead reads)
-  const int Tm = round_up(2 * a.max_tok_total, 128);          // mel-rate rows
+  const StreamState* ss = a.stream_state;
+  if (ss) {
+    CV2_CHECK(B == ss->n_slots && a.n_steps == ss->n_steps, "stream state was made for %d slots / %d steps, call has %d / %d", ss->n_slots,
+              ss->n_steps, B, a.n_steps);
+    CV2_CHECK(a.streaming && !a.finalize && !a.enc_only, "the stream state serves non-final streaming chunks only");
+    CV2_CHECK(2 * (a.max_tok_total - 3) <= ss->T_cap, "chunk of %d mel frames exceeds the stream state's capacity %d",
+              2 * (a.max_tok_total - 3), ss->T_cap);
+  }
+  // with a stream state the row strides are the state's (its k / v^T caches are laid out for T_cap rows)
+  const int Tt = ss ? round_up(ss->T_cap / 2 + 8, 128) : round_up(a.max_tok_total + 4, 128);   // token-rate rows (+ lookahead reads)
+  const int Tm = ss ? ss->T_cap : round_up(2 * a.max_tok_total, 128);                         // mel-rate rows
   static const int tap1[1] = {0};
 
   // ---- lengths on the device (no host sync) ----
   int* len_ctx = ws.get<int>(B);       // prompt + token
   int* len_enc = ws.get<int>(B);       // tokens the encoder keeps (minus the 3 lookahead tokens when not final)
   int* len_mel = ws.get<int>(2 * B);   // mel frames, duplicated for the two CFG rows
+  int* t_lo = ss ? ws.get<int>(2 * B) : nullptr;   // first row of the first tile the estimator computes, per CFG row
   e.launches += 4;
-  if (!dry && a.enc_only) {
+  if (!dry && ss) {
+    launch_stream_lens(a.prompt_len, a.token_len, ss->t_done, len_ctx, len_enc, len_mel, t_lo, B, st);
+  } else if (!dry && a.enc_only) {
     launch_lens_clamp(a.enc_lens, a.enc_T, 0, len_enc, B, st);
     launch_lens_clamp(a.enc_lens, a.enc_T, a.enc_ctx ? 3 : 0, len_ctx, B, st);
   } else if (!dry) {
     launch_lens_affine(a.prompt_len, a.token_len, 1, 0, len_ctx, B, st);
     launch_lens_affine(len_ctx, nullptr, 1, a.finalize ? 0 : -3, len_enc, B, st);
   }
-  if (!dry) {
+  if (!dry && !ss) {
     launch_lens_affine(len_enc, nullptr, 2, 0, len_mel, B, st);
     launch_lens_affine(len_enc, nullptr, 2, 0, len_mel + B, B, st);
   }
   e.tile_lists.clear();
   e.make_tile_list(st, ws, len_ctx, B, Tt, kHalo, dry, len_enc);        // token-rate encoder GEMMs
-  e.make_tile_list(st, ws, len_mel, 2 * B, Tm, kEstHalo, dry);          // estimator (both CFG rows)
+  e.make_tile_list(st, ws, len_mel, 2 * B, Tm, kEstHalo, dry, nullptr, nullptr, t_lo);   // estimator (both CFG rows)
   e.make_tile_list(st, ws, len_mel, B, Tm, kHalo, dry);                 // mel-rate encoder GEMMs
 
   // ---- encoder, token rate ----
@@ -501,12 +540,13 @@ size_t flow_forward(Engine& e, cudaStream_t st, const FlowArgs& a, Arena& ws) {
   // separate CFG-combine + Euler kernel
   const bool fuse_euler = e.fuse_euler && fabsf(a.cfg - 0.7f) < 1e-6f && e.tensors.count("est.proj_cfg.w");
   for (int step = 0; step < a.n_steps; step++) {
+    EstStream es{ss, step, t_lo};
     if (fuse_euler) {
-      EulerFuse ef{Xst, XIN16, a.dt_steps[step], B};
-      est_core(e, st, sb, XIN16, len_mel, 2 * B, Tm, tres, a.n_steps, step, 0, a.streaming, dry, &ef);
+      EulerFuse ef{Xst, XIN16, dry ? 0.f : a.dt_steps[step], B};
+      est_core(e, st, sb, XIN16, len_mel, 2 * B, Tm, tres, a.n_steps, step, 0, a.streaming, dry, &ef, ss ? &es : nullptr);
       continue;
     }
-    est_core(e, st, sb, XIN16, len_mel, 2 * B, Tm, tres, a.n_steps, step, 0, a.streaming, dry);
+    est_core(e, st, sb, XIN16, len_mel, 2 * B, Tm, tres, a.n_steps, step, 0, a.streaming, dry, nullptr, ss ? &es : nullptr);
     e.launches++;
     if (!dry) launch_euler_pack(Xst, sb.V32, nullptr, 0, XIN16, len_mel, B, Tm, a.dt_steps[step], a.cfg, 0, st);
   }
@@ -514,6 +554,29 @@ size_t flow_forward(Engine& e, cudaStream_t st, const FlowArgs& a, Arena& ws) {
   if (!dry)
     launch_ntc_to_nct(Xst, Tm, 80, 0, a.prompt_feat_len, a.mel_out, (long long)80 * a.mel_out_T, a.mel_out_T, 80, len_mel, B, st);
   return ws.peak;
+}
+
+size_t stream_state_bytes(int n_slots, int T_cap, int n_steps) {
+  CV2_CHECK(n_slots >= 1 && T_cap >= 128 && T_cap % 128 == 0 && n_steps >= 1, "stream state: bad sizes (%d slots, T_cap %d, %d steps)",
+            n_slots, T_cap, n_steps);
+  StreamState s;
+  s.n_slots = n_slots; s.T_cap = T_cap; s.n_steps = n_steps;
+  return 256 + ((size_t)n_slots * 4 + 255) / 256 * 256 + 2 * (size_t)n_steps * kEstBlocks * s.kv_block() * sizeof(__half) +
+         (size_t)n_steps * kEstConvs * s.tail_block() * sizeof(__half) + 768;
+}
+
+StreamState stream_state_carve(void* base, size_t bytes, int n_slots, int T_cap, int n_steps) {
+  CV2_CHECK(base && bytes >= stream_state_bytes(n_slots, T_cap, n_steps), "stream state buffer too small");
+  StreamState s;
+  s.n_slots = n_slots; s.T_cap = T_cap; s.n_steps = n_steps;
+  Arena a;
+  a.base = static_cast<uint8_t*>(base);
+  a.cap = bytes;
+  s.t_done = a.get<int>(n_slots);
+  s.kcache = a.get<__half>((size_t)n_steps * kEstBlocks * s.kv_block());
+  s.vcache = a.get<__half>((size_t)n_steps * kEstBlocks * s.kv_block());
+  s.tails = a.get<__half>((size_t)n_steps * kEstConvs * s.tail_block());
+  return s;
 }
 
 }  // namespace cv2

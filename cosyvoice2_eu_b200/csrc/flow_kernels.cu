@@ -50,6 +50,51 @@ void launch_embed_rows(const float* xs, int T_in, const int* lens, const float* 
   embed_rows_kernel<<<dim3(T_alloc, B), 128, 0, st>>>(xs, T_in, lens, ctx, n_ctx, out, T_alloc);
   CV2_LAUNCH_CHECK();
 }
+__global__ void stream_lens_kernel(const int* __restrict__ prompt_len, const int* __restrict__ token_len, int* __restrict__ t_done,
+                                   int* __restrict__ len_ctx, int* __restrict__ len_enc, int* __restrict__ len_mel,
+                                   int* __restrict__ t_lo, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const bool active = token_len[b] > 0;
+  const int lc = active ? prompt_len[b] + token_len[b] : 0;
+  const int le = max(lc - 3, 0);
+  const int lm = 2 * le;
+  const int lo = active ? (t_done[b] / 128) * 128 : 0;
+  len_ctx[b] = lc;
+  len_enc[b] = le;
+  len_mel[b] = len_mel[B + b] = lm;
+  t_lo[b] = t_lo[B + b] = min(lo, lm);
+  if (active) t_done[b] = lm;
+}
+void launch_stream_lens(const int* prompt_len, const int* token_len, int* t_done, int* len_ctx, int* len_enc, int* len_mel, int* t_lo,
+                        int B, cudaStream_t st) {
+  stream_lens_kernel<<<(B + 127) / 128, 128, 0, st>>>(prompt_len, token_len, t_done, len_ctx, len_enc, len_mel, t_lo, B);
+  CV2_LAUNCH_CHECK();
+}
+
+__global__ void tail_swap_kernel(__half* __restrict__ buf, int T_alloc, int C8, long long ld, const int* __restrict__ lens,
+                                 const int* __restrict__ t_lo, __half* __restrict__ cache) {
+  const int nb = T_alloc / 128;
+  const int b = blockIdx.x + 1, s = blockIdx.y;
+  const int edge = b * 128, lo = t_lo[s], len = lens[s];
+  const bool restore = lo == edge && len > lo;
+  const bool save = edge > lo && edge <= len;
+  if (!restore && !save) return;
+  uint4* c = reinterpret_cast<uint4*>(cache + ((long long)(s * nb + b) * 2) * 512);
+  for (int i = threadIdx.x; i < 2 * C8; i += blockDim.x) {
+    const int r = i / C8, k = i - r * C8;
+    uint4* g = reinterpret_cast<uint4*>(buf + ((long long)s * T_alloc + edge - 2 + r) * ld) + k;
+    if (restore) *g = c[r * 64 + k];
+    else c[r * 64 + k] = *g;
+  }
+}
+void launch_tail_swap(__half* buf, int S, int T_alloc, int C, long long ld, const int* lens, const int* t_lo, __half* cache,
+                      cudaStream_t st) {
+  if (T_alloc / 128 < 2) return;
+  tail_swap_kernel<<<dim3(T_alloc / 128 - 1, S), 64, 0, st>>>(buf, T_alloc, C / 8, ld, lens, t_lo, cache);
+  CV2_LAUNCH_CHECK();
+}
+
 __global__ void absmax16_kernel(const __half* __restrict__ p, long long rows, int cols, long long ld, unsigned* __restrict__ slot) {
   float m = 0.f;
   const long long n = rows * cols;

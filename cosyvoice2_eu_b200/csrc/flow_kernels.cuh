@@ -27,6 +27,16 @@ void launch_split16(const float* x, int C, __half* out, int ld, int lo_off, long
 // encoder slot: fp32 embeddings [B, T_in, 512] (+ optional 3-row look-ahead context) -> 16-bit A operand rows, zero padded
 void launch_embed_rows(const float* xs, int T_in, const int* lens, const float* ctx, int n_ctx, __half* out, int B, int T_alloc,
                        cudaStream_t st);
+// incremental streaming (engine.h StreamState): all per-slot lengths of a non-final chunk call in one launch.
+// active slot (token_len > 0): len_ctx = prompt + token, len_enc = len_ctx - 3, len_mel = 2 len_enc (both CFG rows),
+// t_lo = floor(t_done / 128) * 128, then t_done = len_mel; inactive slot: every length 0, t_done untouched.
+void launch_stream_lens(const int* prompt_len, const int* token_len, int* t_done, int* len_ctx, int* len_enc, int* len_mel, int* t_lo,
+                        int B, cudaStream_t st);
+// Causal-conv input rows across 128-row tile boundaries: for boundary b (row 128 b) of sequence s, restore rows 128 b - 2, 128 b - 1
+// of `buf` from the cache if the call starts there (t_lo[s] == 128 b), save them if the call has just produced them
+// (t_lo[s] < 128 b <= lens[s]).  buf: 16-bit [S, T_alloc, ld] (first C columns), cache: [S][T_alloc / 128][2][512].
+void launch_tail_swap(__half* buf, int S, int T_alloc, int C, long long ld, const int* lens, const int* t_lo, __half* cache,
+                      cudaStream_t st);
 // max |x| of a strided 16-bit matrix into *slot (fp32 bit pattern, atomicMax; NaN counts as +inf)
 void launch_absmax16(const __half* p, long long rows, int cols, long long ld, unsigned* slot, cudaStream_t st);
 // out[i] = min(a[i], hi) + add

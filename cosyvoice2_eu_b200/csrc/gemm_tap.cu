@@ -618,11 +618,13 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 // Compact list of the (sequence, t0) row tiles that contain at least one row < len + halo, in (s, t) order.
 __global__ void build_tile_list_kernel(const int* __restrict__ lens, int S, int T_alloc, int halo, int* __restrict__ list,
-                                       int* __restrict__ count) {
+                                       int* __restrict__ count, const int* __restrict__ lo) {
   extern __shared__ int offs[];   // [S + 1]
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
     const int rows = min(lens[s] + halo, T_alloc);
-    offs[s + 1] = rows > 0 ? (rows + kTileM - 1) / kTileM : 0;
+    const int first = lo ? lo[s] / kTileM : 0;
+    const int n = rows > 0 ? (rows + kTileM - 1) / kTileM : 0;
+    offs[s + 1] = n > first ? n - first : 0;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -633,14 +635,15 @@ __global__ void build_tile_list_kernel(const int* __restrict__ lens, int S, int 
   __syncthreads();
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
     const int n = offs[s + 1] - offs[s];
+    const int first = lo ? lo[s] / kTileM : 0;
     for (int k = 0; k < n; k++) {
       list[2 * (offs[s] + k)] = s;
-      list[2 * (offs[s] + k) + 1] = k * kTileM;
+      list[2 * (offs[s] + k) + 1] = (first + k) * kTileM;
     }
   }
 }
-void launch_build_tile_list(const int* lens, int S, int T_alloc, int halo, int* list, int* count, cudaStream_t stream) {
-  build_tile_list_kernel<<<1, 256, (S + 1) * sizeof(int), stream>>>(lens, S, T_alloc, halo, list, count);
+void launch_build_tile_list(const int* lens, int S, int T_alloc, int halo, int* list, int* count, cudaStream_t stream, const int* lo) {
+  build_tile_list_kernel<<<1, 256, (S + 1) * sizeof(int), stream>>>(lens, S, T_alloc, halo, list, count, lo);
   CV2_LAUNCH_CHECK();
 }
 

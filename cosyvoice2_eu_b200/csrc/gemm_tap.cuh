@@ -88,7 +88,9 @@ struct GemmParams {
 // bn in {64, 128, 256}.
 int gemm_tap_spec(int bn, const GemmParams& p);
 // list: [2 * S * (T_alloc/128)] ints, count: 1 int (device)
-void launch_build_tile_list(const int* lens, int S, int T_alloc, int halo, int* list, int* count, cudaStream_t stream);
+// lo (optional, [S]): only tiles with t0 >= floor(lo[s] / 128) * 128 are listed (incremental streaming: earlier rows are final)
+void launch_build_tile_list(const int* lens, int S, int T_alloc, int halo, int* list, int* count, cudaStream_t stream,
+                            const int* lo = nullptr);
 void launch_gemm_tap(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream);
 
 }  // namespace cv2

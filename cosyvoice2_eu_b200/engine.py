@@ -310,6 +310,54 @@ class B200Flow:
             return mel, dict(mu=mu, encoder_out=enc)
         return (mel,)
 
+    # ---- incremental streaming ----
+    def open_stream_group(self, n_slots, max_mel_frames=640):
+        """Device state for up to `n_slots` concurrent streaming sessions whose non-final chunk calls never exceed
+        `max_mel_frames` mel frames (prompt included; rounded up to 128)."""
+        return StreamGroup(self, n_slots, max_mel_frames)
+
+    def inference_stream_group(self, group, requests):
+        """One NON-FINAL streaming chunk (flow.inference(streaming=True, finalize=False)) for the sessions in `requests`
+        ({uuid, token [1,n_visible], prompt_token, prompt_feat, embedding}); each session keeps the slot of `group` it got at
+        its first chunk.  Only the row tiles that hold new frames are computed.  Returns {uuid: (mel [1,80,T_gen] whose frames
+        from 2 * token_offset on are valid -- what token2wav keeps, model.py:311)}."""
+        eng, dev, n = self.eng, self.device, group.n_slots
+        slot_of = [group.slot(r["uuid"]) for r in requests]
+        tl, pl, fl = [0] * n, [0] * n, [0] * n
+        for r, s in zip(requests, slot_of):
+            tl[s], pl[s], fl[s] = int(r["token"].shape[1]), int(r["prompt_token"].shape[1]), int(r["prompt_feat"].shape[1])
+        max_total = max(a + b for a, b in zip(tl, pl))
+        mel_lens = [max(2 * (a + b - self.pre_lookahead_len) - c, 0) if a else 0 for a, b, c in zip(tl, pl, fl)]
+        if 2 * (max_total - self.pre_lookahead_len) > group.T_cap:
+            raise _lib.Cv2Error(f"chunk of {2 * (max_total - 3)} mel frames exceeds the stream group's capacity {group.T_cap}")
+        mel_T = max(mel_lens)
+        with eng.lock, torch.cuda.device(dev):
+            # Device-side token ring (row F3): a session's prompt (tokens, mel, x-vector) is uploaded once, at its first chunk;
+            # afterwards only the speech tokens that are NEW since the previous chunk cross the bus (~25 ints per session).
+            h2d = 0
+            for r, s in zip(requests, slot_of):
+                t = r["token"].reshape(-1).to(torch.int32).cpu()
+                if t.numel() and int(t.max()) >= self.vocab_size:
+                    raise IndexError(f"speech token id {int(t.max())} is out of range for the {self.vocab_size}-entry embedding table")
+                h2d += group.upload(s, r, t)
+            lens = eng.staging("slens", (3, n), torch.int32)
+            lens.copy_(torch.tensor([tl, pl, fl], dtype=torch.int32))
+            (lens,) = eng.staged_to_device([("slens", lens)])
+            self.last_h2d_bytes = h2d + 12 * n
+            tok, ptk, pf, emb = group.tok, group.ptk, group.pf, group.emb
+            mel = torch.empty(n, 80, mel_T, dtype=torch.float32, device=dev)
+            nb = eng.lib.cv2_flow_stream_workspace_bytes(eng.h, n, group.T_cap, self.n_timesteps)
+            if nb == 0:
+                raise _lib.Cv2Error(eng.lib.cv2_last_error().decode())
+            ws = eng.workspace("flow_stream", (n, group.T_cap), nb)
+            _lib.check(eng.lib.cv2_flow_forward_stream(
+                eng.h, eng.stream(), _lib.ptr(tok), tok.shape[1], _lib.ptr(lens[0]), _lib.ptr(ptk), ptk.shape[1], _lib.ptr(lens[1]),
+                _lib.ptr(pf), pf.shape[1] * 80, _lib.ptr(lens[2]), _lib.ptr(emb), _lib.ptr(self.rand_noise), self.rand_noise.shape[2],
+                n, max_total, _lib.ptr(self._t_dev), self._dt_host, self.n_timesteps, self.inference_cfg_rate, _lib.ptr(mel), mel_T,
+                _lib.ptr(group.state), group.state.numel(), group.T_cap, _lib.ptr(ws), ws.numel()))
+            self.last_launches = eng.last_launches()
+        return {r["uuid"]: mel[s:s + 1, :, :mel_lens[s]] for r, s in zip(requests, slot_of)}
+
     @torch.inference_mode()
     def inference(self, token, token_len, prompt_token, prompt_token_len, prompt_feat, prompt_feat_len, embedding, streaming,
                   finalize):
@@ -318,6 +366,89 @@ class B200Flow:
         out = self.inference_batch([token[0]], [prompt_token[0]], [prompt_feat[0]], [embedding[0]], streaming=streaming,
                                    finalize=finalize)
         return out[0], None
+
+
+class StreamGroup:
+    """Incremental-streaming state of the flow for up to `n_slots` concurrent sessions (C side: StreamState, engine.h).
+    Per session ~2.3 MB per mel frame of capacity (k / v^T of 56 blocks x 10 Euler steps x 2 CFG rows): 1.5 GB at 640 frames."""
+
+    def __init__(self, flow, n_slots, max_mel_frames=640):
+        self.flow = flow
+        self.n_slots = int(n_slots)
+        self.T_cap = -(-int(max_mel_frames) // 128) * 128
+        eng = flow.eng
+        nbytes = int(eng.lib.cv2_stream_state_bytes(self.n_slots, self.T_cap, flow.n_timesteps))
+        if nbytes == 0:
+            raise _lib.Cv2Error(eng.lib.cv2_last_error().decode())
+        with torch.inference_mode(False):
+            self.state = torch.zeros(nbytes, dtype=torch.uint8, device=flow.device)
+        self.lock = threading.Lock()
+        self.slots = {}                                  # uuid -> slot
+        self.free = list(range(self.n_slots - 1, -1, -1))
+        # device-resident inputs per slot: the token ring (append only) and the prompt, uploaded once per session
+        self.tok_cap = self.T_cap // 2 + 8
+        dev = flow.device
+        with torch.inference_mode(False):
+            self.tok = torch.zeros(self.n_slots, self.tok_cap, dtype=torch.int32, device=dev)
+            self.ptk = torch.zeros(self.n_slots, self.tok_cap, dtype=torch.int32, device=dev)
+            self.pf = torch.zeros(self.n_slots, 2 * self.tok_cap, 80, dtype=torch.float32, device=dev)
+            self.emb = torch.zeros(self.n_slots, 192, dtype=torch.float32, device=dev)
+        self.n_tok = [0] * self.n_slots                  # speech tokens already on the device, per slot
+        self.has_prompt = [False] * self.n_slots
+
+    def upload(self, s, req, tok_host):
+        """Bring slot s up to date with the request: prompt once, then only the tokens beyond what the ring already holds.
+        Returns the bytes copied host -> device."""
+        n_bytes = 0
+        if not self.has_prompt[s]:
+            p = req["prompt_token"].reshape(-1).to(torch.int32)
+            if p.numel() and int(p.max()) >= self.flow.vocab_size:
+                raise IndexError(f"prompt token id {int(p.max())} is out of range for the {self.flow.vocab_size}-entry embedding table")
+            f = req["prompt_feat"].reshape(-1, 80).float()
+            if p.numel() > self.tok_cap or f.shape[0] > 2 * self.tok_cap:
+                raise _lib.Cv2Error("prompt longer than the stream group's capacity")
+            self.ptk[s, :p.numel()].copy_(p, non_blocking=True)
+            self.pf[s, :f.shape[0]].copy_(f, non_blocking=True)
+            self.emb[s].copy_(req["embedding"].reshape(192).float(), non_blocking=True)
+            self.has_prompt[s] = True
+            n_bytes += 4 * p.numel() + 4 * f.numel() + 4 * 192
+        have, want = self.n_tok[s], int(tok_host.numel())
+        if want > self.tok_cap:
+            raise _lib.Cv2Error("more visible tokens than the stream group's capacity")
+        if want > have:
+            self.tok[s, have:want].copy_(tok_host[have:want], non_blocking=True)
+            self.n_tok[s] = want
+            n_bytes += 4 * (want - have)
+        return n_bytes
+
+    def slot(self, uuid):
+        """The session's slot; a new session takes a free one (its row counter is reset on the stream)."""
+        with self.lock:
+            s = self.slots.get(uuid)
+            if s is None:
+                if not self.free:
+                    raise _lib.Cv2Error(f"stream group is full ({self.n_slots} sessions)")
+                s = self.free.pop()
+                self.slots[uuid] = s
+                self.n_tok[s], self.has_prompt[s] = 0, False
+                eng = self.flow.eng
+                with eng.lock, torch.cuda.device(self.flow.device):
+                    _lib.check(eng.lib.cv2_stream_state_reset_slot(eng.stream(), _lib.ptr(self.state), self.state.numel(), self.n_slots,
+                                                                   self.T_cap, self.flow.n_timesteps, s))
+            return s
+
+    def has(self, uuid):
+        with self.lock:
+            return uuid in self.slots
+
+    def release(self, uuid):
+        with self.lock:
+            s = self.slots.pop(uuid, None)
+            if s is not None:
+                self.free.append(s)
+
+    def fits(self, n_prompt, n_visible):
+        return 2 * (n_prompt + n_visible - 3) <= self.T_cap
 
 
 class B200HiFT:
@@ -464,21 +595,35 @@ class B200Token2Wav:
         return speech, mel_lens * 480
 
     @torch.inference_mode()
-    def token2wav_stream_batch(self, requests, finalize, noises=None):
+    def token2wav_stream_batch(self, requests, finalize, noises=None, group=None):
         """One streaming step for many concurrent sessions at once (BASELINE configs[3]): every request is what
         CosyVoice2Model.tts(stream=True) would pass to token2wav for that session at this step (model.py:358-380):
             dict(token=[1,n_visible], prompt_token, prompt_feat, embedding, token_offset, uuid)
         All requests of one call share `finalize` (non-final chunks run with streaming masks, the final chunk with
         streaming=False, exactly like the reference: model.py:373-380 does not pass `stream`).  The flow runs as ONE ragged
         batch, the vocoder as one batch per cache state (sessions with / without an hift cache), the crossfade and cache
-        update per session on the device.  Returns a list of speech tensors [1, L_b] (same values as per-session calls)."""
+        update per session on the device.  Returns a list of speech tensors [1, L_b] (same values as per-session calls).
+
+        `group` (a StreamGroup from flow.open_stream_group): non-final chunks then run INCREMENTALLY -- the flow computes only the
+        row tiles holding frames that are new since the session's previous chunk instead of the whole prefix (the k / v^T and
+        causal-conv state of earlier frames lives in the group); the final chunk is the reference's full-attention pass over
+        everything, after which the session's slot is released."""
         stream = not finalize
-        mel, mel_lens = self.flow.inference_batch([r["token"][0] for r in requests], [r["prompt_token"][0] for r in requests],
-                                                  [r["prompt_feat"][0] for r in requests], [r["embedding"][0] for r in requests],
-                                                  streaming=stream, finalize=finalize)
+        incremental = group is not None and stream and all(group.fits(r["prompt_token"].shape[1], r["token"].shape[1]) for r in requests)
+        if incremental:
+            by_uuid = self.flow.inference_stream_group(group, requests)
+            per_req = [by_uuid[r["uuid"]] for r in requests]
+        else:
+            mel, mel_lens = self.flow.inference_batch([r["token"][0] for r in requests], [r["prompt_token"][0] for r in requests],
+                                                      [r["prompt_feat"][0] for r in requests], [r["embedding"][0] for r in requests],
+                                                      streaming=stream, finalize=finalize)
+            per_req = [mel[b:b + 1, :, :int(mel_lens[b])] for b in range(len(requests))]
+        if group is not None and finalize:
+            for r in requests:
+                group.release(r["uuid"])
         mels = []
         for b, r in enumerate(requests):
-            m = mel[b:b + 1, :, r["token_offset"] * self.flow.token_mel_ratio:int(mel_lens[b])]
+            m = per_req[b][:, :, r["token_offset"] * self.flow.token_mel_ratio:]
             cache = self._cache_get(r["uuid"])
             if cache is not None:
                 m = torch.concat([cache["mel"], m], dim=2)

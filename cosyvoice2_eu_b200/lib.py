@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libcv2eu_b200.so")
 SYMBOLS = [
     "cv2_last_error", "cv2_version", "cv2_engine_create", "cv2_engine_destroy", "cv2_engine_set_tensor", "cv2_engine_finalize",
     "cv2_engine_last_launches", "cv2_engine_set_option", "cv2_engine_read_ranges", "cv2_debug_set_ffn_trace", "cv2_engine_set_seed_ptr", "cv2_engine_set_profiling", "cv2_engine_read_profile", "cv2_estimator_workspace_bytes", "cv2_estimator_forward", "cv2_flow_workspace_bytes",
-    "cv2_flow_forward", "cv2_encoder_workspace_bytes", "cv2_encoder_forward", "cv2_hift_workspace_bytes", "cv2_hift_forward", "cv2_hift_forward_pcm16", "cv2_crossfade", "cv2_mel_time_stretch", "cv2_prompt_mel_frames", "cv2_prompt_mel_workspace_bytes",
+    "cv2_flow_forward", "cv2_stream_state_bytes", "cv2_stream_state_reset_slot", "cv2_flow_stream_workspace_bytes",
+    "cv2_flow_forward_stream", "cv2_encoder_workspace_bytes", "cv2_encoder_forward", "cv2_hift_workspace_bytes", "cv2_hift_forward", "cv2_hift_forward_pcm16", "cv2_crossfade", "cv2_mel_time_stretch", "cv2_prompt_mel_frames", "cv2_prompt_mel_workspace_bytes",
     "cv2_prompt_mel", "cv2_resample_16k_24k_len", "cv2_resample_16k_24k", "cv2_op_gemm_tap", "cv2_op_flash_attn",
     "cv2_op_rel_attn", "cv2_op_source_stft", "cv2_op_istft", "cv2_op_nsf_source",
 ]
@@ -54,6 +55,13 @@ def load():
     lib.cv2_flow_workspace_bytes.restype = sz
     lib.cv2_flow_forward.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, vp,
                                      C.POINTER(f32), i32, f32, vp, i32, vp, vp, vp, sz]
+    lib.cv2_stream_state_bytes.argtypes = [i32, i32, i32]
+    lib.cv2_stream_state_bytes.restype = sz
+    lib.cv2_stream_state_reset_slot.argtypes = [vp, vp, sz, i32, i32, i32, i32]
+    lib.cv2_flow_stream_workspace_bytes.argtypes = [vp, i32, i32, i32]
+    lib.cv2_flow_stream_workspace_bytes.restype = sz
+    lib.cv2_flow_forward_stream.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, i64, vp, vp, vp, i32, i32, i32, vp,
+                                            C.POINTER(f32), i32, f32, vp, i32, vp, sz, i32, vp, sz]
     lib.cv2_encoder_workspace_bytes.argtypes = [vp, i32, i32, i32]
     lib.cv2_encoder_workspace_bytes.restype = sz
     lib.cv2_encoder_forward.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, i32, vp, sz]
@@ -79,7 +87,7 @@ def load():
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("cv2_last_error", "cv2_version", "cv2_engine_destroy", "cv2_engine_last_launches") and \
-                not name.endswith("_workspace_bytes"):
+                not name.endswith("_bytes"):
             fn.restype = i32
     _lib = lib
     return lib

@@ -61,8 +61,11 @@ class StreamScheduler:
     """open() a session, push() speech tokens as the LLM produces them, close() when it has finished; step() (or run()) turns
     whatever is ready into audio chunks: a list of (uuid, speech [1, L], is_final)."""
 
-    def __init__(self, t2w, token_hop_len=25, pre_lookahead_len=None):
+    def __init__(self, t2w, token_hop_len=25, pre_lookahead_len=None, group=None):
+        """group: optional StreamGroup (B200Flow.open_stream_group) -- non-final chunks then run incrementally on the device state
+        it holds (row F1) instead of recomputing the prefix."""
         self.t2w = t2w
+        self.group = group
         self.token_hop_len = int(token_hop_len)
         self.pre_lookahead_len = int(t2w.flow.pre_lookahead_len if pre_lookahead_len is None else pre_lookahead_len)
         self.sessions = {}
@@ -140,7 +143,8 @@ class StreamScheduler:
             reqs = [dict(token=tok, prompt_token=s.prompt_token, prompt_feat=s.prompt_feat, embedding=s.embedding, token_offset=off,
                          uuid=s.uuid) for s, tok, off in items]
             nz = None if noises is None else [noises[s.uuid] for s, _, _ in items]
-            speeches = self.t2w.token2wav_stream_batch(reqs, finalize=fin, noises=nz)
+            kw = {} if self.group is None else {"group": self.group}
+            speeches = self.t2w.token2wav_stream_batch(reqs, finalize=fin, noises=nz, **kw)
             out.extend((s.uuid, sp, fin) for (s, _, _), sp in zip(items, speeches))
         with self.cv:
             for uuid in [u for u, s in self.sessions.items() if s.done]:

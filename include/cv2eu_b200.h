@@ -84,6 +84,27 @@ int cv2_flow_forward(cv2_engine* e, void* stream, const int32_t* token, int toke
                      const float* t_steps_dev, const float* dt_steps_host, int n_steps, float cfg_rate, float* mel_out,
                      int mel_out_T, float* mu_out, float* enc_out, void* workspace, size_t workspace_bytes);
 
+/* ---- incremental streaming (replaces the prefix recomputation of CosyVoice2Model.tts,
+ *      cosyvoice/cli/model.py:351-381, for the NON-FINAL chunks; the final chunk runs with full attention through cv2_flow_forward
+ *      exactly as the reference does, model.py:373-380).  A stream state serves `n_slots` concurrent sessions; it is caller-owned
+ *      device memory of cv2_stream_state_bytes(), ZERO-INITIALISED once.  It holds, per Euler step and transformer block, the
+ *      k / v^T rows of everything computed so far and, per Euler step and causal conv, the two input rows in front of every
+ *      128-row tile boundary; a chunk call then computes only the row tiles from floor(rows_done / 128) * 128 on.
+ *      cv2_flow_forward_stream takes the same per-utterance inputs as cv2_flow_forward with B = n_slots (row b = slot b; a slot
+ *      with token_len 0 sits this call out).  T_cap (multiple of 128) bounds the mel frames of a non-final chunk call
+ *      (2 * (prompt + visible tokens - 3) <= T_cap).  mel_out [n_slots,80,mel_out_T]: frames after the prompt; frames in
+ *      front of those that are NEW in this call (everything before 2 * token_offset, which token2wav drops anyway,
+ *      model.py:311) are unspecified.  cv2_stream_state_reset_slot starts a new session in a slot. ---- */
+size_t cv2_stream_state_bytes(int n_slots, int T_cap, int n_steps);
+int cv2_stream_state_reset_slot(void* stream, void* state, size_t state_bytes, int n_slots, int T_cap, int n_steps, int slot);
+size_t cv2_flow_stream_workspace_bytes(cv2_engine* e, int n_slots, int T_cap, int n_steps);
+int cv2_flow_forward_stream(cv2_engine* e, void* stream, const int32_t* token, int token_stride, const int32_t* token_len,
+                            const int32_t* prompt_token, int prompt_stride, const int32_t* prompt_len, const float* prompt_feat,
+                            long long prompt_feat_bstride, const int32_t* prompt_feat_len, const float* embedding,
+                            const float* rand_noise, int noise_stride, int n_slots, int max_tok_total, const float* t_steps_dev,
+                            const float* dt_steps_host, int n_steps, float cfg_rate, float* mel_out, int mel_out_T, void* state,
+                            size_t state_bytes, int T_cap, void* workspace, size_t workspace_bytes);
+
 /* ---- encoder slot (boundary #5): UpsampleConformerEncoder.forward (cosyvoice/transformer/upsample_encoder.py:243-306), the
  *      module CosyVoice2Model.load_jit swaps in as `flow.encoder` (cosyvoice/cli/model.py:285-287), called by flow.inference as
  *      `encoder(token, token_len, context=..., streaming=...)` (cosyvoice/flow/flow.py:258-263).

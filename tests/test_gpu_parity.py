@@ -689,3 +689,107 @@ def test_workspaces_do_not_accumulate_across_shapes(engine):
     assert len(kinds) == len(set((k[0], k[1]) for k in eng.ws))
     assert sum(1 for k in eng.ws if k[0] == "flow") <= 2          # default stream (+ a graph-capture side stream at most)
     assert sum(1 for k in eng.pinned if k[0] == "tok") <= 2
+
+
+# ---------------------------------------------------------------------------------------------------- incremental streaming (F1)
+def _stream_reqs(utts, uuids, n_vis, offs):
+    return [dict(token=u["token"][:, :nv], prompt_token=u["prompt_token"], prompt_feat=u["prompt_feat"], embedding=u["embedding"],
+                 token_offset=off, uuid=uid) for u, uid, nv, off in zip(utts, uuids, n_vis, offs)]
+
+
+def test_incremental_streaming_flow_against_reference_chunks(engine, golden):
+    """Row F1: non-final chunks computed INCREMENTALLY (only the row tiles with new frames; k / v^T and causal-conv state of earlier
+    frames come from the StreamGroup) against the mel the UNMODIFIED reference produced for every chunk call of the same session
+    by recomputing the whole prefix (tests/golden/stream_long.npz: calls of 200 ... 450 mel frames, crossing the 128 / 256 / 384-row
+    tile boundaries), <= 1e-2; and against the engine's own prefix-recompute result of the same call (same kernels, same inputs
+    per row: the two must agree to rounding noise)."""
+    flow = engine[0]
+    g = golden("stream_long")
+    u = _utt(g)
+    sched = [(int(a), int(b), bool(c)) for a, b, c in g["schedule"]]
+    group = flow.open_stream_group(2, max_mel_frames=512)
+    assert group.T_cap == 512
+    other = _utt(dict(n_tok=90, n_prompt=20, seed=61))            # a second session in the other slot, out of step with the first
+    from cosyvoice2_eu_b200.scheduler import chunk_schedule
+    sched_o = chunk_schedule(90, 20)
+    for ci, (n_vis, off, fin) in enumerate(sched):
+        if fin:
+            mel, _ = flow.inference(u["token"], None, u["prompt_token"], None, u["prompt_feat"], None, u["embedding"], False, True)
+            kept = mel[:, :, 2 * off:]
+            err = np.abs(kept.cpu().numpy() - g[f"mel{ci}"]).max()
+            print("final chunk (full attention) mel err", err)
+            assert err <= MEL_TOL
+            continue
+        reqs = _stream_reqs([u], ["a"], [n_vis], [off])
+        if 1 <= ci < len(sched_o) and not sched_o[ci - 1][2]:   # the other session starts one step later
+            nv_o, off_o, _ = sched_o[ci - 1]
+            reqs += _stream_reqs([other], ["b"], [nv_o], [off_o])
+        out = flow.inference_stream_group(group, reqs)
+        mel = out["a"]
+        assert mel.shape[2] == int(g[f"mel_len{ci}"])
+        kept = mel[:, :, 2 * off:]
+        err = np.abs(kept.cpu().numpy() - g[f"mel{ci}"]).max()
+        full, _ = flow.inference(u["token"][:, :n_vis], None, u["prompt_token"], None, u["prompt_feat"], None, u["embedding"], True, False)
+        d_full = float((full[:, :, 2 * off:] - kept).abs().max())
+        print(f"chunk {ci}: {mel.shape[2]} frames, incremental vs reference {err:.2e}, vs prefix recompute {d_full:.2e}, "
+              f"launches {flow.last_launches}")
+        assert err <= MEL_TOL
+        assert d_full < 1e-4
+        if "b" in out:
+            nv_o, off_o, _ = sched_o[ci - 1]
+            full_o, _ = flow.inference(other["token"][:, :nv_o], None, other["prompt_token"], None, other["prompt_feat"], None,
+                                       other["embedding"], True, False)
+            assert float((full_o[:, :, 2 * off_o:] - out["b"][:, :, 2 * off_o:]).abs().max()) < 1e-4
+    group.release("a")
+    group.release("b")
+    # a new session in a recycled slot starts from scratch (row counter reset), whatever the slot held
+    v = _utt(dict(n_tok=60, n_prompt=75, seed=62))
+    n_vis, off, _ = chunk_schedule(60, 75)[0]
+    inc = flow.inference_stream_group(group, _stream_reqs([v], ["c"], [n_vis], [off]))["c"]
+    full, _ = flow.inference(v["token"][:, :n_vis], None, v["prompt_token"], None, v["prompt_feat"], None, v["embedding"], True, False)
+    assert float((inc - full).abs().max()) < 1e-4
+
+
+def test_incremental_stream_batch_equals_prefix_recompute(engine):
+    """token2wav_stream_batch(group=...) (incremental non-final chunks, full-attention final chunk) delivers the same audio as
+    the prefix-recompute path for several concurrent sessions of different lengths, and releases the slots at the end."""
+    from cosyvoice2_eu_b200 import B200Token2Wav
+    from cosyvoice2_eu_b200.scheduler import chunk_schedule
+    flow, hift, _ = engine
+    specs = [(130, 75, 71), (95, 25, 72), (160, 60, 73), (56, 49, 74)]
+    utts = [_utt(dict(n_tok=n, n_prompt=p, seed=s)) for n, p, s in specs]
+    scheds = [chunk_schedule(n, p) for n, p, _ in specs]
+    noise_of = lambda si, ci, mel_len: T(weights.make_nsf_noise(mel_len * 480, 2000 * si + ci))
+
+    def run(group):
+        t2w = B200Token2Wav(flow, hift)
+        for si in range(len(specs)):
+            t2w.hift_cache_dict[f"s{si}"] = None
+        got = [[] for _ in specs]
+        for step in range(max(len(s) for s in scheds)):
+            for fin in (False, True):
+                reqs, who, nz = [], [], []
+                for si, (u, sched) in enumerate(zip(utts, scheds)):
+                    if step < len(sched) and sched[step][2] == fin:
+                        n_vis, off, _ = sched[step]
+                        n_new = (n_vis - (0 if fin else 3)) * 2 - off * 2
+                        mel_len = n_new + (8 if t2w.hift_cache_dict[f"s{si}"] is not None else 0)
+                        reqs += _stream_reqs([u], [f"s{si}"], [n_vis], [off])
+                        who.append(si)
+                        nz.append(noise_of(si, step, mel_len))
+                if reqs:
+                    outs = t2w.token2wav_stream_batch(reqs, finalize=fin, noises=nz, group=group)
+                    for si, o in zip(who, outs):
+                        got[si].append(o.cpu())
+        return got
+
+    want = run(None)
+    group = flow.open_stream_group(4, max_mel_frames=640)
+    got = run(group)
+    assert not group.slots and len(group.free) == 4
+    for si in range(len(specs)):
+        assert len(got[si]) == len(want[si]) == len(scheds[si])
+        assert sum(c.shape[1] for c in got[si]) == 2 * 480 * specs[si][0]
+        for a, b in zip(got[si], want[si]):
+            assert a.shape == b.shape
+            assert snr_db(b.numpy(), a.numpy()) > 50
