@@ -47,7 +47,7 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   // sorted the batch by ascending length (length bucketing), so the last wave is made of short CTAs
   const int s = p.reverse_seq ? p.S - 1 - (int)blockIdx.z : (int)blockIdx.z;
   const int len = p.lens ? p.lens[s] : p.len_all;
-  if (t0 >= len + p.halo) return;
+  if (t0 >= len + p.halo || len <= 0) return;
   if (p.lo && t0 < (p.lo[s] / 128) * 128) return;
   const int sh = s * p.heads + h;
   int kv_end = len;

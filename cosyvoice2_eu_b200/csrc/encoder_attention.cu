@@ -43,7 +43,7 @@ rel_attn_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_constant_
   const int h = blockIdx.y;
   const int s = blockIdx.z;
   const int len = p.lens ? p.lens[s] : p.len_all;
-  if (t0 >= len + p.halo) return;
+  if (t0 >= len + p.halo || len <= 0) return;   // (an empty sequence -- an idle streaming slot -- has no key tile at all)
   const int sh = s * 8 + h;
   int kv_end = len;
   if (p.chunk > 0) kv_end = min(len, ((t0 + 127) / p.chunk + 1) * p.chunk);

@@ -621,7 +621,7 @@ __global__ void build_tile_list_kernel(const int* __restrict__ lens, int S, int 
                                        int* __restrict__ count, const int* __restrict__ lo) {
   extern __shared__ int offs[];   // [S + 1]
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
-    const int rows = min(lens[s] + halo, T_alloc);
+    const int rows = lens[s] > 0 ? min(lens[s] + halo, T_alloc) : 0;   // an empty sequence (idle streaming slot) has no tile
     const int first = lo ? lo[s] / kTileM : 0;
     const int n = rows > 0 ? (rows + kTileM - 1) / kTileM : 0;
     offs[s + 1] = n > first ? n - first : 0;
