@@ -4,7 +4,7 @@ Only the hot path lives here: csrc/ (hand-written CUDA kernels + the C ABI of in
 host that mirrors the reference's interface for the path (flow.inference / hift.inference / token2wav)."""
 from .engine import (B200Encoder, B200Flow, B200HiFT, B200Token2Wav, GraphedToken2Wav, StreamGroup, euler_schedule,  # noqa: F401
                      get_engine)
-from .frontend import (align_prompt, extract_speech_feat, extract_speech_feat_batch, mel_spectrogram,  # noqa: F401
-                       resample_16k_to_24k)
+from .frontend import (align_prompt, extract_speech_feat, extract_speech_feat_batch, extract_spk_feat,  # noqa: F401
+                       mel_spectrogram, resample_16k_to_24k)
 from .scheduler import StreamScheduler  # noqa: F401
 from .lib import LIB_PATH, SYMBOLS, Cv2Error  # noqa: F401

@@ -6,6 +6,7 @@
 #include "engine.h"
 #include "flow_kernels.cuh"
 #include "hift_kernels.cuh"
+#include "kaldi_fbank.cuh"
 #include "prompt_mel.cuh"
 
 using namespace cv2;
@@ -427,6 +428,16 @@ int cv2_prompt_mel(void* stream, const float* wav, long long wav_stride, const i
   CV2_API_BEGIN
   CV2_CHECK(wav && n_samples && mel && workspace, "cv2_prompt_mel: null pointer");
   launch_prompt_mel(wav, wav_stride, n_samples, B, max_samples, mel, mel_len, workspace, workspace_bytes, (cudaStream_t)stream);
+  CV2_API_END
+}
+
+int cv2_kaldi_fbank_frames(int n_samples) { return kaldi_fbank_frames(n_samples); }
+
+int cv2_kaldi_fbank(void* stream, const float* wav16, long long wav_stride, const int32_t* n_samples, int B, int max_samples,
+                    float* feat, int32_t* feat_len, int subtract_mean) {
+  CV2_API_BEGIN
+  CV2_CHECK(wav16 && n_samples && feat, "cv2_kaldi_fbank: null pointer");
+  launch_kaldi_fbank(wav16, wav_stride, n_samples, B, max_samples, feat, feat_len, subtract_mean, (cudaStream_t)stream);
   CV2_API_END
 }
 

@@ -104,6 +104,32 @@ def resample_16k_to_24k(speech_16k, device="cuda:0", lengths=None):
     return y if lengths is None else (y, n_out)
 
 
+def extract_spk_feat(speech_16k, device="cuda:0", lengths=None):
+    """frontend.py:276-278, the feature half of _extract_spk_embedding: speech_16k [B, L] (or [L]) at 16 kHz ->
+    `kaldi.fbank(speech, num_mel_bins=80, dither=0, sample_frequency=16000)` minus its mean over frames, [B, T, 80] on `device`
+    (+ the frame counts [B] int32 when `lengths` gives ragged rows).  The CAM++ ONNX session that turns it into the 192-d
+    x-vector stays on the reference's side."""
+    L = _lib.load()
+    x = speech_16k.to(device=device, dtype=torch.float32)
+    if x.dim() == 1:
+        x = x[None]
+    x = x.contiguous()
+    if not x.is_cuda:
+        raise _lib.Cv2Error("x-vector features are computed on the GPU only (there is no CPU fallback)")
+    B, max_n = x.shape
+    if max_n < 400:
+        raise _lib.Cv2Error(f"kaldi.fbank needs at least one 400-sample frame, got {max_n} samples")
+    n = (torch.full((B,), max_n, dtype=torch.int32, device=x.device) if lengths is None
+         else lengths.to(device=x.device, dtype=torch.int32))
+    T = int(L.cv2_kaldi_fbank_frames(int(max_n)))
+    feat = torch.empty(B, T, NUM_MELS, dtype=torch.float32, device=x.device)
+    feat_len = torch.empty(B, dtype=torch.int32, device=x.device)
+    st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    with torch.cuda.device(x.device):
+        _lib.check(L.cv2_kaldi_fbank(st, _lib.ptr(x), x.stride(0), _lib.ptr(n), B, int(max_n), _lib.ptr(feat), _lib.ptr(feat_len), 1))
+    return feat if lengths is None else (feat, feat_len)
+
+
 def align_prompt(speech_feat, speech_feat_len, speech_token, speech_token_len):
     """frontend.py:498-502 (CosyVoice2, 24 kHz): keep n = min(feat frames // 2, tokens) tokens and exactly 2 n mel frames.
     The two length tensors are updated in place, as the reference does."""

@@ -13,7 +13,7 @@ SYMBOLS = [
     "cv2_engine_last_launches", "cv2_engine_set_option", "cv2_engine_read_ranges", "cv2_debug_set_ffn_trace", "cv2_engine_set_seed_ptr", "cv2_engine_set_profiling", "cv2_engine_read_profile", "cv2_estimator_workspace_bytes", "cv2_estimator_forward", "cv2_flow_workspace_bytes",
     "cv2_flow_forward", "cv2_stream_state_bytes", "cv2_stream_state_reset_slot", "cv2_flow_stream_workspace_bytes",
     "cv2_flow_forward_stream", "cv2_encoder_workspace_bytes", "cv2_encoder_forward", "cv2_hift_workspace_bytes", "cv2_hift_forward", "cv2_hift_forward_pcm16", "cv2_crossfade", "cv2_mel_time_stretch", "cv2_prompt_mel_frames", "cv2_prompt_mel_workspace_bytes",
-    "cv2_prompt_mel", "cv2_resample_16k_24k_len", "cv2_resample_16k_24k", "cv2_op_gemm_tap", "cv2_op_flash_attn",
+    "cv2_prompt_mel", "cv2_kaldi_fbank_frames", "cv2_kaldi_fbank", "cv2_resample_16k_24k_len", "cv2_resample_16k_24k", "cv2_op_gemm_tap", "cv2_op_flash_attn",
     "cv2_op_rel_attn", "cv2_op_source_stft", "cv2_op_istft", "cv2_op_nsf_source",
 ]
 
@@ -75,6 +75,8 @@ def load():
     lib.cv2_prompt_mel_workspace_bytes.argtypes = [i32, i32]
     lib.cv2_prompt_mel_workspace_bytes.restype = sz
     lib.cv2_prompt_mel.argtypes = [vp, vp, i64, vp, i32, i32, vp, vp, vp, sz]
+    lib.cv2_kaldi_fbank_frames.argtypes = [i32]
+    lib.cv2_kaldi_fbank.argtypes = [vp, vp, i64, vp, i32, i32, vp, vp, i32]
     lib.cv2_resample_16k_24k_len.argtypes = [i32]
     lib.cv2_resample_16k_24k.argtypes = [vp, vp, i64, vp, i32, i32, vp, i64, vp]
     lib.cv2_op_gemm_tap.argtypes = [vp, vp, i32, i32, i32, i64, vp, i32, i32, vp, i32, i32, C.POINTER(i32), vp, i32, vp, vp, f32,

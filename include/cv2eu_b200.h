@@ -151,6 +151,15 @@ size_t cv2_prompt_mel_workspace_bytes(int B, int max_samples);
 int cv2_prompt_mel(void* stream, const float* wav, long long wav_stride, const int32_t* n_samples, int B, int max_samples,
                    float* mel, int32_t* mel_len, void* workspace, size_t workspace_bytes);
 
+/* x-vector features: what CosyVoiceFrontEnd._extract_spk_embedding hands the CAM++ session
+ * (cosyvoice/cli/frontend.py:276-278): torchaudio.compliance.kaldi.fbank(speech, num_mel_bins=80, dither=0,
+ * sample_frequency=16000) and, with subtract_mean != 0, `feat - feat.mean(dim=0)`.  wav16: [B, wav_stride] fp32 device at
+ * 16 kHz, n_samples: [B] int32 device, max_samples: the largest (host, >= 400); feat: [B, cv2_kaldi_fbank_frames(max_samples), 80]
+ * fp32 device (rows past an utterance's own frames are zero), feat_len: [B] int32 device or NULL. */
+int cv2_kaldi_fbank_frames(int n_samples);
+int cv2_kaldi_fbank(void* stream, const float* wav16, long long wav_stride, const int32_t* n_samples, int B, int max_samples,
+                    float* feat, int32_t* feat_len, int subtract_mean);
+
 /* 16 kHz -> 24 kHz resampling of the prompt, replacing torchaudio.transforms.Resample(orig_freq=16000, new_freq=24000)
  * (cosyvoice/cli/frontend.py:495,541; sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99).  wav16: [B, in_stride] fp32 device,
  * n_in: [B] int32 device, max_in: the largest (host); wav24: [B, out_stride] fp32 device with out_stride >=
