@@ -149,8 +149,17 @@ struct Engine {
   // A: 16-bit [S, T_alloc, ld] (first Kc columns used).  Remaining epilogue fields come in through `p`.
   void gemm(cudaStream_t st, const __half* A, int S, int T_alloc, int Kc, long long ldA, Weight& w, int bn, int ntaps,
             const int* tap_off, GemmParams p, bool dry);
-  // fused FF1 -> GELU -> FF2 -> +residual -> emits (H: 16-bit [S, T_alloc, 256])
-  void ffn(cudaStream_t st, const __half* H, int S, int T_alloc, Weight& w1, Weight& w2, FfnParams p, bool dry);
+  // fused FF1 -> GELU -> FF2 -> +residual -> emits (H: 16-bit [S, T_alloc, 256]).  With `op` the attention out-projection
+  // (x += Wo att + bo, H = LayerNorm3(x)) belongs to the call: chained into the 2-SM kernel when that one runs, else launched
+  // as the separate GEMM in front of the 1-SM kernel.
+  struct OutProj {
+    const __half* att;   // [S, T_alloc, 512]
+    Weight* wo;          // [256, 512] (+ bias)
+    LN ln3;
+    float eps;
+  };
+  void ffn(cudaStream_t st, __half* H, int S, int T_alloc, Weight& w1, Weight& w2, FfnParams p, bool dry, const OutProj* op = nullptr);
+  bool chain_outproj = getenv("CV2_NO_OUTPROJ_CHAIN") == nullptr;
   const CUtensorMap& amap(const __half* A, int S, int T_alloc, int Kc, long long ldA);
   const CUtensorMap& wmap(Weight& w, int bn);
 };

@@ -70,12 +70,25 @@ const CUtensorMap& Engine::amap(const __half* A, int S, int T_alloc, int Kc, lon
   return it->second;
 }
 
-void Engine::ffn(cudaStream_t st, const __half* H, int S, int T_alloc, Weight& w1, Weight& w2, FfnParams p, bool dry) {
+void Engine::ffn(cudaStream_t st, __half* H, int S, int T_alloc, Weight& w1, Weight& w2, FfnParams p, bool dry, const OutProj* op) {
   CV2_CHECK(w1.N == 1024 && w1.Ktot == 256 && w2.N == 256 && w2.Ktot == 1024, "ffn: unexpected weight shapes");
   p.S = S;
   p.T_alloc = T_alloc;
   p.b1 = w1.b;
   p.b2 = w2.b;
+  const bool two_sm = ffn_2cta && S > 1 && p.lens && (long long)S * (T_alloc / 128) >= min_2sm_tiles;
+  const bool chain = op && two_sm && chain_outproj && op->wo->b;
+  if (op && !chain) {   // the out-projection as its own GEMM: + bias + residual -> x32 ; emit LayerNorm3 -> H
+    static const int tap1[1] = {0};
+    GemmParams g;
+    memset(&g, 0, sizeof(g));
+    g.lens = p.lens; g.len_all = p.len_all; g.halo = p.halo; g.out_scale = 1.f;
+    g.res = p.x32; g.res_ld = 256;
+    g.out32 = p.x32; g.out32_ld = 256;
+    g.emit[0].ptr = H; g.emit[0].ld = 256; g.emit[0].kind = EMIT_LN; g.emit[0].a = op->ln3.g; g.emit[0].b = op->ln3.b;
+    g.emit[0].f = op->eps; g.emit[0].scale = 1.f;
+    gemm(st, op->att, S, T_alloc, 512, 512, *op->wo, 256, 1, tap1, g, dry);
+  }
   launches++;
   if (dry) return;
   if (p.lens && !p.tile_list && S > 1) {
@@ -85,12 +98,17 @@ void Engine::ffn(cudaStream_t st, const __half* H, int S, int T_alloc, Weight& w
       p.tile_count = tl->second.count;
     }
   }
-  const CUtensorMap& th = amap(H, S, T_alloc, 256, 256);
   prof_begin(st, F_FFN_FUSED);
-  if (ffn_2cta && p.tile_list && (long long)S * (T_alloc / 128) >= min_2sm_tiles) {
-    launch_ffn_fused2(th, wmap(w1, 64), wmap(w2, 128), p, st);   // 2-SM MMAs, each CTA stages half of every weight tile
+  if (two_sm && p.tile_list) {
+    if (chain) {   // out-projection chained in front: H never exists in global memory
+      p.bo = op->wo->b; p.ln3_g = op->ln3.g; p.ln3_b = op->ln3.b; p.ln3_eps = op->eps;
+      launch_ffn_fused2_chain(amap(op->att, S, T_alloc, 512, 512), wmap(*op->wo, 128), wmap(w1, 64), wmap(w2, 128), p, st);
+    } else {
+      launch_ffn_fused2(amap(H, S, T_alloc, 256, 256), wmap(w1, 64), wmap(w2, 128), p, st);   // 2-SM MMAs, half of every weight tile per CTA
+    }
   } else {
-    launch_ffn_fused(th, wmap(w1, 128), wmap(w2, 128), p, st);
+    CV2_CHECK(!chain, "ffn: chained out-projection without a tile list");
+    launch_ffn_fused(amap(H, S, T_alloc, 256, 256), wmap(w1, 128), wmap(w2, 128), p, st);
   }
   prof_end(st);
   if (range_check) {

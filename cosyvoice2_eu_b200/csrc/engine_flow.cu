@@ -160,7 +160,7 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
           e.range_scan(st, Engine::R_ATTN_OUT, b.ATT16, (long long)S * T, 512, 512);
         }
       }
-      {  // out-proj + bias + residual ; emit LN(norm3)
+      if (!e.fuse_ffn) {  // out-proj + bias + residual ; emit LN(norm3)  (with the fused FFN it belongs to e.ffn below)
         GemmParams p = base_params(lens, kEstHalo);
         p.res = b.X32; p.res_ld = 256;
         p.out32 = b.X32; p.out32_ld = 256;
@@ -181,7 +181,8 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
         } else {
           fp.emit_plain[0] = emit_plain(b.M16, 256);
         }
-        e.ffn(st, b.H16, S, T, e.W(tp + ".ff1"), e.W(tp + ".ff2"), fp, dry);
+        Engine::OutProj op{b.ATT16, &e.W(tp + ".o"), e.ln(tp + ".ln3"), 1e-5f};
+        e.ffn(st, b.H16, S, T, e.W(tp + ".ff1"), e.W(tp + ".ff2"), fp, dry, &op);
         continue;
       }
       {  // FF1 + exact GELU

@@ -19,6 +19,13 @@ struct FfnParams {
   float* x32;               // [S*T_alloc, 256] residual stream, updated in place
   Emit emit_ln;             // ptr != null: LayerNorm(x; a = gamma, b = beta, f = eps) -> 16-bit
   Emit emit_plain[2];       // ptr != null: masked x -> 16-bit (ld / col_off honoured)
+  // chained attention out-projection (2-SM kernel only): the tile first computes x <- x + Wo att + bo into the (still free)
+  // FF1 accumulators, writes x back once and builds h = LayerNorm3(x) as the 128B-swizzled 16-bit H tile directly in shared
+  // memory -- no separate out-proj launch, no 16-bit h round trip through HBM (transformer.py:274, 291-314)
+  const float* bo;          // [256] out-proj bias; null: H comes from global memory (tmH) as before
+  const float* ln3_g;       // [256] LayerNorm3 gamma / beta / eps
+  const float* ln3_b;
+  float ln3_eps;
   long long* trace;         // debug: CTA 0 logs (clock64 << 8 | event code) for its MMA thread [0, 4096) and first epilogue warp
                             // [4096, 8192) (profiles/ffn_trace.py); null in production
 };
@@ -32,5 +39,8 @@ void launch_ffn_fused(const CUtensorMap& tmH, const CUtensorMap& tmW1, const CUt
 // tmW2h: {1024, 256} box {64, 128}.  Requires the compact tile list.
 void launch_ffn_fused2(const CUtensorMap& tmH, const CUtensorMap& tmW1h, const CUtensorMap& tmW2h, const FfnParams& p,
                        cudaStream_t stream);
+// chained form (p.bo != null): tmATT: 3-D {512, T_alloc, S} box {64,128,1} over the attention output; tmWoh: {512, 256} box {64, 128}
+void launch_ffn_fused2_chain(const CUtensorMap& tmATT, const CUtensorMap& tmWoh, const CUtensorMap& tmW1h, const CUtensorMap& tmW2h,
+                             const FfnParams& p, cudaStream_t stream);
 
 }  // namespace cv2

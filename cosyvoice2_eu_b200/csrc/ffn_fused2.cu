@@ -22,9 +22,10 @@ static constexpr int kSlotBytes = 16384;        // remaining shared memory is we
 static constexpr int kOffW = kHBytes;
 static constexpr int kEpiW = 16;                 // epilogue warps: four per TMEM lane quarter
 static constexpr int kOffRed = kOffW + kSlots * kSlotBytes;
-static constexpr int kOffBar = kOffRed + 2 * 2 * 4 * 128 * 4;   // (sum, sum of squares) x [4][128], double-buffered by tile parity
-static constexpr int kOffVec = kOffBar + 256;       // b1 [1024] | b2 [256] | next pre-norm gamma [256] | beta [256], staged once per CTA
-static constexpr int kFfnSmem = kOffVec + (1024 + 3 * 256) * 4;
+static constexpr int kOffRed2 = kOffRed + 2 * 2 * 4 * 128 * 4;  // (sum, sum of squares) x [4][128], double-buffered by tile parity
+static constexpr int kOffBar = kOffRed2 + 2 * 2 * 4 * 128 * 4;  // second set: LayerNorm3 of the chained out-projection
+static constexpr int kOffVec = kOffBar + 256;       // b1 [1024] | b2 [256] | next pre-norm gamma [256] | beta [256] | bo | ln3 gamma | beta
+static constexpr int kFfnSmem = kOffVec + (1024 + 6 * 256) * 4;
 static constexpr int kFfnThreads = 64 + kEpiW * 32;
 static constexpr uint32_t kAcc1 = 0, kAcc2 = 256;   // TMEM columns: acc1 = 2 x 128, acc2 = 256
 
@@ -74,9 +75,17 @@ __device__ __forceinline__ void lds32(const float* sv, float* d) {
   }
 }
 
+// release at cluster scope: the peer's generic-proxy writes to ITS shared memory (the H tile it built) must be visible to the
+// MMA the leader issues for both SMs after observing the barrier
+__device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
+// CHAIN: tmH is the attention output [S, T_alloc, 512] (A operand of the out-projection), tmWo the out-proj weight halves.
+template <bool CHAIN>
 __global__ void __launch_bounds__(kFfnThreads, 1)
-ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW1,
-                 const __grid_constant__ CUtensorMap tmW2, const FfnParams p) {
+ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmWo,
+                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const FfnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];   // 1024 B alignment for the 128B-swizzle atoms
   float* red = reinterpret_cast<float*>(smem + kOffRed);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
@@ -90,11 +99,12 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
   uint64_t* f_seen = f_full + 1;           // MMA thread has observed f_full of a chunk (keeps f_full at most one phase ahead)
   uint64_t* acc2_full = f_seen + 1;
   uint64_t* acc2_empty = acc2_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
+  uint64_t* op_full = acc2_empty + 1;      // CHAIN: out-projection accumulator complete (multicast commit)
+  uint64_t* h_ready = op_full + 1;         // CHAIN: leader only -- both CTAs' epilogue warps have built their H tile in smem
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int t_tiles = p.T_alloc / 128;
   const int row_tiles = __ldg(p.tile_count);                 // (the 2-SM path requires the compact tile list)
   const int total_tiles = (row_tiles + 1) / 2;                // pair units
   const uint32_t rank = cluster_ctarank();
@@ -105,6 +115,9 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
   float* vec_b2 = vec_b1 + 1024;
   float* vec_g = vec_b2 + 256;
   float* vec_b = vec_g + 256;
+  float* vec_bo = vec_b + 256;
+  float* vec_g3 = vec_bo + 256;
+  float* vec_b3 = vec_g3 + 256;
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
     vec_b1[i] = __ldg(p.b1 + i);
     if (i < 256) {
@@ -113,10 +126,16 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         vec_g[i] = __ldg(p.emit_ln.a + i);
         vec_b[i] = __ldg(p.emit_ln.b + i);
       }
+      if (CHAIN) {
+        vec_bo[i] = __ldg(p.bo + i);
+        vec_g3[i] = __ldg(p.ln3_g + i);
+        vec_b3[i] = __ldg(p.ln3_b + i);
+      }
     }
   }
   if (warp == kEpiW && lane == 0) {
     tma_prefetch_desc(&tmH);
+    if (CHAIN) tma_prefetch_desc(&tmWo);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     mbar_init(h_full, 1);          // leader only: its producer's arrive.expect_tx (bytes of BOTH CTAs)
@@ -133,6 +152,8 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
     mbar_init(f_seen, 1);          // leader's MMA thread arrives in both CTAs
     mbar_init(acc2_full, 1);       // multicast commit
     mbar_init(acc2_empty, 2 * kEpiW);   // leader only
+    mbar_init(op_full, 1);              // multicast commit
+    mbar_init(h_ready, 2 * kEpiW);      // leader only
     fence_barrier_init();
   }
   if (warp == kEpiW + 1) {         // both CTAs, same warp id, same destination
@@ -154,10 +175,26 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         int s, t0, len;
         ffn2_tile(p, unit, rank, row_tiles, s, t0, len);
         prefetch_l2_bulk(p.x32 + ((long long)s * p.T_alloc + t0) * 256, 128 * 256 * 4);
-        mbar_wait(h_empty, (lt & 1) ^ 1);
-        if (leader) mbar_expect_tx(h_full, 2 * kHBytes);
+        if (!CHAIN) {
+          mbar_wait(h_empty, (lt & 1) ^ 1);
+          if (leader) mbar_expect_tx(h_full, 2 * kHBytes);
 #pragma unroll
-        for (int kb = 0; kb < 4; kb++) tma2_load_3d(smem + kb * 16384, &tmH, h_full, kb * 64, t0, s);
+          for (int kb = 0; kb < 4; kb++) tma2_load_3d(smem + kb * 16384, &tmH, h_full, kb * 64, t0, s);
+        } else {
+          // out-projection operands through the weight ring, two slots per 64-wide k-block: this CTA's [128 rows x 64] slice
+          // of the attention output, and its 128 of the 256 output rows of Wo
+          for (int kb = 0; kb < 8; kb++) {
+#pragma unroll
+            for (int i = 0; i < 2; i++, wit++) {
+              const int st = wit % kSlots;
+              mbar_wait(&w_empty[st], ((wit / kSlots) & 1) ^ 1);
+              if (leader) mbar_expect_tx(&w_full[st], 2 * kSlotBytes);
+              uint8_t* dst = smem + kOffW + st * kSlotBytes;
+              if (i == 0) tma2_load_3d(dst, &tmH, &w_full[st], kb * 64, t0, s);
+              else tma2_load_2d(dst, &tmWo, &w_full[st], kb * 64, (int)rank * 128);
+            }
+          }
+        }
         for (int o = 0; o < 16; o++) {
           bool is_ff2;
           int c;
@@ -257,7 +294,32 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       };
       for (int unit = unit0; unit < total_tiles; unit += unit_step) {
         ffn_trace(tb, ti, 1);
-        mbar_wait(h_full, lt & 1);
+        if (!CHAIN) {
+          mbar_wait(h_full, lt & 1);
+        } else {
+          // out-projection into the 256 columns of the two FF1 accumulators: they are free -- the last readers, FF2(6) / FF2(7) of
+          // the previous unit, were issued earlier on the same in-order pipe
+          w_ready = false;
+#pragma unroll 1
+          for (int kb = 0; kb < 8; kb++) {
+            const int stA = wit % kSlots;
+            const uint64_t a_desc = umma_smem_desc_sw128(slot_begin());
+            wit++;
+            const int stB = wit % kSlots;
+            const uint64_t b_desc = umma_smem_desc_sw128(slot_begin());
+            wit++;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              umma2_f16(tmem_base + kAcc1, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc2, (kb | k) != 0);
+            umma2_commit(&w_empty[stA]);
+            umma2_commit(&w_empty[stB]);
+          }
+          umma2_commit(op_full);
+          w_ready = false;
+          mbar_wait(h_ready, lt & 1);       // both CTAs have added the residual and written LayerNorm3(x) as their H tile
+          asm volatile("fence.acq_rel.cluster;" ::: "memory");
+          tc_fence_after();
+        }
         ffn_trace(tb, ti, 2);
         // schedule: FF1(0) FF1(1) | FF2(0) FF1(2) | FF2(1) FF1(3) | ... | FF2(5) FF1(7) | FF2(6) FF2(7)
         ff1(0, false);
@@ -295,6 +357,74 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       const bool valid = t < len;
       const long long row = (long long)s * p.T_alloc + t;
       const long long row0 = row - lane;
+      if (CHAIN) {
+        // ---- chained out-projection: x <- acc + bo + x (written back once), H = LayerNorm3(x) as the swizzled 16-bit A tile ----
+        mbar_wait(op_full, lt & 1);
+        tc_fence_after();
+        mbar_wait(h_empty, (lt & 1) ^ 1);      // FF1(7) of the previous unit has read the H tile
+        const uint32_t oaddr = lane_addr + kAcc1 + part * 64;
+        float sum3 = 0.f, sq3 = 0.f;
+        uint32_t raw[32];
+        float v[32], tmp[32];
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ch++) {
+          const int cbase = part * 64 + ch * 32;
+          tmem_ld32(oaddr + ch * 32, raw);
+          lds32(vec_bo + cbase, tmp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]) + tmp[i];
+          tile_load_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, tmp);
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] += tmp[i];
+          if (tile_ok) tile_store_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, v);
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            sum3 += v[i];
+            sq3 = fmaf(v[i], v[i], sq3);
+            raw[i] = __float_as_uint(v[i]);
+          }
+          tmem_st32(oaddr + ch * 32, raw);
+        }
+        tmem_st_wait();
+        float* r3c = reinterpret_cast<float*>(smem + kOffRed2) + (lt & 1) * 1024;
+        float* r3d = r3c + 512;
+        r3c[part * 128 + r] = sum3;
+        r3d[part * 128 + r] = sq3;
+        ffn_bar();
+        const float mean3 = (r3c[r] + r3c[128 + r] + r3c[256 + r] + r3c[384 + r]) * (1.f / 256.f);
+        const float rstd3 = rsqrtf(fmaxf((r3d[r] + r3d[128 + r] + r3d[256 + r] + r3d[384 + r]) * (1.f / 256.f) - mean3 * mean3, 0.f) + p.ln3_eps);
+        // K-major 128B-swizzled atom `part` (columns 64 part .. 64 part + 63): row r at r * 128 B, 16-byte chunk j at (j ^ (r & 7))
+        uint8_t* hrow = smem + part * 16384 + r * 128;
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ch++) {
+          const int cbase = part * 64 + ch * 32;
+          tmem_ld32(oaddr + ch * 32, raw);
+          float gg[32], w[32];
+          lds32(vec_g3 + cbase, gg);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) w[i] = (__uint_as_float(raw[i]) - mean3) * rstd3 * gg[i];
+          lds32(vec_b3 + cbase, gg);
+#pragma unroll
+          for (int i = 0; i < 32; i++) w[i] = valid ? (w[i] + gg[i]) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            uint4 u;
+            __half2 h0 = __floats2half2_rn(w[j * 8 + 0], w[j * 8 + 1]), h1 = __floats2half2_rn(w[j * 8 + 2], w[j * 8 + 3]);
+            __half2 h2 = __floats2half2_rn(w[j * 8 + 4], w[j * 8 + 5]), h3 = __floats2half2_rn(w[j * 8 + 6], w[j * 8 + 7]);
+            u.x = *reinterpret_cast<uint32_t*>(&h0);
+            u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2);
+            u.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(hrow + (((ch * 4 + j) ^ (r & 7)) << 4)) = u;
+          }
+        }
+        fence_proxy_async_smem();            // generic-proxy writes of H -> visible to the tensor core's async-proxy reads
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader_release(h_ready);
+      }
       // ---- 8 hidden chunks: bias + GELU -> 16-bit chunk in shared memory (A operand of FF2) ----
       for (int c = 0; c < 8; c++, g++) {
         const int b = c & 1;
@@ -416,13 +546,15 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
 
 extern long long* g_ffn_trace_ptr();
 
-void launch_ffn_fused2(const CUtensorMap& tmH, const CUtensorMap& tmW1h, const CUtensorMap& tmW2h, const FfnParams& p_in,
-                       cudaStream_t stream) {
+template <bool CHAIN>
+static void launch_ffn2(const CUtensorMap& tmH, const CUtensorMap& tmWo, const CUtensorMap& tmW1h, const CUtensorMap& tmW2h,
+                        const FfnParams& p_in, cudaStream_t stream) {
   static PerDeviceOnce once;
   static int max_clusters = 0;   // every device of a box is the same part
   FfnParams p = p_in;
   p.trace = g_ffn_trace_ptr();
   CV2_CHECK(p.tile_list && p.tile_count && p.lens, "ffn_fused2: the 2-SM path needs the compact tile list");
+  CV2_CHECK(!CHAIN || (p.bo && p.ln3_g && p.ln3_b), "ffn_fused2: chained out-projection needs its bias and LayerNorm3 vectors");
   cudaLaunchConfig_t q = {};
   q.blockDim = dim3(kFfnThreads);
   q.dynamicSmemBytes = kFfnSmem;
@@ -433,20 +565,30 @@ void launch_ffn_fused2(const CUtensorMap& tmH, const CUtensorMap& tmW1h, const C
   q.attrs = at;
   q.numAttrs = 1;
   once.run([&] {
-    CV2_CUDA(cudaFuncSetAttribute(ffn_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem));
+    CV2_CUDA(cudaFuncSetAttribute(ffn_fused2_kernel<CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem));
     int dev = 0, sms = 0;
     CV2_CUDA(cudaGetDevice(&dev));
     CV2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     q.gridDim = dim3(sms / 2 * 2);
-    CV2_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, ffn_fused2_kernel, &q));
+    CV2_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, ffn_fused2_kernel<CHAIN>, &q));
     CV2_CHECK(max_clusters > 0, "ffn_fused2: no 2-CTA cluster fits");
   });
   CV2_CHECK(p.T_alloc % 128 == 0, "ffn_fused2: T_alloc %d not a multiple of 128", p.T_alloc);
   const int units = ((p.T_alloc / 128) * p.S + 1) / 2;
   const int clusters = units < max_clusters ? units : max_clusters;
   q.gridDim = dim3(2 * clusters);
-  CV2_CUDA(cudaLaunchKernelEx(&q, ffn_fused2_kernel, tmH, tmW1h, tmW2h, p));
+  CV2_CUDA(cudaLaunchKernelEx(&q, ffn_fused2_kernel<CHAIN>, tmH, tmWo, tmW1h, tmW2h, p));
   CV2_LAUNCH_CHECK();
+}
+
+void launch_ffn_fused2(const CUtensorMap& tmH, const CUtensorMap& tmW1h, const CUtensorMap& tmW2h, const FfnParams& p,
+                       cudaStream_t stream) {
+  launch_ffn2<false>(tmH, tmW1h /* unused */, tmW1h, tmW2h, p, stream);
+}
+
+void launch_ffn_fused2_chain(const CUtensorMap& tmATT, const CUtensorMap& tmWoh, const CUtensorMap& tmW1h, const CUtensorMap& tmW2h,
+                             const FfnParams& p, cudaStream_t stream) {
+  launch_ffn2<true>(tmATT, tmWoh, tmW1h, tmW2h, p, stream);
 }
 
 }  // namespace cv2

@@ -793,3 +793,32 @@ def test_incremental_stream_batch_equals_prefix_recompute(engine):
         for a, b in zip(got[si], want[si]):
             assert a.shape == b.shape
             assert snr_db(b.numpy(), a.numpy()) > 50
+
+
+def test_chained_out_projection_matches_separate_launch(engine, golden):
+    """The attention out-projection chained into the 2-SM FFN kernel (x += Wo att + bo in the FF1 accumulators, LayerNorm3 written
+    straight into the swizzled shared-memory H tile) against the separate out-proj GEMM + FFN launches: same operands, same
+    k order -- the mel must agree to rounding noise, and both match the reference."""
+    flow = engine[0]
+    lib = flow.eng.lib
+    g = golden("cfg1")
+    u = _utt(g)
+    utts = [_utt(dict(n_tok=240 + 3 * i, n_prompt=60, seed=40 + i)) for i in range(16)]    # 160 row tiles: 2-SM path, odd tails
+    args = ([x["token"][0] for x in utts], [x["prompt_token"][0] for x in utts], [x["prompt_feat"][0] for x in utts],
+            [x["embedding"][0] for x in utts])
+    mel_chain = flow.inference_batch(*args)[0].cpu().numpy()
+    assert lib.cv2_engine_set_option(flow.eng.h, b"min_2sm_tiles", 0) == 0
+    try:
+        one_chain, _ = flow.inference(u["token"], None, u["prompt_token"], None, u["prompt_feat"], None, u["embedding"], False, True)
+        assert lib.cv2_engine_set_option(flow.eng.h, b"chain_outproj", 0) == 0
+        one_sep, _ = flow.inference(u["token"], None, u["prompt_token"], None, u["prompt_feat"], None, u["embedding"], False, True)
+        mel_sep = flow.inference_batch(*args)[0].cpu().numpy()
+    finally:
+        lib.cv2_engine_set_option(flow.eng.h, b"chain_outproj", 1)
+        lib.cv2_engine_set_option(flow.eng.h, b"min_2sm_tiles", 148)
+    d_b = np.abs(mel_chain - mel_sep).max()
+    d_1 = float((one_chain - one_sep).abs().max())
+    print("chained vs separate out-projection: batch", d_b, "single utterance", d_1)
+    assert np.isfinite(mel_chain).all()
+    assert d_b < 2e-3 and d_1 < 2e-3
+    assert np.abs(one_chain.cpu().numpy() - g["mel"]).max() <= MEL_TOL
