@@ -63,7 +63,7 @@ def algorithmic_flops(n_tokens, n_prompt=N_PROMPT):
         ffn = 56 * 2 * 2 * 256 * 1024.0          # FF1 + FF2 of the 56 transformer blocks, per frame per CFG row
         fused = os.environ.get("CV2_NO_FFN_FUSION") is None
         # the attention out-projection (56 x [512 -> 256]) is chained into the FFN kernel on the 2-SM path (big launches)
-        outp = 56 * 2 * 512 * 256.0 if (fused and os.environ.get("CV2_NO_OUTPROJ_CHAIN") is None and len(n_tokens) >= 16) else 0.0
+        outp = 56 * 2 * 512 * 256.0 if (fused and os.environ.get("CV2_NO_OUTPROJ_CHAIN") is None) else 0.0
         f["gemm_tap<256>"] += 20 * T * (est_lin - 40960.0 - (ffn if fused else 0.0) - outp)
         f["ffn_fused"] += 20 * T * ((ffn if fused else 0.0) + outp)
         f["gemm_tap<128>"] += 20 * T * 40960.0

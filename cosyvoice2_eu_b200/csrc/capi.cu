@@ -120,6 +120,7 @@ int cv2_engine_set_option(cv2_engine* h, const char* name, int value) {
   else if (n == "cluster_mc") h->e.cluster_mc = value != 0;
   else if (n == "ffn_2cta") h->e.ffn_2cta = value != 0;
   else if (n == "min_2sm_tiles") h->e.min_2sm_tiles = value;
+  else if (n == "min_2sm_tiles_ffn") h->e.min_2sm_tiles_ffn = value;
   else if (n == "chain_outproj") h->e.chain_outproj = value != 0;
   else if (n == "range_check") {
     use_device(h);

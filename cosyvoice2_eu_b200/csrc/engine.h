@@ -82,7 +82,11 @@ struct Engine {
   std::unordered_map<std::string, Weight> weights;      // lazily built from tensors
   std::unordered_map<uint64_t, CUtensorMap> amap_cache;  // activation tensor maps
   long long launches = 0;                                // kernels launched by the last forward (claims for bench)
-  int min_2sm_tiles = 148;   // the 2-SM (cta_group::2) GEMM / FFN forms switch on at this many row tiles (one per SM)
+  // the 2-SM (cta_group::2) GEMM / FFN forms switch on at this many row tiles
+  int min_2sm_tiles = getenv("CV2_MIN_2SM_TILES") ? atoi(getenv("CV2_MIN_2SM_TILES")) : 148;
+  // ... and the fused FFN (whose 2-SM form also carries the chained out-projection: one launch less per transformer block,
+  // which is what a launch-latency-bound small batch needs) already at this many
+  int min_2sm_tiles_ffn = getenv("CV2_MIN_2SM_TILES_FFN") ? atoi(getenv("CV2_MIN_2SM_TILES_FFN")) : 2;
 
   // ---- opt-in fp16 range telemetry (option "range_check"): operands are fp16 (saturates at 65504), so a trained checkpoint
   //      can be checked for headroom: after every launch the 16-bit tensors it wrote are scanned for their max |x| ----

@@ -76,7 +76,7 @@ void Engine::ffn(cudaStream_t st, __half* H, int S, int T_alloc, Weight& w1, Wei
   p.T_alloc = T_alloc;
   p.b1 = w1.b;
   p.b2 = w2.b;
-  const bool two_sm = ffn_2cta && S > 1 && p.lens && (long long)S * (T_alloc / 128) >= min_2sm_tiles;
+  const bool two_sm = ffn_2cta && S > 1 && p.lens && (long long)S * (T_alloc / 128) >= (min_2sm_tiles < min_2sm_tiles_ffn ? min_2sm_tiles : min_2sm_tiles_ffn);
   const bool chain = op && two_sm && chain_outproj && op->wo->b;
   if (op && !chain) {   // the out-projection as its own GEMM: + bias + residual -> x32 ; emit LayerNorm3 -> H
     static const int tap1[1] = {0};
