@@ -4,7 +4,8 @@ prompts (oracle/make_golden_fbank.py); the numpy oracle and the CUDA kernel are 
 
 Tolerance: torchaudio works in fp32 through an FFT, so bins whose power sits within a few decades of the fp32 epsilon floor
 (log value < -10: digital silence, the stop band of a clean tone) carry its own rounding noise of ~1e-3; everywhere else the
-log-mel values agree to 1e-4."""
+float64 oracle agrees with it to 1e-4 and the fp32 kernel (two fp32 computations, each ~6e-5 from the float64 truth) to 3e-4
+on log-mel values that span +-10."""
 import numpy as np
 import pytest
 import torch
@@ -46,7 +47,7 @@ def test_gpu_fbank_matches_torchaudio(golden, name):
     from cosyvoice2_eu_b200 import extract_spk_feat
     g = golden("fbank")
     feat = extract_spk_feat(torch.from_numpy(g[f"{name}.wav"])[None])
-    _check(feat[0].cpu().numpy(), g, name)
+    _check(feat[0].cpu().numpy(), g, name, tol_hi=3e-4)
 
 
 @pytest.mark.gpu
@@ -65,7 +66,7 @@ def test_gpu_fbank_ragged_batch_equals_single_prompts(golden):
         k = int(feat_len[i])
         assert torch.equal(feat[i, :k], one)
         assert float(feat[i, k:].abs().max()) == 0.0 if k < feat.shape[1] else True
-        _check(feat[i, :k].cpu().numpy(), g, n)
+        _check(feat[i, :k].cpu().numpy(), g, n, tol_hi=3e-4)
 
 
 @pytest.mark.gpu
