@@ -349,6 +349,9 @@ def main():
     stop.set()
     h2d = flow.last_h2d_bytes
     d2h = out.numel() * 4 + 4 * B
+    workspace_gb = {}
+    for (kind, _), ent in eng.ws.items():
+        workspace_gb[kind] = max(workspace_gb.get(kind, 0.0), ent[0].numel() / 1e9)
 
     # ---- BASELINE configs[4]: a 4096-utterance corpus sharded by utterance over the ranks (strong scaling): cost-balanced
     #      shards, length-bucketed batches of <= 64 through the public batched API (host inputs), audio packed into one flat
@@ -473,6 +476,8 @@ def main():
         "hbm_kernels": hbm_kernels,
         "gemm256_by_epilogue": g256,
         "whole_step_tflops": total_flop / 1e12 / (ms / args.steps / 1e3) / world,
+        "whole_step_frac_of_peak": total_flop / 1e12 / (ms / args.steps / 1e3) / world / peak,
+        "workspace_gb": workspace_gb,
         "clocks": clocks_summary(clk),
     }
     if corpus:

@@ -29,8 +29,12 @@ static constexpr int kFfnSmem = kOffVec + (1024 + 6 * 256) * 4;
 static constexpr int kFfnThreads = 64 + kEpiW * 32;
 static constexpr uint32_t kAcc1 = 0, kAcc2 = 256;   // TMEM columns: acc1 = 2 x 128, acc2 = 256
 
-__device__ __forceinline__ void ffn_trace(long long* buf, int& idx, int code) {
-  if (buf && idx < 4095) buf[idx++] = (clock64() << 8) | code;
+__device__ __forceinline__ void ffn_trace(long long* buf, int& idx, int code, float dep = 0.f) {
+  if (buf && idx < 4095) {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "f"(dep) : "memory");   // `dep` orders the read after the value exists
+    buf[idx++] = (t << 8) | code;
+  }
 }
 __device__ __forceinline__ void ffn_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
@@ -164,7 +168,6 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
   cluster_sync();                  // the peer signals this CTA's barriers: everything must be initialised cluster-wide
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
   if (warp == kEpiW) {
     if (lane == 0) {
       // ------------------------------- TMA producer (both CTAs) --------------------
@@ -359,9 +362,11 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       const long long row0 = row - lane;
       if (CHAIN) {
         // ---- chained out-projection: x <- acc + bo + x (written back once), H = LayerNorm3(x) as the swizzled 16-bit A tile ----
+        ffn_trace(tb, ti, 30);
         mbar_wait(op_full, lt & 1);
         tc_fence_after();
         mbar_wait(h_empty, (lt & 1) ^ 1);      // FF1(7) of the previous unit has read the H tile
+        ffn_trace(tb, ti, 31);
         const uint32_t oaddr = lane_addr + kAcc1 + part * 64;
         float sum3 = 0.f, sq3 = 0.f;
         uint32_t raw[32];
@@ -387,11 +392,13 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           tmem_st32(oaddr + ch * 32, raw);
         }
         tmem_st_wait();
+        ffn_trace(tb, ti, 32);
         float* r3c = reinterpret_cast<float*>(smem + kOffRed2) + (lt & 1) * 1024;
         float* r3d = r3c + 512;
         r3c[part * 128 + r] = sum3;
         r3d[part * 128 + r] = sq3;
         ffn_bar();
+        ffn_trace(tb, ti, 33);
         const float mean3 = (r3c[r] + r3c[128 + r] + r3c[256 + r] + r3c[384 + r]) * (1.f / 256.f);
         const float rstd3 = rsqrtf(fmaxf((r3d[r] + r3d[128 + r] + r3d[256 + r] + r3d[384 + r]) * (1.f / 256.f) - mean3 * mean3, 0.f) + p.ln3_eps);
         // K-major 128B-swizzled atom `part` (columns 64 part .. 64 part + 63): row r at r * 128 B, 16-byte chunk j at (j ^ (r & 7))
@@ -424,6 +431,7 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader_release(h_ready);
+        ffn_trace(tb, ti, 34);
       }
       // ---- 8 hidden chunks: bias + GELU -> 16-bit chunk in shared memory (A operand of FF2) ----
       for (int c = 0; c < 8; c++, g++) {
@@ -483,10 +491,13 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]) + tmp[i];
+        ffn_trace(tb, ti, 23);
         tile_load_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, tmp);
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] += tmp[i];
+        ffn_trace(tb, ti, 24, v[0]);
         tile_store_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, v);
+        ffn_trace(tb, ti, 25);
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const Emit& em = p.emit_plain[e];
@@ -513,7 +524,9 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         red_d = red_c + 512;
         red_c[part * 128 + r] = sum2;
         red_d[part * 128 + r] = sq2;
+        ffn_trace(tb, ti, 26);
         ffn_bar();
+        ffn_trace(tb, ti, 27);
         const float mean2 = (red_c[r] + red_c[128 + r] + red_c[256 + r] + red_c[384 + r]) * (1.f / 256.f);
         const float rstd2 = rsqrtf(fmaxf((red_d[r] + red_d[128 + r] + red_d[256 + r] + red_d[384 + r]) * (1.f / 256.f) - mean2 * mean2, 0.f) + p.emit_ln.f);
 #pragma unroll 1
