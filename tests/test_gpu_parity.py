@@ -396,15 +396,18 @@ def test_speed_change_matches_linear_interpolation(engine, golden, speed):
     assert wav.shape == (1, 480 * T_out)
 
 
-def test_stream_scheduler_on_the_engine(engine, golden):
+@pytest.mark.parametrize("incremental", [False, True])
+def test_stream_scheduler_on_the_engine(engine, golden, incremental):
     """StreamScheduler (row F3) driving the real engine: three sessions fed token by token, chunks delivered through batched
     steps; the (70, 10) session's chunk shapes are the golden ones of the reference's own chunk loop, every session's audio adds
-    up to 2 * 480 samples per token, and the vocoder caches are gone afterwards."""
+    up to 2 * 480 samples per token, and the vocoder caches are gone afterwards.  With `incremental` the scheduler owns a
+    StreamGroup (row F1): same chunks, slots released at the end."""
     from cosyvoice2_eu_b200 import B200Token2Wav, StreamScheduler
     flow, hift, _ = engine
     g = golden("stream")
     t2w = B200Token2Wav(flow, hift)
-    sch = StreamScheduler(t2w, token_hop_len=25)
+    group = flow.open_stream_group(3, max_mel_frames=256) if incremental else None
+    sch = StreamScheduler(t2w, token_hop_len=25, group=group)
     specs = {"s0": (70, 10, 3), "s1": (95, 25, 8), "s2": (55, 12, 9)}
     utts = {u: _utt(dict(n_tok=n, n_prompt=p, seed=s)) for u, (n, p, s) in specs.items()}
     for u, ut in utts.items():
@@ -428,6 +431,8 @@ def test_stream_scheduler_on_the_engine(engine, golden):
         # (a crossfaded head is w0 * new + w1 * old of two signals clamped to 0.99: Hamming halves sum to at most 1.08)
         assert all(bool(torch.isfinite(c).all()) and float(c.abs().max()) <= 0.99 * 1.09 for c in chunks[u])
         assert u not in t2w.hift_cache_dict
+    if incremental:
+        assert not group.slots and len(group.free) == 3
 
 
 # ======================================================================================================================
