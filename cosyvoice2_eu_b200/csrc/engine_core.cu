@@ -57,13 +57,14 @@ const CUtensorMap& Engine::wmap(Weight& w, int bn) {
   return w.map[bi];
 }
 
-const CUtensorMap& Engine::amap(const __half* A, int S, int T_alloc, int Kc, long long ldA) {
-  uint64_t key = mix(mix(mix(mix(mix(0x1234, (uint64_t)(uintptr_t)A), (uint64_t)Kc), (uint64_t)ldA), (uint64_t)T_alloc), (uint64_t)S);
+const CUtensorMap& Engine::amap(const __half* A, int S, int T_alloc, int Kc, long long ldA, int box_rows) {
+  uint64_t key = mix(mix(mix(mix(mix(mix(0x1234, (uint64_t)(uintptr_t)A), (uint64_t)Kc), (uint64_t)ldA), (uint64_t)T_alloc), (uint64_t)S),
+                     (uint64_t)box_rows);
   auto it = amap_cache.find(key);
   if (it == amap_cache.end()) {
     uint64_t dims[3] = {(uint64_t)Kc, (uint64_t)T_alloc, (uint64_t)S};
     uint64_t strides[2] = {(uint64_t)ldA * 2, (uint64_t)T_alloc * (uint64_t)ldA * 2};
-    uint32_t box[3] = {64, 128, 1};
+    uint32_t box[3] = {64, (uint32_t)box_rows, 1};
     if (amap_cache.size() > 8192) amap_cache.clear();
     it = amap_cache.emplace(key, make_tmap_16b(A, 3, dims, strides, box)).first;
   }
@@ -149,7 +150,14 @@ void Engine::gemm(cudaStream_t st, const __half* A, int S, int T_alloc, int Kc, 
   { static const int dbg = getenv("CV2_DBG_SKIP_EPI") ? atoi(getenv("CV2_DBG_SKIP_EPI")) : 0; p.dbg_skip_epi = (dbg == 1) || (dbg == 2 && p.q != nullptr) || (dbg == 3 && p.res != nullptr); }
   if (cluster_mc && bn == 256 && p.tile_list && (long long)S * (T_alloc / 128) >= min_2sm_tiles) p.tmB_half = &wmap(w, 128);
   const CUtensorMap& tb = wmap(w, bn);
-  const CUtensorMap& ta = amap(A, p.S_map > 0 ? p.S_map : S, T_alloc, Kc, ldA);
+  const CUtensorMap ta = amap(A, p.S_map > 0 ? p.S_map : S, T_alloc, Kc, ldA);   // (copies: the cache may be flushed by the next lookup)
+  CUtensorMap ta_halo;
+  if (conv_mode && gemm_tap_conv_eligible(bn, p)) {   // k-tap conv of a narrow vocoder stage: one A box per k-block, resident weights
+    ta_halo = amap(A, S, T_alloc, Kc, ldA, kConvHaloRows);
+    p.tmA_halo = &ta_halo;
+    p.conv_min_off = p.tap_off[0];
+    for (int i = 1; i < ntaps; i++) p.conv_min_off = p.tap_off[i] < p.conv_min_off ? p.tap_off[i] : p.conv_min_off;
+  }
   prof_begin(st, bn == 256 ? F_COUNT + gemm_tap_spec(bn, p) : bi);
   launch_gemm_tap(bn, ta, tb, p, st);
   prof_end(st);

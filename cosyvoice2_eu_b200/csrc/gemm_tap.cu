@@ -44,6 +44,24 @@ struct GemmSmem {
   static constexpr int kTotal = kVecOff + (kVecBias + 4 * kVecLn) * 4;
 };
 
+// conv mode (GemmParams::tmA_halo): ring of [192 x 64] A boxes + the resident weight matrix
+template <int BN>
+struct GemmSmemConv {
+  static constexpr int kParts = BN >= 128 ? 4 : 2;
+  static constexpr int kEpiWarps = 4 * kParts;
+  static constexpr int kThreads = 64 + kEpiWarps * 32;
+  static constexpr int kGroups = 1;   // (two epilogue groups, one per accumulator buffer, were measured neutral here: 22.0 vs 22.3 ms)
+  static constexpr int kStageBytes = kConvHaloRows * kKBlock * 2;   // 24 KB
+  static constexpr int kStages = 4;
+  static constexpr int kWOff = kStages * kStageBytes;               // resident weights: [ntaps * kb_per_tap][BN x 64]
+  static constexpr int kWBytes = 96 * 1024;
+  static constexpr int kRedOff = kWOff + kWBytes;
+  static constexpr int kBarOff = kRedOff + 2 * 4 * kParts * 128 * 4;
+  static constexpr int kVecBias = 2048, kVecLn = 256;
+  static constexpr int kVecOff = kBarOff + 512;
+  static constexpr int kTotal = kVecOff + (kVecBias + 4 * kVecLn) * 4;
+};
+
 template <int NT>
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
@@ -106,10 +124,16 @@ using EpiGeneric = EpiCfg<-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1
 // CTAs (stage free, accumulator full) and the peer's epilogue warps release accumulators on the leader's barrier.
 // Why: in cta_group::1 form these short-K GEMMs run the tensor pipe at ~55 % (issue path: profiles/micro/mma_bubble.cu); the
 // 2-SM form does twice the work per instruction and sustains the nominal rate (profiles/micro/mma_2cta.cu).
-template <int BN, class Cfg, int CS>
+template <int BN, int CS, bool CONV>
+struct SmemOf { using type = GemmSmem<BN, CS>; };
+template <int BN, int CS>
+struct SmemOf<BN, CS, true> { using type = GemmSmemConv<BN>; };
+
+template <int BN, class Cfg, int CS, bool CONV = false>
 __global__ void __launch_bounds__(GemmSmem<BN, CS>::kThreads, 1)
 gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using SM = GemmSmem<BN, CS>;
+  using SM = typename SmemOf<BN, CS, CONV>::type;
+  static_assert(!CONV || CS == 1, "conv mode is a 1-SM form (its 2-SM form was built and measured no faster: 23.0 vs 22.3 ms)");
   constexpr int kStages = SM::kStages;
   constexpr int kEpiWarps = SM::kEpiWarps;
   constexpr int kParts = SM::kParts;
@@ -120,6 +144,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_full = empty_bar + kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + SM::kBarOff + 256);   // conv mode: resident weights have landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -169,6 +194,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(&tmem_full[i], 1);               // CS = 2: multicast commit
       mbar_init(&tmem_empty[i], CS * kEpiWarps / SM::kGroups); // released by the warps of the owning group (CS = 2: of both CTAs, on the leader's)
     }
+    if (CONV) mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   if (warp == kEpiWarps + 1) {
@@ -185,6 +211,24 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       // ------------------------------- TMA producer -------------------------------
       int kit = 0;
+      if constexpr (CONV) {
+        // the whole weight matrix once (N <= BN: one n tile), then per tile and k-block ONE [192 x 64] box of A rows
+        // t0 + min_off .. t0 + min_off + 191 that serves every tap
+        constexpr int kWTile = BN * kKBlock * 2;   // one [BN x 64] weight tile
+        mbar_expect_tx(w_bar, (uint32_t)(num_it * kWTile));
+        for (int it = 0; it < num_it; it++) tma_load_2d(smem + SM::kWOff + it * kWTile, &tmB, w_bar, it * kKBlock, 0);
+        for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+          TileCoord c;
+          bool tvalid;
+          if (!tile_coord<CS>(p, tile, n_tiles, t_tiles, BN, rank, row_count, c, tvalid)) continue;
+          for (int kb = 0; kb < p.kb_per_tap; kb++, kit++) {
+            const int st = kit % kStages;
+            mbar_wait(&empty_bar[st], ((kit / kStages) & 1) ^ 1);
+            mbar_expect_tx(&full_bar[st], SM::kStageBytes);
+            tma_load_3d(smem + st * SM::kStageBytes, &tmA, &full_bar[st], kb * kKBlock, c.t0 + p.conv_min_off, c.s);
+          }
+        }
+      } else
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         TileCoord c;
         bool tvalid;
@@ -226,6 +270,28 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         gtrace(tb, ti, 2);
         const uint32_t d_tmem = tmem_base + acc * BN;
+        if constexpr (CONV) {
+          if (lt == 0) mbar_wait(w_bar, 0);
+          const uint32_t w_addr = smem_u32(smem + SM::kWOff);
+          for (int kb = 0; kb < p.kb_per_tap; kb++, kit++) {
+            const int st = kit % kStages;
+            mbar_wait(&full_bar[st], (kit / kStages) & 1);
+            tc_fence_after();
+            const uint32_t box = smem_u32(smem + st * SM::kStageBytes);
+            for (int tap = 0; tap < p.ntaps; tap++) {
+              // rows of this tap start (off - min_off) rows into the box: a descriptor whose start is not 1024-byte aligned
+              const uint32_t a_addr = box + (uint32_t)(p.tap_off[tap] - p.conv_min_off) * 128u;
+              // (the tensor core applies the 128B swizzle to ABSOLUTE shared-memory address bits, exactly like the TMA write did:
+              // measured -- with the descriptor's "matrix base offset" field set to (start >> 7) & 7 the result is wrong)
+              const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
+              const uint64_t b_desc = umma_smem_desc_sw128(w_addr + (uint32_t)(tap * p.kb_per_tap + kb) * (BN * kKBlock * 2));
+#pragma unroll
+              for (int k = 0; k < kKBlock / 16; k++)
+                umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | tap | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[st]);
+          }
+        } else
         for (int it = 0; it < num_it; it++, kit++) {
           const int st = kit % kStages;
           const uint32_t ph = (kit / kStages) & 1;
@@ -696,9 +762,45 @@ static void launch_cfg_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   CV2_LAUNCH_CHECK();
 }
 
+// conv mode (GemmParams::tmA_halo): persistent 1-SM CTAs, [192 x 64] A boxes, resident weights
+template <int BN, class Cfg>
+static void launch_conv(const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using SM = GemmSmemConv<BN>;
+  static PerDeviceOnce once;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    CV2_CUDA(cudaGetDevice(&dev));
+    CV2_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  once.run([] { CV2_CUDA(cudaFuncSetAttribute(gemm_tap_kernel<BN, Cfg, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal)); });
+  const int rows = (p.T_alloc / kTileM) * p.S;
+  const int grid = rows < g_num_sms ? rows : g_num_sms;
+  gemm_tap_kernel<BN, Cfg, 1, true><<<grid, SM::kThreads, SM::kTotal, stream>>>(*p.tmA_halo, tmB, p);
+  CV2_LAUNCH_CHECK();
+}
+
+bool gemm_tap_conv_eligible(int bn, const GemmParams& p) {
+  if (bn != 64 && bn != 128) return false;
+  if (p.N > bn || p.ntaps < 2 || p.q || p.S_map > 0) return false;
+  if ((long long)p.ntaps * p.kb_per_tap * bn * kKBlock * 2 > GemmSmemConv<64>::kWBytes) return false;
+  int lo = p.tap_off[0], hi = p.tap_off[0];
+  for (int j = 0; j < p.ntaps; j++) {
+    if (p.tap_seq[j] != 0) return false;
+    lo = p.tap_off[j] < lo ? p.tap_off[j] : lo;
+    hi = p.tap_off[j] > hi ? p.tap_off[j] : hi;
+  }
+  return hi - lo <= kConvHaloRows - kTileM;
+}
+
 // tmB2: weight map with a {64, BN/2} box for the 2-CTA multicast path (null: single-CTA path)
 template <int BN, class Cfg>
 static void launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  if constexpr (BN != 256) {
+    if (p.tmA_halo) {
+      launch_conv<BN, Cfg>(tmB, p, stream);
+      return;
+    }
+  }
   if constexpr (BN == 256) {
     if (p.tmB_half && p.tile_list) {
       launch_cfg_cs<BN, Cfg, 2>(tmA, *p.tmB_half, p, stream);

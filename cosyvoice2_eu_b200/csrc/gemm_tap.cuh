@@ -47,6 +47,12 @@ struct GemmParams {
   int dbg_skip_epi;              // measurement aid: epilogue drains the accumulator without computing or storing
   const CUtensorMap* tmB_half;   // host pointer: weight map with a {64, BN/2} box -> 2-CTA cluster with TMA multicast of the
                                  // weight operand (BN = 256 and a compact tile list only); null: one CTA per tile
+  // "conv mode" (k-tap convs of the vocoder's narrow stages, BN = 64 / 128, N <= BN): instead of one [128 x 64] A tile PER TAP
+  // (the same rows shifted by the tap offset: 11 x 16 KB for a k = 11 conv) ONE [192 x 64] box per k-block carries the rows of
+  // all taps and every tap reads it through a row-shifted shared-memory descriptor; the whole weight matrix (<= 96 KB) is
+  // loaded once per CTA and stays resident.  Per-tile TMA traffic: 24 KB per k-block instead of (16 + BN / 8) KB per tap.
+  const CUtensorMap* tmA_halo;   // host pointer: A map with a {64, 192, 1} box; null: normal mode
+  int conv_min_off;              // smallest tap offset (first row of the box = t0 + conv_min_off)
   // epilogue program: v = acc * acc_scale + bias -> LN -> act -> + rowvec[s] -> (mask) -> + res + res2 -> *scale (+= out32) -> store / emit
   float acc_scale;     // 0 / 1: none; else the raw accumulator is multiplied by it before the bias (weights stored pre-scaled to
                        // keep a 16-bit low half out of the subnormal range); generic epilogue only, not with ln
@@ -87,6 +93,9 @@ struct GemmParams {
 // Launch; tmA = 3-D map {Kc, T_alloc, S} box {64,128,1}; tmB = 2-D map {Ktot_pad, N} box {64, BN}.
 // bn in {64, 128, 256}.
 int gemm_tap_spec(int bn, const GemmParams& p);
+// can this launch run in conv mode (see GemmParams::tmA_halo)?  bn / N / taps / k-blocks as launch_gemm_tap gets them
+bool gemm_tap_conv_eligible(int bn, const GemmParams& p);
+static constexpr int kConvHaloRows = 192;
 // list: [2 * S * (T_alloc/128)] ints, count: 1 int (device)
 // lo (optional, [S]): only tiles with t0 >= floor(lo[s] / 128) * 128 are listed (incremental streaming: earlier rows are final)
 void launch_build_tile_list(const int* lens, int S, int T_alloc, int halo, int* list, int* count, cudaStream_t stream,

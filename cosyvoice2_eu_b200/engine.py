@@ -186,6 +186,32 @@ class B200Encoder:
     __call__ = forward
 
 
+class B200Estimator:
+    """The `flow.decoder.estimator` slot (boundary #4): called like the nn.Module the reference keeps there
+    (`estimator(x, mask, mu, t, spks, cond, streaming=...)`, cosyvoice/flow/flow_matching.py:127) and backed by cv2_estimator_forward,
+    the entry with the I/O contract of the TensorRT branch (flow_matching.py:129-150, cosyvoice/bin/export_onnx.py:89-109)."""
+
+    def __init__(self, flow):
+        self._flow = flow
+
+    def forward(self, x, mask, mu, t, spks, cond, streaming=False):
+        return self._flow.estimator_forward(x, mask, mu, t, spks, cond, streaming=streaming)
+
+    __call__ = forward
+
+    def eval(self):
+        return self
+
+
+class _Decoder:
+    """`flow.decoder` as far as the reference's loaders touch it: the assignable `estimator` attribute (CosyVoice2Model.load_trt
+    deletes and replaces it, cosyvoice/cli/model.py:107-109)."""
+
+    def __init__(self, flow):
+        self.estimator = B200Estimator(flow)
+        self.fp16 = False
+
+
 class B200Flow:
     """Drop-in for the reference flow object (CausalMaskedDiffWithXvec) on the inference path."""
 
@@ -200,6 +226,7 @@ class B200Flow:
         self.device = self.eng.device
         self.vocab_size = 6561
         self.encoder = B200Encoder(self)          # boundary #5 (model.py:285-287 assigns flow.encoder)
+        self.decoder = _Decoder(self)             # boundary #4 (model.py:107-109 assigns flow.decoder.estimator)
         g = torch.Generator(device="cpu")
         g.manual_seed(0)  # CausalConditionalCFM.__init__: set_all_random_seed(0); randn([1,80,15000])  (flow_matching.py:195-198)
         self.rand_noise = torch.randn([1, 80, 50 * 300], generator=g).to(self.device)

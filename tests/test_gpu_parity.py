@@ -44,6 +44,15 @@ def test_estimator_single_call(engine, golden):
         assert err < 5e-3
 
 
+def test_estimator_slot_object(engine, golden):
+    """`flow.decoder.estimator` is the assignable slot the reference's loaders use (model.py:107-109) and is called like the
+    nn.Module (flow_matching.py:127): same result as the direct entry."""
+    flow = engine[0]
+    g = golden("est")
+    out = flow.decoder.estimator(T(g["x"]), T(g["mask"]), T(g["mu"]), T(g["t"]), T(g["spks"]), T(g["cond"]), streaming=True)
+    assert np.abs(out.cpu().numpy() - g["out_streaming"]).max() < 5e-3
+
+
 def test_estimator_ragged_mask(engine, golden, fixture_weights):
     """Padded batch rows must reproduce the unpadded B=1 result (length-aware kernels)."""
     import token2wav_oracle as O
