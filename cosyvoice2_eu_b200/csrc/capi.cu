@@ -122,6 +122,7 @@ int cv2_engine_set_option(cv2_engine* h, const char* name, int value) {
   else if (n == "min_2sm_tiles") h->e.min_2sm_tiles = value;
   else if (n == "min_2sm_tiles_ffn") h->e.min_2sm_tiles_ffn = value;
   else if (n == "chain_outproj") h->e.chain_outproj = value != 0;
+  else if (n == "ffn_hsplit") h->e.ffn_hsplit = value != 0;
   else if (n == "conv_mode") h->e.conv_mode = value;
   else if (n == "range_check") {
     use_device(h);

@@ -164,6 +164,7 @@ struct Engine {
   };
   void ffn(cudaStream_t st, __half* H, int S, int T_alloc, Weight& w1, Weight& w2, FfnParams p, bool dry, const OutProj* op = nullptr);
   bool chain_outproj = getenv("CV2_NO_OUTPROJ_CHAIN") == nullptr;
+  bool ffn_hsplit = getenv("CV2_NO_FFN_HSPLIT") == nullptr;   // small launches: hidden split of the chained FFN (ffn_fused2.cu)
   const CUtensorMap& amap(const __half* A, int S, int T_alloc, int Kc, long long ldA, int box_rows = 128);
   // conv mode of the tap GEMM for the vocoder's narrow stages (gemm_tap.cuh: GemmParams::tmA_halo): 0 off, 1 on
   int conv_mode = getenv("CV2_CONV_MODE") ? atoi(getenv("CV2_CONV_MODE")) : 1;

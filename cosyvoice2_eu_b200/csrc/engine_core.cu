@@ -103,8 +103,14 @@ void Engine::ffn(cudaStream_t st, __half* H, int S, int T_alloc, Weight& w1, Wei
   if (two_sm && p.tile_list) {
     if (chain) {   // out-projection chained in front: H never exists in global memory
       p.bo = op->wo->b; p.ln3_g = op->ln3.g; p.ln3_b = op->ln3.b; p.ln3_eps = op->eps;
-      launch_ffn_fused2_chain(amap(op->att, S, T_alloc, 512, 512), wmap(*op->wo, 128), wmap(w1, 64), wmap(w2, 128), p, st);
+      if (ffn_hsplit && p.hsplit == 4 && p.slabs)   // small launch: the hidden dimension of every tile pair divided among four CTA pairs
+        launch_ffn_fused2_chain_split(amap(op->att, S, T_alloc, 512, 512), wmap(*op->wo, 128), wmap(w1, 64), wmap(w2, 128), p, st);
+      else {
+        p.hsplit = 0;
+        launch_ffn_fused2_chain(amap(op->att, S, T_alloc, 512, 512), wmap(*op->wo, 128), wmap(w1, 64), wmap(w2, 128), p, st);
+      }
     } else {
+      p.hsplit = 0;
       launch_ffn_fused2(amap(H, S, T_alloc, 256, 256), wmap(w1, 64), wmap(w2, 128), p, st);   // 2-SM MMAs, half of every weight tile per CTA
     }
   } else {

@@ -40,8 +40,10 @@ static Emit emit_ln(__half* ptr, long long ld, const LN& ln, float eps) {
 // Estimator core: xin16 [S, T_alloc, 320] -> v32 [S, T_alloc, 80].  temb_res: per-resnet time vectors
 // [14][nt][256]; row `trow` (stride trow_ld: 0 = shared by all sequences, 256 = one per sequence).
 // ---------------------------------------------------------------------------------------------------------
+static constexpr int kFfnSplitMaxTiles = 36;   // 18 tile pairs x 4 hidden splits <= 74 resident CTA pairs
 struct EstBuffers {
   float *X32, *R32, *V32;
+  float* SP32;   // small launches: x' + 4 partial FF2 sums of the hidden-split FFN (null otherwise)
   __half *H16, *Q16, *K16, *VT16, *ATT16, *F16, *C16, *CAT16, *M16, *N16;
 };
 static EstBuffers est_alloc(Arena& ws, int S, int T) {
@@ -60,6 +62,7 @@ static EstBuffers est_alloc(Arena& ws, int S, int T) {
   b.CAT16 = ws.get<__half>(rows * 512);
   b.M16 = ws.get<__half>(rows * 256);
   b.N16 = ws.get<__half>(rows * 256);
+  b.SP32 = (long long)S * (T / 128) <= kFfnSplitMaxTiles ? ws.get<float>(rows * 256 * 5) : nullptr;
   return b;
 }
 
@@ -171,6 +174,11 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
         FfnParams fp;
         memset(&fp, 0, sizeof(fp));
         fp.lens = lens; fp.halo = kEstHalo; fp.x32 = b.X32;
+        if (b.SP32 && !es) {
+          fp.hsplit = 4;
+          fp.xprime = b.SP32;
+          fp.slabs = b.SP32 + (size_t)S * T * 256;
+        }
         if (j < 3) {
           fp.emit_ln = emit_ln(b.H16, 256, e.ln("est.tfm." + std::to_string(r) + "." + std::to_string(j + 1) + ".ln1"), 1e-5f);
         } else if (r == 0) {

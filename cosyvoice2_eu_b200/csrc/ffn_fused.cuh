@@ -26,6 +26,14 @@ struct FfnParams {
   const float* ln3_g;       // [256] LayerNorm3 gamma / beta / eps
   const float* ln3_b;
   float ln3_eps;
+  // hidden split (chained 2-SM kernel, small launches only): a tile pair is worked on by `hsplit` CTA pairs, each taking 8 / hsplit
+  // of the eight hidden chunks.  Every pair recomputes the out-projection and LayerNorm3 (it needs the whole H tile), pair 0 stores
+  // x' = x + Wo att + bo to `xprime`, every pair stores its partial FF2 sum to its slab, and ffn_reduce adds them up, applies b2,
+  // updates x32 and emits the next pre-norm.  One launch more, but the launch's critical path -- ONE unit -- shrinks from eight
+  // serial GELU chunks to two: this is what a batch-1 call (12 row tiles for 148 SMs) is bound by.
+  int hsplit;               // 0 / 1: off
+  float* slabs;             // [hsplit][S * T_alloc][256] fp32
+  float* xprime;            // [S * T_alloc][256] fp32
   long long* trace;         // debug: CTA 0 logs (clock64 << 8 | event code) for its MMA thread [0, 4096) and first epilogue warp
                             // [4096, 8192) (profiles/ffn_trace.py); null in production
 };
@@ -42,5 +50,9 @@ void launch_ffn_fused2(const CUtensorMap& tmH, const CUtensorMap& tmW1h, const C
 // chained form (p.bo != null): tmATT: 3-D {512, T_alloc, S} box {64,128,1} over the attention output; tmWoh: {512, 256} box {64, 128}
 void launch_ffn_fused2_chain(const CUtensorMap& tmATT, const CUtensorMap& tmWoh, const CUtensorMap& tmW1h, const CUtensorMap& tmW2h,
                              const FfnParams& p, cudaStream_t stream);
+// p.hsplit == 4: the same kernel with the hidden dimension of every tile pair divided among four CTA pairs, followed by the reduction
+void launch_ffn_fused2_chain_split(const CUtensorMap& tmATT, const CUtensorMap& tmWoh, const CUtensorMap& tmW1h, const CUtensorMap& tmW2h,
+                                   const FfnParams& p, cudaStream_t stream);
+int ffn_fused2_max_pairs();   // CTA pairs that are resident at once (after the first launch on this device; 0 before)
 
 }  // namespace cv2

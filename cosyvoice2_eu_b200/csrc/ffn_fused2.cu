@@ -86,7 +86,7 @@ __device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
 }
 
 // CHAIN: tmH is the attention output [S, T_alloc, 512] (A operand of the out-projection), tmWo the out-proj weight halves.
-template <bool CHAIN>
+template <bool CHAIN, int HS = 1>
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmWo,
                   const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const FfnParams p) {
@@ -109,8 +109,10 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  static_assert(HS == 1 || (CHAIN && 8 % HS == 0), "the hidden split exists for the chained kernel only");
+  constexpr int kNC = 8 / HS;                                 // hidden chunks per unit
   const int row_tiles = __ldg(p.tile_count);                 // (the 2-SM path requires the compact tile list)
-  const int total_tiles = (row_tiles + 1) / 2;                // pair units
+  const int total_tiles = ((row_tiles + 1) / 2) * HS;         // units: tile pairs x hidden splits
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
@@ -176,7 +178,8 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       int lt = 0, wit = 0;
       for (int unit = unit0; unit < total_tiles; unit += unit_step) {
         int s, t0, len;
-        ffn2_tile(p, unit, rank, row_tiles, s, t0, len);
+        ffn2_tile(p, unit / HS, rank, row_tiles, s, t0, len);
+        const int c0 = (unit % HS) * kNC;
         prefetch_l2_bulk(p.x32 + ((long long)s * p.T_alloc + t0) * 256, 128 * 256 * 4);
         if (!CHAIN) {
           mbar_wait(h_empty, (lt & 1) ^ 1);
@@ -198,10 +201,11 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
             }
           }
         }
-        for (int o = 0; o < 16; o++) {
+        for (int o = 0; o < 2 * kNC; o++) {
           bool is_ff2;
           int c;
-          ffn_op(o, is_ff2, c);
+          if (HS == 1) ffn_op(o, is_ff2, c);
+          else { is_ff2 = o >= kNC; c = c0 + (o % kNC); }     // split: FF1(c0) .. FF1(c0+n-1), FF2(c0) .. FF2(c0+n-1)
           for (int i = 0; i < 2; i++, wit++) {     // two 16 KB slots per op and CTA
             const int st = wit % kSlots;
             mbar_wait(&w_empty[st], ((wit / kSlots) & 1) ^ 1);
@@ -269,7 +273,8 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         umma2_commit(&acc1_full[b]);
         ffn_trace(tb, ti, 3);
       };
-      auto ff2 = [&](int c) {
+      int c_first = 0;   // first chunk of the unit: its FF2 overwrites the output accumulator
+      auto ff2 = [&](int c, bool ff2_next = false) {
         ffn_trace(tb, ti, 4);
         if (!f_ready) mbar_wait(f_full, fcnt & 1);      // GELU chunk c (16-bit) is in TMEM in both CTAs
         f_ready = false;
@@ -284,10 +289,10 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           const uint64_t b_desc = umma_smem_desc_sw128(slot_begin());
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            umma2_f16_ts(tmem_base + kAcc2, a_tmem + kb * 32 + k * 8, b_desc + (uint64_t)(k * 2), idesc2, (c | kb | k) != 0);
+            umma2_f16_ts(tmem_base + kAcc2, a_tmem + kb * 32 + k * 8, b_desc + (uint64_t)(k * 2), idesc2, ((c - c_first) | kb | k) != 0);
             if (k == 1) {
               poll_next_slot();
-              if (kb == 1 && c == 6) poll_f();          // FF2(7) follows FF2(6) directly
+              if (kb == 1 && (c == 6 || ff2_next)) poll_f();          // FF2(7) follows FF2(6) directly
             }
           }
           umma2_commit(&w_empty[wit % kSlots]);
@@ -324,19 +329,31 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           tc_fence_after();
         }
         ffn_trace(tb, ti, 2);
-        // schedule: FF1(0) FF1(1) | FF2(0) FF1(2) | FF2(1) FF1(3) | ... | FF2(5) FF1(7) | FF2(6) FF2(7)
-        ff1(0, false);
-        ff1(1, true);
-        mbar_wait(acc2_empty, (lt & 1) ^ 1);            // both CTAs' output epilogues have drained acc2
-        tc_fence_after();
+        if constexpr (HS == 1) {
+          // schedule: FF1(0) FF1(1) | FF2(0) FF1(2) | FF2(1) FF1(3) | ... | FF2(5) FF1(7) | FF2(6) FF2(7)
+          ff1(0, false);
+          ff1(1, true);
+          mbar_wait(acc2_empty, (lt & 1) ^ 1);            // both CTAs' output epilogues have drained acc2
+          tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 6; c++) {
-          ff2(c);
-          ff1(c + 2, true);
+          for (int c = 0; c < 6; c++) {
+            ff2(c);
+            ff1(c + 2, true);
+          }
+          umma2_commit(h_empty);                          // all FF1 MMAs of this unit issued: the H tiles may be refilled
+          ff2(6);
+          ff2(7);
+        } else {
+          static_assert(HS == 1 || kNC == 2, "split schedule is written for two chunks per unit");
+          c_first = (unit % HS) * kNC;                    // FF1(c0) FF1(c0+1) | FF2(c0) FF2(c0+1)
+          ff1(c_first, false);
+          ff1(c_first + 1, true);
+          umma2_commit(h_empty);
+          mbar_wait(acc2_empty, (lt & 1) ^ 1);
+          tc_fence_after();
+          ff2(c_first, true);
+          ff2(c_first + 1);
         }
-        umma2_commit(h_empty);                          // all FF1 MMAs of this unit issued: the H tiles may be refilled
-        ff2(6);
-        ff2(7);
         umma2_commit(acc2_full);
         lt++;
       }
@@ -355,7 +372,8 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
     int ti = 0;
     for (int unit = unit0; unit < total_tiles; unit += unit_step) {
       int s, t0, len;
-      const bool tile_ok = ffn2_tile(p, unit, rank, row_tiles, s, t0, len);
+      const bool tile_ok = ffn2_tile(p, unit / HS, rank, row_tiles, s, t0, len);
+      const int hs = unit % HS;
       const int t = t0 + r;
       const bool valid = t < len;
       const long long row = (long long)s * p.T_alloc + t;
@@ -382,7 +400,11 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           tile_load_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, tmp);
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] += tmp[i];
-          if (tile_ok) tile_store_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, v);
+          if (HS == 1) {
+            if (tile_ok) tile_store_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, v);
+          } else if (tile_ok && hs == 0) {     // split: x32 stays untouched until the reduction; x' goes to its own buffer
+            tile_store_f32_h16(p.xprime + row0 * 256 + cbase, 256, stg, lane, v);
+          }
 #pragma unroll
           for (int i = 0; i < 32; i++) {
             sum3 += v[i];
@@ -434,7 +456,7 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         ffn_trace(tb, ti, 34);
       }
       // ---- 8 hidden chunks: bias + GELU -> 16-bit chunk in shared memory (A operand of FF2) ----
-      for (int c = 0; c < 8; c++, g++) {
+      for (int c = hs * kNC; c < hs * kNC + kNC; c++, g++) {
         const int b = c & 1;
         float bv[32];
         lds32(vec_b1 + c * 128 + part * 32, bv);
@@ -474,6 +496,25 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       const uint32_t taddr = lane_addr + kAcc2 + part * 64;
       const bool want_ln = tile_ok && p.emit_ln.ptr != nullptr;
       if (!tile_ok) {   // filler tile of an odd tail: nothing to store, just hand acc2 back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(acc2_empty);
+        lt++;
+        continue;
+      }
+      if constexpr (HS > 1) {   // split: this pair's partial FF2 sum goes to its slab; bias, residual and LayerNorm happen in ffn_reduce
+        float* slab = p.slabs + (long long)hs * p.S * p.T_alloc * 256;
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ch++) {
+          const int cbase = part * 64 + ch * 32;
+          uint32_t raw[32];
+          tmem_ld32(taddr + ch * 32, raw);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]);
+          if (tile_ok) tile_store_f32_h16(slab + row0 * 256 + cbase, 256, stg, lane, v);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(acc2_empty);
@@ -602,6 +643,131 @@ void launch_ffn_fused2(const CUtensorMap& tmH, const CUtensorMap& tmW1h, const C
 void launch_ffn_fused2_chain(const CUtensorMap& tmATT, const CUtensorMap& tmWoh, const CUtensorMap& tmW1h, const CUtensorMap& tmW2h,
                              const FfnParams& p, cudaStream_t stream) {
   launch_ffn2<true>(tmATT, tmWoh, tmW1h, tmW2h, p, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Hidden split for small launches (FfnParams::hsplit): the reduction of the partial FF2 sums.
+//   x = x' + sum_h slab_h + b2 -> x32 ; masked 16-bit emits / LayerNorm emit of the result (what the unsplit kernel's output
+//   epilogue does).  One warp per row (8 consecutive columns per lane: 2 x 128-bit per operand), 8 rows per CTA: a batch-1 call
+//   has ~2 300 rows, and the kernel is a latency chain per row, so it wants every row in flight at once.
+// ---------------------------------------------------------------------------------------------------------
+template <int HS>
+__global__ void __launch_bounds__(256) ffn_reduce_kernel(const FfnParams p) {
+  const int tile = blockIdx.x >> 4;
+  if (tile >= __ldg(p.tile_count)) return;
+  const int s = __ldg(p.tile_list + 2 * tile), t0 = __ldg(p.tile_list + 2 * tile + 1);
+  const int len = __ldg(p.lens + s);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long slab_stride = (long long)p.S * p.T_alloc * 256;
+  float bias[8], g[8], be[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) bias[i] = __ldg(p.b2 + lane * 8 + i);
+  const bool want_ln = p.emit_ln.ptr != nullptr;
+  if (want_ln) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      g[i] = __ldg(p.emit_ln.a + lane * 8 + i);
+      be[i] = __ldg(p.emit_ln.b + lane * 8 + i);
+    }
+  }
+  {
+    const int t = t0 + (blockIdx.x & 15) * 8 + warp;
+    const long long row = (long long)s * p.T_alloc + t;
+    const bool valid = t < len;
+    float v[8];
+    {
+      const float4* src = reinterpret_cast<const float4*>(p.xprime + row * 256 + lane * 8);
+      const float4 a = src[0], b = src[1];
+      v[0] = a.x + bias[0]; v[1] = a.y + bias[1]; v[2] = a.z + bias[2]; v[3] = a.w + bias[3];
+      v[4] = b.x + bias[4]; v[5] = b.y + bias[5]; v[6] = b.z + bias[6]; v[7] = b.w + bias[7];
+    }
+#pragma unroll
+    for (int h = 0; h < HS; h++) {
+      const float4* src = reinterpret_cast<const float4*>(p.slabs + h * slab_stride + row * 256 + lane * 8);
+      const float4 a = src[0], b = src[1];
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+      v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    float4* dst = reinterpret_cast<float4*>(p.x32 + row * 256 + lane * 8);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const Emit& em = p.emit_plain[e];
+      if (!em.ptr) continue;
+      uint32_t pk[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        __half2 hh = __floats2half2_rn(valid ? v[2 * i] : 0.f, valid ? v[2 * i + 1] : 0.f);
+        pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      *reinterpret_cast<uint4*>(em.ptr + row * em.ld + em.col_off + lane * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    if (want_ln) {
+      float sum = 0.f, sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        sum += v[i];
+        sq = fmaf(v[i], v[i], sq);
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        sq += __shfl_xor_sync(0xffffffffu, sq, d);
+      }
+      const float mean = sum * (1.f / 256.f);
+      const float rstd = rsqrtf(fmaxf(sq * (1.f / 256.f) - mean * mean, 0.f) + p.emit_ln.f);
+      uint32_t pk[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float w0 = valid ? (v[2 * i] - mean) * rstd * g[2 * i] + be[2 * i] : 0.f;
+        const float w1 = valid ? (v[2 * i + 1] - mean) * rstd * g[2 * i + 1] + be[2 * i + 1] : 0.f;
+        __half2 hh = __floats2half2_rn(w0, w1);
+        pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      *reinterpret_cast<uint4*>(p.emit_ln.ptr + row * p.emit_ln.ld + p.emit_ln.col_off + lane * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+static int g_ffn2_max_pairs = 0;
+int ffn_fused2_max_pairs() { return g_ffn2_max_pairs; }
+
+void launch_ffn_fused2_chain_split(const CUtensorMap& tmATT, const CUtensorMap& tmWoh, const CUtensorMap& tmW1h, const CUtensorMap& tmW2h,
+                                   const FfnParams& p_in, cudaStream_t stream) {
+  constexpr int HS = 4;
+  static PerDeviceOnce once;
+  FfnParams p = p_in;
+  p.trace = nullptr;
+  CV2_CHECK(p.hsplit == HS && p.slabs && p.xprime, "ffn_fused2 split: hsplit must be %d with slab / x' scratch", HS);
+  CV2_CHECK(p.tile_list && p.tile_count && p.lens && p.bo && p.ln3_g && p.ln3_b, "ffn_fused2 split: chained form with a compact tile list only");
+  CV2_CHECK(p.T_alloc % 128 == 0, "ffn_fused2: T_alloc %d not a multiple of 128", p.T_alloc);
+  cudaLaunchConfig_t q = {};
+  q.blockDim = dim3(kFfnThreads);
+  q.dynamicSmemBytes = kFfnSmem;
+  q.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  q.attrs = at;
+  q.numAttrs = 1;
+  once.run([&] {
+    CV2_CUDA(cudaFuncSetAttribute(ffn_fused2_kernel<true, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem));
+    int dev = 0, sms = 0;
+    CV2_CUDA(cudaGetDevice(&dev));
+    CV2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    q.gridDim = dim3(sms / 2 * 2);
+    CV2_CUDA(cudaOccupancyMaxActiveClusters(&g_ffn2_max_pairs, ffn_fused2_kernel<true, HS>, &q));
+    CV2_CHECK(g_ffn2_max_pairs > 0, "ffn_fused2: no 2-CTA cluster fits");
+  });
+  const int row_tiles = (p.T_alloc / 128) * p.S;
+  const int units = ((row_tiles + 1) / 2) * HS;
+  const int clusters = units < g_ffn2_max_pairs ? units : g_ffn2_max_pairs;
+  q.gridDim = dim3(2 * clusters);
+  CV2_CUDA(cudaLaunchKernelEx(&q, ffn_fused2_kernel<true, HS>, tmATT, tmWoh, tmW1h, tmW2h, p));
+  CV2_LAUNCH_CHECK();
+  ffn_reduce_kernel<HS><<<row_tiles * 16, 256, 0, stream>>>(p);
+  CV2_LAUNCH_CHECK();
 }
 
 }  // namespace cv2
