@@ -5,6 +5,6 @@ for v in "$@"; do
 import json,sys
 l=json.loads(sys.stdin.read().strip().splitlines()[-1])
 f=l['families']
-print('$v', 'value %.1f ms/step %.1f' % (l['value'], l['ms_per_step']), {k: round(f[k]['ms_per_step'],1) for k in ('flash_attn','ffn_fused','gemm_tap<256>','gemm_tap<128>','gemm_tap<64>')})
+print('$v', 'value %.1f ms/step %.1f' % (l['value'], l['ms_per_step']), {k: round(f[k]['ms_per_step'],1) for k in ('flash_attn','ffn_fused','gemm_tap<256>','gemm_tap<128>','gemm_tap<64>')}, 'qkv %.1f' % l['gemm256_by_epilogue']['qkv_split']['ms_per_step'])
 "
 done
