@@ -4,7 +4,8 @@
 // integers (valid length per sequence; optional block-causal chunk) inside the kernel.
 //
 // One CTA = 128 query rows of one (sequence, head), key tiles of 64.  warp 4: TMA producer (Q once, K / V^T tiles through a
-// 2-stage ring), warp 5: tcgen05.mma issuer (S = Q K^T into TMEM, O += P V with P as the TMEM A operand), warps 0-3: online
+// 2-stage ring), warp 5: tcgen05.mma issuer (warp-uniform code, one elected lane: S = Q K^T into TMEM, O += P V with P as the TMEM
+// A operand; a single lane of divergent code pays ~100 cycles per MMA, profiles/r2/micro_mma_issue.txt), warps 0-3: online
 // softmax, one thread per row.  Four CTAs per SM.  (Round 1 also carried four measured-and-rejected variants -- P through
 // shared memory, double-buffered S at two CTAs per SM, 32-key steps, 2-SM pairs; their numbers are in profiles/README.md,
 // the code is in the history before round 2.)
@@ -77,7 +78,7 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(&kv_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 4);          // one arrival per softmax warp
     mbar_init(o_done, 1);
     fence_barrier_init();
   }
@@ -101,34 +102,40 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(128, kKT, 0);
-      constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0);
-      const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(smem));
-      auto issue_s = [&](int j) {
-        const int st = j % k9Stages;
-        mbar_wait(&kv_full[st], (j / k9Stages) & 1);
-        tc_fence_after();
-        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(smem + k9OffK + st * kKBytes));
+    // warp-uniform control flow (descriptor arithmetic on the uniform datapath), one elected lane issues
+    constexpr uint32_t idesc_s = umma_idesc_f16(128, kKT, 0);
+    constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0);
+    const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(smem));
+    auto s_mmas = [&](int j) {   // S_j = Q K_j^T (the caller has waited for kv_full of tile j); elected lane only
+      const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(smem + k9OffK + (j % k9Stages) * kKBytes));
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-          umma_f16(tmem_base + k9TmemS, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0);
-        umma_commit(s_full);
-      };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < nkt; j++) {
-        mbar_wait(p_full, j & 1);   // softmax j has replaced S_j by P_j in tensor memory
-        tc_fence_after();
-        const int st = j % k9Stages;
-        const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(smem + k9OffV + st * kVBytes));
+      for (int k = 0; k < 4; k++)
+        umma_f16(tmem_base + k9TmemS, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0);
+      umma_commit(s_full);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) s_mmas(0);
+    __syncwarp();
+    for (int j = 0; j < nkt; j++) {
+      // K_{j+1} / V_{j+1} only depend on PV(j-1): polled here, outside the softmax -> PV -> S chain
+      if (j + 1 < nkt) mbar_wait(&kv_full[(j + 1) % k9Stages], ((j + 1) / k9Stages) & 1);
+      mbar_wait(p_full, j & 1);   // softmax j has replaced S_j by P_j in tensor memory
+      tc_fence_after();
+      const int st = j % k9Stages;
+      const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(smem + k9OffV + st * kVBytes));
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kKT / 16; k++)
           umma_f16_ts(tmem_base + k9TmemO, tmem_base + k9TmemS + k * 8, v_desc + (uint64_t)(k * 2), idesc_o, (j | k) != 0);
-        umma_commit(&kv_empty[st]);
-        if (j + 1 < nkt) issue_s(j + 1);   // in order behind PV(j): S_{j+1} overwrites P_j only after it was consumed
+        // S_{j+1} in order behind PV(j) (it overwrites P_j only after that was consumed), and first in line: the softmax chain
+        // waits for it, the stage release below does not
+        if (j + 1 < nkt) s_mmas(j + 1);
         else umma_commit(o_done);
+        umma_commit(&kv_empty[st]);
       }
+      __syncwarp();
     }
   } else {
     const int r = warp * 32 + lane;
@@ -144,10 +151,11 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int kbase = j * kKT;
       const bool edge = kbase + kKT > kv_lim;
       uint32_t sa[32];
-      // pass 1: row maximum
+      // pass 1: row maximum, chunk 1 first: chunk 0 (masked) is still in registers when pass 2 starts -- one tensor-memory round
+      // trip less per key tile.  (Both 32-column loads in flight at once was measured no faster: 301.5 vs 297.0 us.)
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 2; c++) {
+      for (int c = 1; c >= 0; c--) {
         tmem_ld32(lane_addr + k9TmemS + c * 32, sa);
         tmem_ld_wait();
         if (edge) {
@@ -171,7 +179,9 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         alpha = fast_exp2(mref - mxl);
         mref = mxl;
       }
+      bool have0 = true;             // chunk 0 of S is in `sa` (warp-uniform)
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+        have0 = false;               // (sa is the scratch of the rescale)
 #pragma unroll
         for (int c = 0; c < 2; c++) {
           tmem_ld32(lane_addr + k9TmemO + c * 32, sa);
@@ -186,12 +196,14 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 2; c++) {
-        tmem_ld32(lane_addr + k9TmemS + c * 32, sa);
-        tmem_ld_wait();
-        if (edge) {
+        if (c == 1 || !have0) {
+          tmem_ld32(lane_addr + k9TmemS + c * 32, sa);
+          tmem_ld_wait();
+          if (edge) {
 #pragma unroll
-          for (int i = 0; i < 32; i++)
-            if (kbase + c * 32 + i >= kv_lim) sa[i] = 0xff800000u;
+            for (int i = 0; i < 32; i++)
+              if (kbase + c * 32 + i >= kv_lim) sa[i] = 0xff800000u;
+          }
         }
         uint32_t pk[16];
         const float2 sc2 = make_float2(LOG2E, LOG2E), nm2 = make_float2(-mref, -mref);
@@ -212,7 +224,8 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       l += (la.x + la.y) + (lb.x + lb.y);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
     }
     const float inv = l > 0.f ? 1.f / l : 0.f;
     mbar_wait(o_done, 0);
