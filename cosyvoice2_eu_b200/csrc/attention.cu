@@ -144,6 +144,9 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (p.chunk > 0) kv_lim = min(len, (t / p.chunk + 1) * p.chunk);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const float LOG2E = 1.4426950408889634f;
+    // lazy rescale: the reference only moves when a tile's maximum exceeds it by 2^kLazy; probabilities then reach 2^kLazy, which a
+    // 16-bit P (max 65504, relative precision independent of magnitude) and the fp32 accumulators hold without loss
+    constexpr float kLazy = 13.f;
     float mref = 0.f, l = 0.f;     // reference max in log2 units
     for (int j = 0; j < nkt; j++) {
       mbar_wait(s_full, j & 1);     // also implies PV(j-1) has completed (same in-order pipe, commit covers prior MMAs)
@@ -175,7 +178,7 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       float alpha = 1.f;
       if (j == 0) {
         mref = mxl;
-      } else if (mxl > mref + 8.f) {
+      } else if (mxl > mref + kLazy) {
         alpha = fast_exp2(mref - mxl);
         mref = mxl;
       }
