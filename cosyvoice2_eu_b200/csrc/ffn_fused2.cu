@@ -223,8 +223,12 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       }
     }
   } else if (warp == kEpiW + 1) {
-    if (lane == 0 && leader) {
+    if (leader) {
       // ------------------------------- MMA issuer (leader CTA, for both SMs) -------
+      // The whole warp runs this code (warp-uniform control flow: descriptor arithmetic and barrier polls on the uniform datapath)
+      // and ONE elected lane issues the tcgen05 instructions: a single lane of divergent code pays ~100 cycles per MMA
+      // (profiles/r2/micro_mma_issue.txt), which for FF1's sixteen N = 128 MMAs per chunk (64 cycles each on the pipe) was the
+      // chunk phase's bound (r2/ffn_trace_chained_2sm.txt: 1 700 cycles per FF1 against 1 024 nominal).
       // The 2-SM pipe retires these MMAs at the nominal rate (8 per 513 cycles in the trace), but its queue is shallow and
       // the issuing thread blocks on it, so every cycle the thread spends elsewhere between bursts is an idle tensor pipe: a
       // satisfied mbarrier poll alone costs ~120 cycles.  Hence (i) the op schedule is straight-line code per chunk, and
@@ -236,7 +240,7 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       const uint32_t w_base = smem_u32(smem + kOffW);
       int lt = 0, wit = 0, fcnt = 0;
       bool w_ready = false, f_ready = false;
-      long long* tb = blockIdx.x == 0 ? p.trace : nullptr;
+      long long* tb = (blockIdx.x == 0 && lane == 0) ? p.trace : nullptr;
       int ti = 0;
       auto poll_next_slot = [&]() {
         const int n = wit + 1;
@@ -254,23 +258,26 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 2; i++) {
           const uint32_t w_addr = slot_begin();
-#pragma unroll
-          for (int kk = 0; kk < 2; kk++) {
-            const int kb = 2 * i + kk;
-            const uint64_t a_desc = umma_smem_desc_sw128(h_addr + kb * 16384);
-            const uint64_t b_desc = umma_smem_desc_sw128(w_addr + kk * 8192);
+          const uint64_t a_desc0 = umma_smem_desc_sw128(h_addr + (2 * i) * 16384), a_desc1 = umma_smem_desc_sw128(h_addr + (2 * i + 1) * 16384);
+          const uint64_t b_desc0 = umma_smem_desc_sw128(w_addr), b_desc1 = umma_smem_desc_sw128(w_addr + 8192);
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; k++)
-              umma2_f16(tmem_base + kAcc1 + b * 128, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc1, (kb | k) != 0);
-            if (kk == 0) {               // middle of the burst: look ahead
-              poll_next_slot();
-              if (i == 1 && poll_f_after) poll_f();
-            }
+              umma2_f16(tmem_base + kAcc1 + b * 128, a_desc0 + (uint64_t)(k * 2), b_desc0 + (uint64_t)(k * 2), idesc1, (i | k) != 0);
           }
-          umma2_commit(&w_empty[wit % kSlots]);
+          __syncwarp();
+          poll_next_slot();               // middle of the burst: look ahead
+          if (i == 1 && poll_f_after) poll_f();
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              umma2_f16(tmem_base + kAcc1 + b * 128, a_desc1 + (uint64_t)(k * 2), b_desc1 + (uint64_t)(k * 2), idesc1, 1u);
+            umma2_commit(&w_empty[wit % kSlots]);
+            if (i == 1) umma2_commit(&acc1_full[b]);
+          }
+          __syncwarp();
           wit++;
         }
-        umma2_commit(&acc1_full[b]);
         ffn_trace(tb, ti, 3);
       };
       int c_first = 0;   // first chunk of the unit: its FF2 overwrites the output accumulator
@@ -280,22 +287,30 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         f_ready = false;
         fcnt++;
         ffn_trace(tb, ti, 5);
-        mbar_arrive(f_seen);                            // back-pressure (see ffn_fused.cu), relayed to the peer
-        mbar_arrive_rank(f_seen, 1);
         tc_fence_after();
         const uint32_t a_tmem = tmem_base + kAcc1 + (c & 1) * 128;
 #pragma unroll
         for (int kb = 0; kb < 2; kb++) {
           const uint64_t b_desc = umma_smem_desc_sw128(slot_begin());
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            umma2_f16_ts(tmem_base + kAcc2, a_tmem + kb * 32 + k * 8, b_desc + (uint64_t)(k * 2), idesc2, ((c - c_first) | kb | k) != 0);
-            if (k == 1) {
-              poll_next_slot();
-              if (kb == 1 && (c == 6 || ff2_next)) poll_f();          // FF2(7) follows FF2(6) directly
+          if (elect_one()) {
+            if (kb == 0) {
+              mbar_arrive(f_seen);                      // back-pressure (see ffn_fused.cu), relayed to the peer
+              mbar_arrive_rank(f_seen, 1);
             }
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+              umma2_f16_ts(tmem_base + kAcc2, a_tmem + kb * 32 + k * 8, b_desc + (uint64_t)(k * 2), idesc2, ((c - c_first) | kb | k) != 0);
           }
-          umma2_commit(&w_empty[wit % kSlots]);
+          __syncwarp();
+          poll_next_slot();
+          if (kb == 1 && (c == 6 || ff2_next)) poll_f();          // FF2(7) follows FF2(6) directly
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 2; k < 4; k++)
+              umma2_f16_ts(tmem_base + kAcc2, a_tmem + kb * 32 + k * 8, b_desc + (uint64_t)(k * 2), idesc2, 1u);
+            umma2_commit(&w_empty[wit % kSlots]);
+          }
+          __syncwarp();
           wit++;
         }
         ffn_trace(tb, ti, 6);
@@ -316,13 +331,16 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
             const int stB = wit % kSlots;
             const uint64_t b_desc = umma_smem_desc_sw128(slot_begin());
             wit++;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-              umma2_f16(tmem_base + kAcc1, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc2, (kb | k) != 0);
-            umma2_commit(&w_empty[stA]);
-            umma2_commit(&w_empty[stB]);
+              for (int k = 0; k < 4; k++)
+                umma2_f16(tmem_base + kAcc1, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc2, (kb | k) != 0);
+              umma2_commit(&w_empty[stA]);
+              umma2_commit(&w_empty[stB]);
+              if (kb == 7) umma2_commit(op_full);
+            }
+            __syncwarp();
           }
-          umma2_commit(op_full);
           w_ready = false;
           mbar_wait(h_ready, lt & 1);       // both CTAs have added the residual and written LayerNorm3(x) as their H tile
           asm volatile("fence.acq_rel.cluster;" ::: "memory");
@@ -340,7 +358,8 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
             ff2(c);
             ff1(c + 2, true);
           }
-          umma2_commit(h_empty);                          // all FF1 MMAs of this unit issued: the H tiles may be refilled
+          if (elect_one()) umma2_commit(h_empty);         // all FF1 MMAs of this unit issued: the H tiles may be refilled
+          __syncwarp();
           ff2(6);
           ff2(7);
         } else {
@@ -348,13 +367,15 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           c_first = (unit % HS) * kNC;                    // FF1(c0) FF1(c0+1) | FF2(c0) FF2(c0+1)
           ff1(c_first, false);
           ff1(c_first + 1, true);
-          umma2_commit(h_empty);
+          if (elect_one()) umma2_commit(h_empty);
+          __syncwarp();
           mbar_wait(acc2_empty, (lt & 1) ^ 1);
           tc_fence_after();
           ff2(c_first, true);
           ff2(c_first + 1);
         }
-        umma2_commit(acc2_full);
+        if (elect_one()) umma2_commit(acc2_full);
+        __syncwarp();
         lt++;
       }
     }
