@@ -299,7 +299,7 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
             }
 #pragma unroll
             for (int k = 0; k < 2; k++)
-              umma2_f16_ts(tmem_base + kAcc2, a_tmem + kb * 32 + k * 8, b_desc + (uint64_t)(k * 2), idesc2, ((c - c_first) | kb | k) != 0);
+              umma2_f16_ts(tmem_base + kAcc2, a_tmem + kb * 32 + k * 8, b_desc + (uint64_t)(k * 2), idesc2, (CHAIN && HS == 1) ? 1u : (uint32_t)(((c - c_first) | kb | k) != 0));
           }
           __syncwarp();
           poll_next_slot();
@@ -400,7 +400,7 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       const long long row = (long long)s * p.T_alloc + t;
       const long long row0 = row - lane;
       if (CHAIN) {
-        // ---- chained out-projection: x <- acc + bo + x (written back once), H = LayerNorm3(x) as the swizzled 16-bit A tile ----
+        // ---- chained out-projection: x' = acc + bo + x (kept in tensor memory as the FF2 accumulator's initial value), H = LayerNorm3(x') as the swizzled 16-bit A tile ----
         ffn_trace(tb, ti, 30);
         mbar_wait(op_full, lt & 1);
         tc_fence_after();
@@ -421,9 +421,7 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           tile_load_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, tmp);
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] += tmp[i];
-          if (HS == 1) {
-            if (tile_ok) tile_store_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, v);
-          } else if (tile_ok && hs == 0) {     // split: x32 stays untouched until the reduction; x' goes to its own buffer
+          if (HS > 1 && tile_ok && hs == 0) {     // split: x32 stays untouched until the reduction; x' goes to its own buffer
             tile_store_f32_h16(p.xprime + row0 * 256 + cbase, 256, stg, lane, v);
           }
 #pragma unroll
@@ -433,6 +431,10 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
             raw[i] = __float_as_uint(v[i]);
           }
           tmem_st32(oaddr + ch * 32, raw);
+          // x' is not written back to global memory: it becomes the INITIAL VALUE of the FF2 accumulator (same rows, same 256
+          // columns; the previous unit's output epilogue -- these very warps -- has drained it), every FF2 MMA accumulates, and the
+          // output epilogue finds x' + FF2 there: no fp32 store here, no residual load there (256 KB per tile, and their latency)
+          if (HS == 1) tmem_st32(lane_addr + kAcc2 + cbase, raw);
         }
         tmem_st_wait();
         ffn_trace(tb, ti, 32);
@@ -554,9 +556,11 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]) + tmp[i];
         ffn_trace(tb, ti, 23);
-        tile_load_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, tmp);
+        if (!(CHAIN && HS == 1)) {   // (chained: the accumulator was initialised with x', see the mid-epilogue)
+          tile_load_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, tmp);
 #pragma unroll
-        for (int i = 0; i < 32; i++) v[i] += tmp[i];
+          for (int i = 0; i < 32; i++) v[i] += tmp[i];
+        }
         ffn_trace(tb, ti, 24, v[0]);
         tile_store_f32_h16(p.x32 + row0 * 256 + cbase, 256, stg, lane, v);
         ffn_trace(tb, ti, 25);
