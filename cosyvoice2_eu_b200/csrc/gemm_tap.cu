@@ -254,11 +254,14 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == kEpiWarps + 1) {
-    if (lane == 0 && leader) {
+    constexpr bool kUni = BN == 256;   // measured on one box: BN = 256 107.4 vs 109.0 ms per step, BN = 128 16.5 vs 15.6 (worse), BN = 64 equal
+    if (leader && (kUni || lane == 0)) {
       // ------------------------------- MMA issuer (CS = 2: for both SMs) ----------
+      // BN = 256: warp-uniform control flow (descriptors and barrier polls on the uniform datapath), one elected lane issues; the
+      // narrower tiles keep the single-lane form
       constexpr uint32_t idesc = umma_idesc_f16(CS * kTileM, BN, 0);
       int kit = 0, lt = 0;
-      long long* tb = (p.trace && blockIdx.x == 0) ? p.trace + 4096 : nullptr;
+      long long* tb = (p.trace && blockIdx.x == 0 && lane == 0) ? p.trace + 4096 : nullptr;
       int ti = 0;
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         TileCoord c;
@@ -278,18 +281,22 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(&full_bar[st], (kit / kStages) & 1);
             tc_fence_after();
             const uint32_t box = smem_u32(smem + st * SM::kStageBytes);
-            for (int tap = 0; tap < p.ntaps; tap++) {
-              // rows of this tap start (off - min_off) rows into the box: a descriptor whose start is not 1024-byte aligned
-              const uint32_t a_addr = box + (uint32_t)(p.tap_off[tap] - p.conv_min_off) * 128u;
-              // (the tensor core applies the 128B swizzle to ABSOLUTE shared-memory address bits, exactly like the TMA write did:
-              // measured -- with the descriptor's "matrix base offset" field set to (start >> 7) & 7 the result is wrong)
-              const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
-              const uint64_t b_desc = umma_smem_desc_sw128(w_addr + (uint32_t)(tap * p.kb_per_tap + kb) * (BN * kKBlock * 2));
+            if (kUni ? elect_one() : true) {
+              for (int tap = 0; tap < p.ntaps; tap++) {
+                // rows of this tap start (off - min_off) rows into the box: a descriptor whose start is not 1024-byte aligned
+                const uint32_t a_addr = box + (uint32_t)(p.tap_off[tap] - p.conv_min_off) * 128u;
+                // (the tensor core applies the 128B swizzle to ABSOLUTE shared-memory address bits, exactly like the TMA write did:
+                // measured -- with the descriptor's "matrix base offset" field set to (start >> 7) & 7 the result is wrong)
+                const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
+                const uint64_t b_desc = umma_smem_desc_sw128(w_addr + (uint32_t)(tap * p.kb_per_tap + kb) * (BN * kKBlock * 2));
 #pragma unroll
-              for (int k = 0; k < kKBlock / 16; k++)
-                umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | tap | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < kKBlock / 16; k++)
+                  umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | tap | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(&empty_bar[st]);
+              if (kb + 1 == p.kb_per_tap) umma_commit(&tmem_full[acc]);   // accumulator complete
             }
-            umma_commit(&empty_bar[st]);
+            if (kUni) __syncwarp();
           }
         } else
         for (int it = 0; it < num_it; it++, kit++) {
@@ -301,16 +308,21 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t a_addr = smem_u32(smem + st * SM::kStageBytes);
           const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
           const uint64_t b_desc = umma_smem_desc_sw128(a_addr + kABytes);
+          if (kUni ? elect_one() : true) {
 #pragma unroll
-          for (int k = 0; k < kKBlock / 16; k++) {
-            if (CS == 1) umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
-            else umma2_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kKBlock / 16; k++) {
+              if (CS == 1) umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+              else umma2_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+            }
+            if (CS == 1) umma_commit(&empty_bar[st]);
+            else umma2_commit(&empty_bar[st]);
+            if (it + 1 == num_it) {      // accumulator complete
+              if (CS == 1) umma_commit(&tmem_full[acc]);
+              else umma2_commit(&tmem_full[acc]);
+            }
           }
-          if (CS == 1) umma_commit(&empty_bar[st]);
-          else umma2_commit(&empty_bar[st]);
+          if (kUni) __syncwarp();
         }
-        if (CS == 1) umma_commit(&tmem_full[acc]);
-        else umma2_commit(&tmem_full[acc]);
         gtrace(tb, ti, 4);
         lt++;
       }
