@@ -152,7 +152,7 @@ void Engine::gemm(cudaStream_t st, const __half* A, int S, int T_alloc, int Kc, 
   }
   const int bi = bn == 64 ? 0 : (bn == 128 ? 1 : 2);
   // 2-CTA clusters with TMA multicast of the weight operand: big launches only (>= 2 row tiles per SM pair), compact list required
-  { extern long long* g_ffn_trace_ptr(); static const int tq = getenv("CV2_TRACE_QKV") != nullptr; p.trace = (tq ? p.q != nullptr : (p.res != nullptr && p.N == 256 && p.emit[0].kind != 0 && bn == 256 && p.ntaps == 1)) && g_ffn_trace_ptr() ? g_ffn_trace_ptr() + 8192 : nullptr; }
+  { extern long long* g_ffn_trace_ptr(); static const int tq = getenv("CV2_TRACE_QKV") != nullptr; static const int tc = getenv("CV2_TRACE_CONV") != nullptr; p.trace = (tc ? (p.ntaps == 3 && p.res != nullptr && bn == 256 && p.ln != 0) : tq ? p.q != nullptr : (p.res != nullptr && p.N == 256 && p.emit[0].kind != 0 && bn == 256 && p.ntaps == 1)) && g_ffn_trace_ptr() ? g_ffn_trace_ptr() + 8192 : nullptr; }
   { static const int dbg = getenv("CV2_DBG_SKIP_EPI") ? atoi(getenv("CV2_DBG_SKIP_EPI")) : 0; p.dbg_skip_epi = (dbg == 1) || (dbg == 2 && p.q != nullptr) || (dbg == 3 && p.res != nullptr); }
   if (cluster_mc && bn == 256 && p.tile_list && (long long)S * (T_alloc / 128) >= min_2sm_tiles) p.tmB_half = &wmap(w, 128);
   const CUtensorMap& tb = wmap(w, bn);

@@ -5,6 +5,6 @@ for v in "$@"; do
 import json,sys
 l=json.loads(sys.stdin.read().strip().splitlines()[-1])
 f=l['families']
-print('$v', 'value %.1f ms/step %.1f' % (l['value'], l['ms_per_step']), {k: round(f[k]['ms_per_step'],1) for k in ('flash_attn','ffn_fused','gemm_tap<256>','gemm_tap<128>','gemm_tap<64>')}, 'qkv %.1f' % l['gemm256_by_epilogue']['qkv_split']['ms_per_step'])
+print('$v', 'value %.1f ms/step %.1f' % (l['value'], l['ms_per_step']), {k: round(f[k]['ms_per_step'],1) for k in ('flash_attn','ffn_fused','gemm_tap<256>','gemm_tap<128>','gemm_tap<64>')}, 'qkv %.1f conv1 %.1f conv2 %.1f' % tuple(l['gemm256_by_epilogue'][k]['ms_per_step'] for k in ('qkv_split', 'conv+ln+mish+temb', 'conv+ln+mish+res+ln_emit')))
 "
 done
