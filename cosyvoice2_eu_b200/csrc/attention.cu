@@ -38,6 +38,25 @@ static constexpr int k9OffBar = k9OffV + k9Stages * kVBytes;
 static constexpr int k9Smem = k9OffBar + 128;
 static constexpr int k9Threads = 6 * 32;
 static constexpr uint32_t k9TmemS = 0, k9TmemO = 64;
+#ifndef CV2_ATTN_POLY_EVERY
+#define CV2_ATTN_POLY_EVERY 0
+#endif
+static constexpr int kPolyEvery = CV2_ATTN_POLY_EVERY;   // 0: all exponentials on the XU pipe; n: one pair of every n-th group of four on the FMA pipe
+
+// measurement aid (profiles/attn_trace.py), compiled in only with -DCV2_ATTN_TRACE: the kernel is sensitive to every register
+// (a run-time-null trace pointer alone cost 273 -> 347 us through 52 B of spills at the 80-register ceiling of four CTAs per SM)
+#ifdef CV2_ATTN_TRACE
+__device__ __forceinline__ void atrace(long long* tb, int& ti, int code) {
+  if (tb && ti < 2040) {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    tb[ti++] = (t << 8) | code;
+  }
+}
+#define ATRACE(code) atrace(tb, ti, code)
+#else
+#define ATRACE(code) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(k9Threads, 4)
 flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -67,6 +86,12 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // (trace: a CTA in the middle of the grid, so that its SM is shared with three others in steady state)
+#ifdef CV2_ATTN_TRACE
+  long long* tb = (p.trace && blockIdx.x == 2 && blockIdx.y == 3 && blockIdx.z == (unsigned)(p.S / 3) && lane == 0 && (warp == 0 || warp == 5))
+                      ? p.trace + (warp == 0 ? 0 : 2048) : nullptr;
+  int ti = 0;
+#endif
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -121,7 +146,9 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int j = 0; j < nkt; j++) {
       // K_{j+1} / V_{j+1} only depend on PV(j-1): polled here, outside the softmax -> PV -> S chain
       if (j + 1 < nkt) mbar_wait(&kv_full[(j + 1) % k9Stages], ((j + 1) / k9Stages) & 1);
+      ATRACE(20);
       mbar_wait(p_full, j & 1);   // softmax j has replaced S_j by P_j in tensor memory
+      ATRACE(21);
       tc_fence_after();
       const int st = j % k9Stages;
       const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(smem + k9OffV + st * kVBytes));
@@ -136,6 +163,7 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         umma_commit(&kv_empty[st]);
       }
       __syncwarp();
+      ATRACE(22);
     }
   } else {
     const int r = warp * 32 + lane;
@@ -149,7 +177,9 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     constexpr float kLazy = 13.f;
     float mref = 0.f, l = 0.f;     // reference max in log2 units
     for (int j = 0; j < nkt; j++) {
+      ATRACE(1);
       mbar_wait(s_full, j & 1);     // also implies PV(j-1) has completed (same in-order pipe, commit covers prior MMAs)
+      ATRACE(2);
       tc_fence_after();
       const int kbase = j * kKT;
       const bool edge = kbase + kKT > kv_lim;
@@ -175,6 +205,7 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
       const float mxl = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * LOG2E;
+      ATRACE(3);
       float alpha = 1.f;
       if (j == 0) {
         mref = mxl;
@@ -215,7 +246,9 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const float2 x01 = ffma2(make_float2(__uint_as_float(sa[i]), __uint_as_float(sa[i + 1])), sc2, nm2);
           const float2 x23 = ffma2(make_float2(__uint_as_float(sa[i + 2]), __uint_as_float(sa[i + 3])), sc2, nm2);
           const float2 e01 = make_float2(fast_exp2(x01.x), fast_exp2(x01.y));
-          const float2 e23 = make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
+          // every kPolyEvery-th group of four: the second pair on the FMA pipe (cubic, 1e-4 relative: below the 16-bit rounding of P)
+          const float2 e23 = (kPolyEvery > 0 && ((i >> 2) % (kPolyEvery > 0 ? kPolyEvery : 1)) == 0) ? poly_exp2_pair(x23)
+                                                                                                   : make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
           la = fadd2(la, e01);
           lb = fadd2(lb, e23);
           __half2 h0 = __floats2half2_rn(e01.x, e01.y), h1 = __floats2half2_rn(e23.x, e23.y);
@@ -225,10 +258,13 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_st16(lane_addr + k9TmemS + c * 16, pk);
       }
       l += (la.x + la.y) + (lb.x + lb.y);
+      ATRACE(4);
       tmem_st_wait();
+      ATRACE(5);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      ATRACE(6);
     }
     const float inv = l > 0.f ? 1.f / l : 0.f;
     mbar_wait(o_done, 0);
@@ -254,7 +290,12 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 5) tmem_dealloc<128>(tmem_base);
 }
 
-void launch_flash_attn(const AttnParams& p, cudaStream_t stream) {
+extern long long* g_ffn_trace_ptr();
+
+void launch_flash_attn(const AttnParams& p_in, cudaStream_t stream) {
+  AttnParams p = p_in;
+  static const bool tr = getenv("CV2_TRACE_ATTN") != nullptr;
+  p.trace = tr ? g_ffn_trace_ptr() : nullptr;
   CV2_CHECK(p.T_alloc % 128 == 0, "attention: T_alloc %d not a multiple of 128", p.T_alloc);
   static PerDeviceOnce once;
   once.run([] { CV2_CUDA(cudaFuncSetAttribute(flash_attn_v9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k9Smem)); });

@@ -16,6 +16,8 @@ struct AttnParams {
   int chunk;         // 0: every valid key visible; >0: key j visible to query i iff j < (i/chunk+1)*chunk
   int halo;
   int reverse_seq;   // dispatch sequences S-1 .. 0 (longest first for an ascending length-sorted batch)
+  long long* trace;  // measurement aid (profiles/attn_trace.py): one mid-grid CTA logs (clock64 << 8 | event) for its first softmax
+                     // warp [0, 2048) and its MMA warp [2048, 4096); null in production
   const int* lo;     // optional [S]: query tiles with t0 < floor(lo[s] / 128) * 128 are skipped (incremental streaming)
 };
 void launch_flash_attn(const AttnParams& p, cudaStream_t stream);
