@@ -254,6 +254,7 @@ void launch_nsf_source(const float* f0, int f0_stride, float* P, int T_alloc, co
 __constant__ float c_cos16[16];
 __constant__ float c_sin16[16];
 __constant__ float c_hann16[16];
+__constant__ float c_inv_env4[4];     // 1 / (sum of the squared window of the four frames covering a hop): interior hops of the iSTFT
 static PerDeviceOnce g_tables_once;   // __constant__ memory is per device
 static void upload_tables() {
   float c[16], s[16], w[16];
@@ -265,6 +266,13 @@ static void upload_tables() {
   CV2_CUDA(cudaMemcpyToSymbol(c_cos16, c, sizeof(c)));
   CV2_CUDA(cudaMemcpyToSymbol(c_sin16, s, sizeof(s)));
   CV2_CUDA(cudaMemcpyToSymbol(c_hann16, w, sizeof(w)));
+  float inv[4];
+  for (int i = 0; i < 4; i++) {
+    float e = 0.f;
+    for (int kp0 = 12; kp0 >= 0; kp0 -= 4) e = fmaf(w[kp0 + i], w[kp0 + i], e);   // the kernel's own order (df = -1 .. 2)
+    inv[i] = 1.f / e;
+  }
+  CV2_CUDA(cudaMemcpyToSymbol(c_inv_env4, inv, sizeof(inv)));
 }
 static void ensure_tables() { g_tables_once.run(upload_tables); }
 void hift_init_tables() { ensure_tables(); }
@@ -484,9 +492,14 @@ __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp
       const float mag = fminf(__expf(cv[k]), 100.f);
       const float ph = __sinf(cv[9 + k]);    // MUFU sine: abs error ~1e-6 on the conv_post phase logits (|x| of a few units),
                                              // six orders below the 35 dB parity budget; |ph| <= 1 for the sincos below
-      float sn, cs;
-      __sincosf(ph, &sn, &cs);
-      X[k] = make_float2(mag * cs, mag * sn);
+      // |ph| <= 1: sine and cosine as Taylor polynomials on the FMA pipe (packed pair; truncation error 2.8e-8 / 2.8e-7 at |ph| = 1)
+      // instead of two more MUFU ops per bin -- the kernel was bound by its 36 transcendentals per 72-byte frame
+      const float ph2 = ph * ph;
+      float2 sc = ffma2(make_float2(ph2, ph2), make_float2(2.7557319e-6f, 2.4801587e-5f), make_float2(-1.9841270e-4f, -1.3888889e-3f));
+      sc = ffma2(sc, make_float2(ph2, ph2), make_float2(8.3333333e-3f, 4.1666667e-2f));
+      sc = ffma2(sc, make_float2(ph2, ph2), make_float2(-1.6666667e-1f, -0.5f));
+      sc = ffma2(sc, make_float2(ph2, ph2), make_float2(1.f, 1.f));      // (sin(ph) / ph, cos(ph))
+      X[k] = make_float2(mag * sc.y, mag * (sc.x * ph));
     }
     // n = 0 and n = 8: only cosines (+-1)
     const float ev = X[2].x + X[4].x + X[6].x, od = X[1].x + X[3].x + X[5].x + X[7].x;
@@ -525,10 +538,17 @@ __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp
     for (int i = 0; i < 4; i++) env[i] = fmaf(c_hann16[kp0 + i], c_hann16[kp0 + i], env[i]);
   }
   float4 o;
-  o.x = fminf(fmaxf(acc.x / env[0], -0.99f), 0.99f);
-  o.y = fminf(fmaxf(acc.y / env[1], -0.99f), 0.99f);
-  o.z = fminf(fmaxf(acc.z / env[2], -0.99f), 0.99f);
-  o.w = fminf(fmaxf(acc.w / env[3], -0.99f), 0.99f);
+  if (q >= 1 && q + 2 < F) {   // all four frames present: the envelope is the same four numbers for every interior hop (no divisions)
+    o.x = fminf(fmaxf(acc.x * c_inv_env4[0], -0.99f), 0.99f);
+    o.y = fminf(fmaxf(acc.y * c_inv_env4[1], -0.99f), 0.99f);
+    o.z = fminf(fmaxf(acc.z * c_inv_env4[2], -0.99f), 0.99f);
+    o.w = fminf(fmaxf(acc.w * c_inv_env4[3], -0.99f), 0.99f);
+  } else {
+    o.x = fminf(fmaxf(acc.x / env[0], -0.99f), 0.99f);
+    o.y = fminf(fmaxf(acc.y / env[1], -0.99f), 0.99f);
+    o.z = fminf(fmaxf(acc.z / env[2], -0.99f), 0.99f);
+    o.w = fminf(fmaxf(acc.w / env[3], -0.99f), 0.99f);
+  }
   *reinterpret_cast<float4*>(wav + (long long)b * wav_bstride + 4 * (long long)q) = o;
   if (pcm) {   // the servers' wire format: (speech * 2**15).astype(int16), i.e. truncation toward zero (fastapi/server.py:42)
     short4 s4;
