@@ -382,14 +382,33 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int lt = 0;
     long long* tb = (p.trace && blockIdx.x == 0 && (warp == 0 || warp == 13) && lane == 0) ? p.trace + (warp == 0 ? 0 : 2048) : nullptr;
     int ti = 0;
+    // Tile coordinates come from two dependent global loads (tile list entry, then the sequence length): ~1.5 k cycles of latency
+    // that used to sit between two tiles of an epilogue group (clock64 trace of the QKV GEMM).  With a compact tile list every
+    // unit is a tile, so (i) the other group's tiles are skipped without loading anything and (ii) the coordinates of this group's
+    // NEXT tile are fetched while the current tile's epilogue runs.
+    TileCoord c_pref;
+    bool tv_pref = false, have_pref = false;
+    const int pref_step = unit_step * (p.tile_list ? kGroups : 1);
     for (int tile = unit0; tile < total_tiles; tile += unit_step) {
-      TileCoord c;
-      bool tvalid;
-      if (!tile_coord<CS>(p, tile, n_tiles, t_tiles, BN, rank, row_count, c, tvalid)) continue;
-      if (kGroups > 1 && (lt & 1) != grp) {   // the other group's tile
+      if (p.tile_list && kGroups > 1 && (lt & 1) != grp) {   // the other group's tile (compact list: every unit counts)
         lt++;
         continue;
       }
+      TileCoord c;
+      bool tvalid;
+      if (have_pref) {
+        c = c_pref;
+        tvalid = tv_pref;
+        have_pref = false;
+      } else if (!tile_coord<CS>(p, tile, n_tiles, t_tiles, BN, rank, row_count, c, tvalid)) {
+        continue;
+      }
+      if (!p.tile_list && kGroups > 1 && (lt & 1) != grp) {   // the other group's tile
+        lt++;
+        continue;
+      }
+      if (p.tile_list && tile + pref_step < total_tiles)
+        have_pref = tile_coord<CS>(p, tile + pref_step, n_tiles, t_tiles, BN, rank, row_count, c_pref, tv_pref);
       if (CS > 1 && !tvalid) {   // filler tile of an odd tail: drain the accumulator, store nothing
         mbar_wait(&tmem_full[lt & 1], (lt >> 1) & 1);
         tc_fence_after();
