@@ -480,6 +480,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
 
       float sum2 = 0.f, sq2 = 0.f;
+      bool released = false;   // (warp-uniform: all lanes of a warp own the same columns)
       const float* rv = has_rv ? p.rowvec + (long long)c.s * p.rowvec_ld : nullptr;
 #pragma unroll 1
       for (int ch = 0; ch < kChunks; ch++) {
@@ -492,6 +493,17 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         float tmp[32];
         if (has_bias) vload(vec_bias, c_bias, p.bias, cbase, tmp, full, nv);
         tmem_ld_wait();
+        if (!stat2 && (ch == kChunks - 1 || cl + 32 >= ncols)) {
+          released = true;
+          // last read of this accumulator (no LayerNorm-emit sweep follows): hand it back to the MMA warp NOW, not after this chunk's
+          // math and stores have drained -- the next tile's MMAs then overlap them (QKV trace: ~1.3 k cycles per tile)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CS == 1) mbar_arrive(&tmem_empty[acc]);
+            else mbar_arrive_leader(&tmem_empty[acc]);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]);
         gtrace(tb, ti, 12, v[0] + tmp[0]);
@@ -693,12 +705,13 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
       gtrace(tb, ti, 20);
-      // release this accumulator buffer to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CS == 1) mbar_arrive(&tmem_empty[acc]);
-        else mbar_arrive_leader(&tmem_empty[acc]);
+      if (stat2 || !released) {   // (otherwise released right after the last accumulator read, see the chunk loop)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CS == 1) mbar_arrive(&tmem_empty[acc]);
+          else mbar_arrive_leader(&tmem_empty[acc]);
+        }
       }
       lt++;
     }
