@@ -685,6 +685,15 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int cbase = c.n0 + cl;
           tmem_ld32(taddr + ch * 32, raw);
           tmem_ld_wait();
+          if (ch == kChunks - 1 || cl + 32 >= ncols) {   // last read of the accumulator: release it before this chunk's math and stores
+            released = true;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CS == 1) mbar_arrive(&tmem_empty[acc]);
+              else mbar_arrive_leader(&tmem_empty[acc]);
+            }
+          }
 #pragma unroll
           for (int e = 0; e < 3; e++) {
             const Emit& em = p.emit[e];
@@ -705,7 +714,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
       gtrace(tb, ti, 20);
-      if (stat2 || !released) {   // (otherwise released right after the last accumulator read, see the chunk loop)
+      if (!released) {   // (normally released right after the last accumulator read, see the chunk loops)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
