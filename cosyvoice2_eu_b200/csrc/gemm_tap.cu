@@ -448,6 +448,62 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         continue;
       }
 
+      if constexpr (Cfg::QKV == 1 && Cfg::BIAS == 0 && Cfg::LN == 0 && Cfg::ACT == 0 && BN == 256) {
+        // q / k / v^T split of the estimator blocks (nothing but the split): software-pipelined over the four 32-column chunks.  The
+        // tensor-memory read of chunk c+1 is in flight while chunk c is converted, and the accumulator goes back to the MMA warp as
+        // soon as the LAST chunk has been read -- before the stores of chunks 2 and 3 -- so the next tile's MMAs overlap them.
+        if (!p.q2) {
+          const int hd = p.heads * 64;
+          const int cb0 = c.n0 + my_c0;                 // first global column of this thread's 128
+          const int which = cb0 / hd;                   // 0 q, 1 k, 2 v (hd is a multiple of 128: the thread's columns never straddle)
+          const int cc0 = cb0 - which * hd;
+          const float sc = valid ? (which == 0 ? p.q_scale : 1.f) : 0.f;
+          uint32_t rawq[32], pk[16];
+          tmem_ld32(taddr, rawq);
+          tmem_ld_wait();
+#pragma unroll
+          for (int ch = 0; ch < kChunks; ch++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+              __half2 h2 = __floats2half2_rn(__uint_as_float(rawq[2 * i]) * sc, __uint_as_float(rawq[2 * i + 1]) * sc);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            if (ch + 1 < kChunks) {
+              tmem_ld32(taddr + (ch + 1) * 32, rawq);
+              tmem_ld_wait();
+              if (ch + 2 == kChunks) {   // that was the last read of this accumulator
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if (CS == 1) mbar_arrive(&tmem_empty[acc]);
+                  else mbar_arrive_leader(&tmem_empty[acc]);
+                }
+              }
+            }
+            const int cc = cc0 + ch * 32;
+            const int h = cc >> 6, d0 = cc & 63;
+            gtrace(tb, ti, 30 + which);
+            if (which < 2) {   // q / k: row-major per head; lane-pair transposed 256-bit stores (tile_store_f16 on packed data)
+              __half* g0 = (which == 0 ? p.q : p.k) + (((long long)c.s * p.heads + h) * p.T_alloc + (t - lane)) * 64 + d0;
+              lane_group_transpose<8, 1>(pk, lane);
+              __half* pp = g0 + (lane & ~1) * 64 + (lane & 1) * 16;
+              stg256(pp, pk);
+              stg256(pp + 64, pk + 8);
+            } else {           // v: transposed per head, one 2-byte store per (lane = t, d)
+              __half* dst = p.vt + (((long long)c.s * p.heads + h) * 64 + d0) * p.T_alloc + t;
+#pragma unroll
+              for (int i = 0; i < 16; i++) {
+                const uint32_t u = pk[i];
+                dst[(long long)(2 * i) * p.T_alloc] = __ushort_as_half((unsigned short)(u & 0xffffu));
+                dst[(long long)(2 * i + 1) * p.T_alloc] = __ushort_as_half((unsigned short)(u >> 16));
+              }
+            }
+          }
+          gtrace(tb, ti, 20);
+          lt++;
+          continue;
+        }
+      }
       float mean = 0.f, rstd = 1.f;
       uint32_t raw[32];
       float v[32];
