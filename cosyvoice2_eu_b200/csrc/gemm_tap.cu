@@ -489,14 +489,20 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               __half* pp = g0 + (lane & ~1) * 64 + (lane & 1) * 16;
               stg256(pp, pk);
               stg256(pp + 64, pk + 8);
-            } else {           // v: transposed per head, one 2-byte store per (lane = t, d)
-              __half* dst = p.vt + (((long long)c.s * p.heads + h) * 64 + d0) * p.T_alloc + t;
+            } else {           // v: transposed per head.  Lane pairs exchange so that every lane holds (t, t+1) for 16 of the 32 d rows
+                               // of the chunk: 16 four-byte stores per lane instead of 32 two-byte ones (the epilogue is issue bound)
+              const bool odd = lane & 1;
+              uint32_t out[16];
 #pragma unroll
               for (int i = 0; i < 16; i++) {
-                const uint32_t u = pk[i];
-                dst[(long long)(2 * i) * p.T_alloc] = __ushort_as_half((unsigned short)(u & 0xffffu));
-                dst[(long long)(2 * i + 1) * p.T_alloc] = __ushort_as_half((unsigned short)(u >> 16));
+                // pk[i] = (d = 2i, d = 2i+1) of row t.  Even lane keeps d = 2i of both rows, odd lane d = 2i+1.
+                const uint32_t other = __shfl_xor_sync(0xffffffffu, pk[i], 1);
+                const uint32_t lo = odd ? other : pk[i], hi = odd ? pk[i] : other;      // lo: row t_even, hi: row t_even + 1
+                out[i] = odd ? __byte_perm(lo, hi, 0x7632) : __byte_perm(lo, hi, 0x5410);
               }
+              __half* dst = p.vt + (((long long)c.s * p.heads + h) * 64 + d0 + (odd ? 1 : 0)) * p.T_alloc + (t & ~1);
+#pragma unroll
+              for (int i = 0; i < 16; i++) *reinterpret_cast<uint32_t*>(dst + (long long)(2 * i) * p.T_alloc) = out[i];
             }
           }
           gtrace(tb, ti, 20);
