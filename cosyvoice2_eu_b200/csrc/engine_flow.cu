@@ -143,9 +143,9 @@ static void est_core(Engine& e, cudaStream_t st, const EstBuffers& b, const __ha
         k16 = es->ss->kcache + blk;
         vt16 = es->ss->vcache + blk;
       }
-      {  // q,k,v (no bias); q pre-scaled by 1/sqrt(64)
+      {  // q,k,v (no bias); q pre-scaled by 1/sqrt(64) through its weights
         GemmParams p = base_params(lens, kEstHalo);
-        p.q = b.Q16; p.k = k16; p.vt = vt16; p.heads = 8; p.q_scale = 0.125f;
+        p.q = b.Q16; p.k = k16; p.vt = vt16; p.heads = 8; p.q_scale = 1.f;   // (1/sqrt(64) is folded into the packed q weights, pack.py)
         e.gemm(st, b.H16, S, T, 256, 256, e.W(tp + ".qkv"), 256, 1, tap1, p, dry);
       }
       {

@@ -458,15 +458,24 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int which = cb0 / hd;                   // 0 q, 1 k, 2 v (hd is a multiple of 128: the thread's columns never straddle)
           const int cc0 = cb0 - which * hd;
           const float sc = valid ? (which == 0 ? p.q_scale : 1.f) : 0.f;
+          const bool plain = __all_sync(0xffffffffu, sc == 1.f);   // all 32 rows valid and unscaled (the usual case): no multiplies
           uint32_t rawq[32], pk[16];
           tmem_ld32(taddr, rawq);
           tmem_ld_wait();
 #pragma unroll
           for (int ch = 0; ch < kChunks; ch++) {
+            if (plain) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-              __half2 h2 = __floats2half2_rn(__uint_as_float(rawq[2 * i]) * sc, __uint_as_float(rawq[2 * i + 1]) * sc);
-              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+              for (int i = 0; i < 16; i++) {
+                __half2 h2 = __floats2half2_rn(__uint_as_float(rawq[2 * i]), __uint_as_float(rawq[2 * i + 1]));
+                pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; i++) {
+                __half2 h2 = __floats2half2_rn(__uint_as_float(rawq[2 * i]) * sc, __uint_as_float(rawq[2 * i + 1]) * sc);
+                pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+              }
             }
             if (ch + 1 < kChunks) {
               tmem_ld32(taddr + (ch + 1) * 32, rawq);

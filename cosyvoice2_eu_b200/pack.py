@@ -115,7 +115,9 @@ def pack_flow(sd):
             s, d = f"{e}{g}.1.{j}", f"est.tfm.{r}.{j}"
             o[d + ".ln1_g"] = _f32(sd[s + ".norm1.weight"])
             o[d + ".ln1_b"] = _f32(sd[s + ".norm1.bias"])
-            o[d + ".qkv.w"] = _lin_w(torch.cat([sd[s + ".attn1.to_q.weight"], sd[s + ".attn1.to_k.weight"], sd[s + ".attn1.to_v.weight"]], 0))
+            # the 1/sqrt(64) of the attention scores is folded into the q rows (a power of two: exact), so the QKV epilogue -- which is
+            # issue bound -- does not multiply
+            o[d + ".qkv.w"] = _lin_w(torch.cat([sd[s + ".attn1.to_q.weight"] * 0.125, sd[s + ".attn1.to_k.weight"], sd[s + ".attn1.to_v.weight"]], 0))
             o[d + ".o.w"] = _lin_w(sd[s + ".attn1.to_out.0.weight"])
             o[d + ".o.b"] = _f32(sd[s + ".attn1.to_out.0.bias"])
             o[d + ".ln3_g"] = _f32(sd[s + ".norm3.weight"])
