@@ -183,6 +183,41 @@ def test_flash_attention(chunk):
     assert err < 5e-3, err
 
 
+@pytest.mark.parametrize("chunk", [0, 50])
+def test_flash_attention_long_ragged_and_lazy_rescale(chunk):
+    """The estimator attention at the bench's tile count (T_alloc = 1152: 9 query tiles, 18 key tiles) with edge lengths (1, one key
+    tile +- 1, a full allocation) and with logits that GROW along the keys, so that the running reference maximum has to be raised
+    -- the lazy rescale (threshold 2^13, attention.cu) and its O / l rescaling are otherwise almost never taken by random data."""
+    lib, L = _lib()
+    g = torch.Generator().manual_seed(5)
+    S, H, T, D = 7, 8, 1152, 64
+    lens = torch.tensor([1152, 1151, 1, 64, 65, 129, 700], dtype=torch.int32)
+    q = (torch.randn(S, H, T, D, generator=g) * 0.25).half()
+    k = (torch.randn(S, H, T, D, generator=g) * 2).half()
+    v = torch.randn(S, H, T, D, generator=g).half()
+    # sequences 0 and 6: keys aligned with the queries and growing with the key index: scores climb by ~60 nats over the sequence
+    ramp = torch.linspace(0.0, 6.0, T)[None, :, None]
+    for s_ in (0, 6):
+        base = torch.randn(H, 1, D, generator=g)
+        base = base / base.norm(dim=-1, keepdim=True)
+        q[s_] = (base * 2.5 + torch.randn(H, T, D, generator=g) * 0.05).half()
+        k[s_] = (base * 4.0 * ramp + torch.randn(H, T, D, generator=g) * 0.5).half()
+    ref = _attn_ref(q, k, v, lens, chunk)
+    qd, kd = q.cuda(), k.cuda()
+    vtd = v.transpose(2, 3).contiguous().cuda()
+    out = torch.zeros(S, T, H * D, dtype=torch.float16, device="cuda")
+    lens_d = lens.cuda()
+    lib.check(L.cv2_op_flash_attn(_s(), lib.ptr(qd), lib.ptr(kd), lib.ptr(vtd), lib.ptr(out), lib.ptr(lens_d), 0, S, H, T, chunk))
+    torch.cuda.synchronize()
+    o = out.float().cpu()
+    assert bool(torch.isfinite(o).all())
+    for s_ in range(S):
+        n = int(lens[s_])
+        err = float((o[s_, :n] - ref[s_, :n]).abs().max())
+        assert err < 8e-3, (s_, n, err)
+        assert float(o[s_, n:].abs().max()) == 0.0 if n < T else True
+
+
 @pytest.mark.parametrize("chunk,T,Tal,len1", [(0, 100, 128, 61), (25, 100, 128, 61), (0, 300, 384, 170), (50, 300, 384, 257)])
 def test_rel_attention(chunk, T, Tal, len1):
     import token2wav_oracle as O
