@@ -38,10 +38,6 @@ static constexpr int k9OffBar = k9OffV + k9Stages * kVBytes;
 static constexpr int k9Smem = k9OffBar + 128;
 static constexpr int k9Threads = 6 * 32;
 static constexpr uint32_t k9TmemS = 0, k9TmemO = 64;
-#ifndef CV2_ATTN_POLY_EVERY
-#define CV2_ATTN_POLY_EVERY 0
-#endif
-static constexpr int kPolyEvery = CV2_ATTN_POLY_EVERY;   // 0: all exponentials on the XU pipe; n: one pair of every n-th group of four on the FMA pipe
 
 // measurement aid (profiles/attn_trace.py), compiled in only with -DCV2_ATTN_TRACE: the kernel is sensitive to every register
 // (a run-time-null trace pointer alone cost 273 -> 347 us through 52 B of spills at the 80-register ceiling of four CTAs per SM)
@@ -246,9 +242,9 @@ flash_attn_v9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const float2 x01 = ffma2(make_float2(__uint_as_float(sa[i]), __uint_as_float(sa[i + 1])), sc2, nm2);
           const float2 x23 = ffma2(make_float2(__uint_as_float(sa[i + 2]), __uint_as_float(sa[i + 3])), sc2, nm2);
           const float2 e01 = make_float2(fast_exp2(x01.x), fast_exp2(x01.y));
-          // every kPolyEvery-th group of four: the second pair on the FMA pipe (cubic, 1e-4 relative: below the 16-bit rounding of P)
-          const float2 e23 = (kPolyEvery > 0 && ((i >> 2) % (kPolyEvery > 0 ? kPolyEvery : 1)) == 0) ? poly_exp2_pair(x23)
-                                                                                                   : make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
+          // (one pair of every 2nd / 4th group on the FMA pipe instead -- a cubic 2^x -- measured 276.2 / 274.5 against 273.5 us: the
+          // exponentials do not bound this kernel, profiles/README.md)
+          const float2 e23 = make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
           la = fadd2(la, e01);
           lb = fadd2(lb, e23);
           __half2 h0 = __floats2half2_rn(e01.x, e01.y), h1 = __floats2half2_rn(e23.x, e23.y);

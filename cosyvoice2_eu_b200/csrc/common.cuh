@@ -331,37 +331,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x on the FMA / ALU pipes (no MUFU): Cody-Waite split with the round-down magic add, cubic minimax for 2^f on [0,1)
-// (max relative error 1.03e-4, below the 16-bit rounding of the probabilities it feeds), exponent spliced in with one
-// shift-add.  x <= ~120; anything below -126 flushes to (almost) zero.
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -126.f);
-  float t;
-  asm("add.rm.ftz.f32 %0, %1, 0f4B400000;" : "=f"(t) : "f"(x));   // 2^23 + 2^22: floor(x) lands in the low mantissa bits
-  const float fl = t - 12582912.f;
-  const float f = x - fl;
-  float p = fmaf(f, 0.07826797f, 0.22630768f);
-  p = fmaf(p, f, 0.69542435f);
-  p = fmaf(p, f, 1.0f);
-  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
-}
-// the same on a packed pair (FADD2.RM / FFMA2: half the FMA-pipe issue slots); profiles/micro/softmax_pipes.cu
-__device__ __forceinline__ float2 poly_exp2_pair(float2 x) {
-  x.x = fmaxf(x.x, -126.f);
-  x.y = fmaxf(x.y, -126.f);
-  const float2 magic = make_float2(12582912.f, 12582912.f);
-  float2 t;
-  asm("add.rm.ftz.f32x2 %0, %1, %2;"
-      : "=l"(*reinterpret_cast<unsigned long long*>(&t))
-      : "l"(*reinterpret_cast<unsigned long long*>(&x)), "l"(*reinterpret_cast<const unsigned long long*>(&magic)));
-  const float2 fl = fadd2(t, make_float2(-12582912.f, -12582912.f));
-  const float2 f = ffma2(fl, make_float2(-1.f, -1.f), x);
-  float2 p = ffma2(f, make_float2(0.07826797f, 0.07826797f), make_float2(0.22630768f, 0.22630768f));
-  p = ffma2(p, f, make_float2(0.69542435f, 0.69542435f));
-  p = ffma2(p, f, make_float2(1.f, 1.f));
-  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23)),
-                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23)));
-}
 __device__ __forceinline__ float mish_f(float x) {
   // x * tanh(softplus(x)); softplus with PyTorch's threshold 20
   float sp = x > 20.f ? x : log1pf(__expf(x));
